@@ -1,0 +1,244 @@
+"""ctypes binding of ``libgecco_crf_b200.so`` (C ABI: ``include/gecco_crf_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or no B200 is visible, the calls
+raise.  The CPU oracle under ``oracle/`` is test infrastructure and is never imported from here.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import pathlib
+from typing import Optional
+
+import numpy
+
+from .model_io import CRFWeights
+
+__all__ = ["CRFEngine", "GcrfError", "load_library", "library_path", "EXPORTED_SYMBOLS"]
+
+GCRF_FLAG_DEVICE_PTRS = 0x1
+GCRF_FLAG_OUT_F32 = 0x2
+GCRF_FLAG_PTR64 = 0x4
+
+# every symbol include/gecco_crf_b200.h declares (tests/test_abi.py checks the header against this)
+EXPORTED_SYMBOLS = (
+    "gcrf_version",
+    "gcrf_last_error",
+    "gcrf_device_count",
+    "gcrf_model_create",
+    "gcrf_model_destroy",
+    "gcrf_model_set_stream",
+    "gcrf_model_synchronize",
+    "gcrf_marginals_windowed",
+    "gcrf_marginals_chain",
+    "gcrf_host_alloc",
+    "gcrf_host_free",
+    "gcrf_model_launch_count",
+    "gcrf_model_last_kernel_ms",
+)
+
+_STATUS = {0: "GCRF_OK", -1: "GCRF_EINVAL", -2: "GCRF_ENODEVICE", -3: "GCRF_ECUDA", -4: "GCRF_ENOMEM",
+           -5: "GCRF_EUNSUPPORTED"}
+
+
+class GcrfError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{_STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+def library_path() -> pathlib.Path:
+    return pathlib.Path(__file__).resolve().parent / "libgecco_crf_b200.so"
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it was not built (``python -c "import __graft_entry__ as g; g.build()"``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} is missing: build it with `make -C gecco_b200/csrc` (or __graft_entry__.build()); "
+            "gecco_b200 has no CPU fallback"
+        )
+    lib = ctypes.CDLL(str(path))
+    vp, i32, i64, u32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
+    lib.gcrf_version.restype = ctypes.c_int
+    lib.gcrf_version.argtypes = []
+    lib.gcrf_last_error.restype = ctypes.c_char_p
+    lib.gcrf_last_error.argtypes = []
+    lib.gcrf_device_count.restype = ctypes.c_int
+    lib.gcrf_device_count.argtypes = []
+    lib.gcrf_model_create.restype = ctypes.c_int
+    lib.gcrf_model_create.argtypes = [vp, i32, i32, vp, i32, i32, ctypes.POINTER(vp)]
+    lib.gcrf_model_destroy.restype = None
+    lib.gcrf_model_destroy.argtypes = [vp]
+    lib.gcrf_model_set_stream.restype = ctypes.c_int
+    lib.gcrf_model_set_stream.argtypes = [vp, vp]
+    lib.gcrf_model_synchronize.restype = ctypes.c_int
+    lib.gcrf_model_synchronize.argtypes = [vp]
+    lib.gcrf_marginals_windowed.restype = ctypes.c_int
+    lib.gcrf_marginals_windowed.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, u32]
+    lib.gcrf_marginals_chain.restype = ctypes.c_int
+    lib.gcrf_marginals_chain.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp, u32]
+    lib.gcrf_host_alloc.restype = ctypes.c_int
+    lib.gcrf_host_alloc.argtypes = [ctypes.POINTER(vp), u64]
+    lib.gcrf_host_free.restype = ctypes.c_int
+    lib.gcrf_host_free.argtypes = [vp]
+    lib.gcrf_model_launch_count.restype = i64
+    lib.gcrf_model_launch_count.argtypes = [vp]
+    lib.gcrf_model_last_kernel_ms.restype = ctypes.c_double
+    lib.gcrf_model_last_kernel_ms.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _check(lib: ctypes.CDLL, status: int) -> None:
+    if status != 0:
+        raise GcrfError(status, lib.gcrf_last_error().decode("utf-8", "replace"))
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from ``gcrf_host_alloc``."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        self.dtype = numpy.dtype(dtype)
+        n = int(numpy.prod(shape))
+        ptr = ctypes.c_void_p()
+        _check(self._lib, self._lib.gcrf_host_alloc(ctypes.byref(ptr), max(1, n * self.dtype.itemsize)))
+        self._ptr = ptr
+        buf = (ctypes.c_char * max(1, n * self.dtype.itemsize)).from_address(ptr.value)
+        self.array = numpy.frombuffer(buf, dtype=self.dtype, count=n).reshape(shape)
+
+    def free(self) -> None:
+        if self._ptr is not None:
+            self.array = None
+            self._lib.gcrf_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CRFEngine:
+    """One model handle on one B200 (``gcrf_model``).  Not thread-safe; use one engine per thread/device."""
+
+    def __init__(self, weights: CRFWeights, device: int = 0, positive_label: str = "1"):
+        self._lib = load_library()
+        self.weights = weights
+        self.device = int(device)
+        state_w = numpy.ascontiguousarray(weights.state_w, dtype=numpy.float64)
+        trans_w = numpy.ascontiguousarray(weights.trans_w, dtype=numpy.float64)
+        A, L = state_w.shape
+        # gecco/crf/__init__.py:253 asks the tagger for p['1']: resolve the label id by name
+        pos = weights.label_id(positive_label)
+        handle = ctypes.c_void_p()
+        _check(self._lib, self._lib.gcrf_model_create(state_w.ctypes.data, A, L, trans_w.ctypes.data, pos,
+                                                     self.device, ctypes.byref(handle)))
+        self._handle = handle
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None:
+            self._lib.gcrf_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _host_csr(contig_ptr, gene_ptr, attr_idx):
+        contig_ptr = numpy.ascontiguousarray(contig_ptr, dtype=numpy.int32)
+        gene_ptr = numpy.asarray(gene_ptr)
+        if gene_ptr.dtype == numpy.int64 and (gene_ptr.size == 0 or int(gene_ptr[-1]) > 0x7FFFFFFF):
+            gene_ptr = numpy.ascontiguousarray(gene_ptr, dtype=numpy.int64)
+            flags = GCRF_FLAG_PTR64
+        else:
+            gene_ptr = numpy.ascontiguousarray(gene_ptr, dtype=numpy.int32)
+            flags = 0
+        attr_idx = numpy.ascontiguousarray(attr_idx, dtype=numpy.int32)
+        return contig_ptr, gene_ptr, attr_idx, flags
+
+    # ------------------------------------------------------------------ host-pointer calls
+    def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window: Optional[int] = None,
+                           step: Optional[int] = None, pad: bool = True, out: Optional[numpy.ndarray] = None,
+                           f32: bool = False) -> numpy.ndarray:
+        """Per-gene cluster probability (``gcrf_marginals_windowed``, host buffers, blocking)."""
+        contig_ptr, gene_ptr, attr_idx, flags = self._host_csr(contig_ptr, gene_ptr, attr_idx)
+        C, G, nnz = len(contig_ptr) - 1, len(gene_ptr) - 1, len(attr_idx)
+        dtype = numpy.float32 if f32 else numpy.float64
+        if out is None:
+            out = numpy.empty(G, dtype=dtype)
+        elif out.dtype != dtype or out.size != G or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous array of G elements of the requested dtype")
+        if f32:
+            flags |= GCRF_FLAG_OUT_F32
+        window = self.weights.window_size if window is None else window
+        step = self.weights.window_step if step is None else step
+        _check(self._lib, self._lib.gcrf_marginals_windowed(
+            self._handle, contig_ptr.ctypes.data, gene_ptr.ctypes.data, attr_idx.ctypes.data if nnz else None,
+            C, G, nnz, int(window), int(step), int(bool(pad)), out.ctypes.data if G else None, flags))
+        return out
+
+    def marginals_chain(self, contig_ptr, gene_ptr, attr_idx, *, out: Optional[numpy.ndarray] = None,
+                        f32: bool = False) -> numpy.ndarray:
+        """Whole-contig marginals (``gcrf_marginals_chain``): one chain per contig, no windows."""
+        contig_ptr, gene_ptr, attr_idx, flags = self._host_csr(contig_ptr, gene_ptr, attr_idx)
+        C, G, nnz = len(contig_ptr) - 1, len(gene_ptr) - 1, len(attr_idx)
+        dtype = numpy.float32 if f32 else numpy.float64
+        if out is None:
+            out = numpy.empty(G, dtype=dtype)
+        if f32:
+            flags |= GCRF_FLAG_OUT_F32
+        _check(self._lib, self._lib.gcrf_marginals_chain(
+            self._handle, contig_ptr.ctypes.data, gene_ptr.ctypes.data, attr_idx.ctypes.data if nnz else None,
+            C, G, nnz, out.ctypes.data if G else None, flags))
+        return out
+
+    # ------------------------------------------------------------------ device-pointer calls
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run later calls on the given ``cudaStream_t`` (an int; ``None`` = the engine's own stream)."""
+        _check(self._lib, self._lib.gcrf_model_set_stream(self._handle, ctypes.c_void_p(cuda_stream or 0)))
+
+    def marginals_windowed_device(self, contig_ptr: int, gene_ptr: int, attr_idx: int, C: int, G: int, nnz: int,
+                                  out: int, *, window: Optional[int] = None, step: Optional[int] = None,
+                                  pad: bool = True, f32: bool = False, ptr64: bool = False) -> None:
+        """Enqueue on device-resident arrays given as raw device addresses; returns without syncing."""
+        flags = GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_OUT_F32 if f32 else 0) | (GCRF_FLAG_PTR64 if ptr64 else 0)
+        window = self.weights.window_size if window is None else window
+        step = self.weights.window_step if step is None else step
+        _check(self._lib, self._lib.gcrf_marginals_windowed(
+            self._handle, contig_ptr, gene_ptr, attr_idx, C, G, nnz, int(window), int(step), int(bool(pad)), out, flags))
+
+    def marginals_chain_device(self, contig_ptr: int, gene_ptr: int, attr_idx: int, C: int, G: int, nnz: int,
+                               out: int, *, f32: bool = False, ptr64: bool = False) -> None:
+        flags = GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_OUT_F32 if f32 else 0) | (GCRF_FLAG_PTR64 if ptr64 else 0)
+        _check(self._lib, self._lib.gcrf_marginals_chain(self._handle, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags))
+
+    def synchronize(self) -> None:
+        _check(self._lib, self._lib.gcrf_model_synchronize(self._handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gcrf_model_launch_count(self._handle))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.gcrf_model_last_kernel_ms(self._handle))

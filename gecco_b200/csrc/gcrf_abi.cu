@@ -1,0 +1,380 @@
+// gcrf_abi.cu — the extern "C" surface declared in include/gecco_crf_b200.h.
+// Owns the model handle (device weight table, stream, grow-only staging buffers) and turns the
+// host- or device-pointer CSR batch into kernel launches.  No CPU fallback exists on purpose.
+#include "../../include/gecco_crf_b200.h"
+#include "gcrf_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t err, const char *what) {
+    const int code = (err == cudaErrorMemoryAllocation) ? GCRF_ENOMEM : GCRF_ECUDA;
+    return fail(code, "%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+}
+
+#define GCRF_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t err__ = (call);                            \
+        if (err__ != cudaSuccess) return fail_cuda(err__, #call); \
+    } while (0)
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;  // slack so slightly larger batches do not reallocate
+        cudaError_t err = cudaMalloc(&ptr, want);
+        if (err != cudaSuccess) {
+            want = bytes;
+            err = cudaMalloc(&ptr, want);
+        }
+        if (err == cudaSuccess) cap = want;
+        return err;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct gcrf_model {
+    int device = 0;
+    int num_sms = 0;
+    int32_t A = 0;
+    gcrf::ModelDev dev{};
+    float *d_table = nullptr;
+    double *d_table64 = nullptr;
+    double m01 = 0, m10 = 0, m11 = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+    DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Host-side sanity checks of a CSR batch given as host pointers (cheap, O(C)).
+int check_host_csr(const int32_t *contig_ptr, const void *gene_ptr, bool ptr64, int64_t C, int64_t G, int64_t nnz) {
+    if (contig_ptr[0] != 0 || contig_ptr[C] != G) return fail(GCRF_EINVAL, "contig_ptr must start at 0 and end at G");
+    for (int64_t c = 0; c < C; ++c)
+        if (contig_ptr[c + 1] <= contig_ptr[c]) return fail(GCRF_EINVAL, "contig_ptr must be strictly increasing (contig %lld is empty)", (long long)c);
+    const int64_t first = ptr64 ? static_cast<const int64_t *>(gene_ptr)[0] : static_cast<const int32_t *>(gene_ptr)[0];
+    const int64_t last = ptr64 ? static_cast<const int64_t *>(gene_ptr)[G] : static_cast<const int32_t *>(gene_ptr)[G];
+    if (first != 0 || last != nnz) return fail(GCRF_EINVAL, "gene_ptr must start at 0 and end at nnz");
+    return GCRF_OK;
+}
+
+struct Batch {
+    gcrf::CsrDev csr{};
+    void *d_out = nullptr;
+    size_t out_bytes = 0;
+    bool device_ptrs = false;
+};
+
+// Validates the common arguments and, in host-pointer mode, stages the inputs on the device.
+int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx,
+                int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags, Batch *b) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (C < 0 || G < 0 || nnz < 0) return fail(GCRF_EINVAL, "negative size");
+    if (G > 0x7fffffff - 1024) return fail(GCRF_EINVAL, "G must fit in int32 (shard the batch)");
+    if ((C == 0) != (G == 0)) return fail(GCRF_EINVAL, "C and G must both be zero or both be positive");
+    if (C > G) return fail(GCRF_EINVAL, "more contigs than genes");
+    if (G > 0 && (!contig_ptr || !gene_ptr || !out)) return fail(GCRF_EINVAL, "NULL array");
+    if (nnz > 0 && !attr_idx) return fail(GCRF_EINVAL, "attr_idx is NULL");
+    const bool ptr64 = (flags & GCRF_FLAG_PTR64) != 0;
+    if (!ptr64 && nnz > 0x7fffffff) return fail(GCRF_EINVAL, "nnz >= 2^31 needs GCRF_FLAG_PTR64");
+    b->device_ptrs = (flags & GCRF_FLAG_DEVICE_PTRS) != 0;
+    b->out_bytes = (size_t)G * ((flags & GCRF_FLAG_OUT_F32) ? sizeof(float) : sizeof(double));
+    b->csr.C = C;
+    b->csr.G = G;
+    b->csr.nnz = nnz;
+    if (G == 0) return GCRF_OK;
+
+    if (b->device_ptrs) {
+        if ((reinterpret_cast<uintptr_t>(attr_idx) & 15u) != 0)
+            return fail(GCRF_EINVAL, "device attr_idx must be 16-byte aligned");
+        b->csr.contig_ptr = contig_ptr;
+        b->csr.gene_ptr32 = ptr64 ? nullptr : static_cast<const int32_t *>(gene_ptr);
+        b->csr.gene_ptr64 = ptr64 ? static_cast<const int64_t *>(gene_ptr) : nullptr;
+        b->csr.attr_idx = attr_idx;
+        b->d_out = out;
+        return GCRF_OK;
+    }
+
+    const int rc = check_host_csr(contig_ptr, gene_ptr, ptr64, C, G, nnz);
+    if (rc != GCRF_OK) return rc;
+    const size_t gene_bytes = (size_t)(G + 1) * (ptr64 ? 8 : 4);
+    GCRF_CUDA(m->b_contig.reserve((size_t)(C + 1) * 4));
+    GCRF_CUDA(m->b_gene.reserve(gene_bytes));
+    GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 16));
+    GCRF_CUDA(m->b_out.reserve(b->out_bytes));
+    GCRF_CUDA(cudaMemcpyAsync(m->b_contig.ptr, contig_ptr, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+    GCRF_CUDA(cudaMemcpyAsync(m->b_gene.ptr, gene_ptr, gene_bytes, cudaMemcpyHostToDevice, m->stream));
+    if (nnz > 0)
+        GCRF_CUDA(cudaMemcpyAsync(m->b_attr.ptr, attr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
+    b->csr.contig_ptr = static_cast<const int32_t *>(m->b_contig.ptr);
+    b->csr.gene_ptr32 = ptr64 ? nullptr : static_cast<const int32_t *>(m->b_gene.ptr);
+    b->csr.gene_ptr64 = ptr64 ? static_cast<const int64_t *>(m->b_gene.ptr) : nullptr;
+    b->csr.attr_idx = static_cast<const int32_t *>(m->b_attr.ptr);
+    b->d_out = m->b_out.ptr;
+    return GCRF_OK;
+}
+
+int finish_batch(gcrf_model *m, const Batch &b, void *out) {
+    if (b.device_ptrs || b.csr.G == 0) return GCRF_OK;
+    GCRF_CUDA(cudaMemcpyAsync(out, b.d_out, b.out_bytes, cudaMemcpyDeviceToHost, m->stream));
+    GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    return GCRF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcrf_version(void) { return GCRF_ABI_VERSION; }
+
+const char *gcrf_last_error(void) { return g_error; }
+
+int gcrf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double *trans_w, int32_t pos_label,
+                      int32_t device, gcrf_model **out) {
+    if (!out) return fail(GCRF_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!state_w || !trans_w || A < 0 || L <= 0) return fail(GCRF_EINVAL, "bad model arrays");
+    if (L != 2) return fail(GCRF_EUNSUPPORTED, "the device path handles 2-label models (GECCO labels '0'/'1'), got L=%d", L);
+    if (pos_label < 0 || pos_label >= L) return fail(GCRF_EINVAL, "pos_label out of range");
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(GCRF_ENODEVICE, "no CUDA device available (%s); this library has no CPU path",
+                    err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+    }
+    if (device < 0 || device >= ndev) return fail(GCRF_ENODEVICE, "device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    GCRF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(GCRF_ENODEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+
+    // fold the 2-label model (see gcrf_kernels.cuh): p = pos_label, o = the other label
+    const int p = pos_label, o = 1 - pos_label;
+    const double too = trans_w[o * 2 + o];
+    const double m01 = std::exp(trans_w[o * 2 + p] - too);
+    const double m10 = std::exp(trans_w[p * 2 + o] - too);
+    const double m11 = std::exp(trans_w[p * 2 + p] - too);
+    if (!std::isfinite(m01) || !std::isfinite(m10) || !std::isfinite(m11) || m01 <= 0 || m10 <= 0 || m11 <= 0)
+        return fail(GCRF_EUNSUPPORTED, "transition weights out of FP32 range");
+    // Odds stay finite in FP32 when f_max * max(m11,1) * e^{2 clamp} < ~e^85, f_max = sup of the
+    // message map (m01 + r m11)/(1 + r m10) and of its backward twin.
+    const double fmax = std::fmax(std::fmax(m01, m11 / m10), std::fmax(m10, m11 / m01));
+    double clamp = 0.5 * (85.0 - std::log(std::fmax(fmax, 1.0)) - std::log(std::fmax(m11, 1.0)));
+    if (clamp > 30.0) clamp = 30.0;
+    if (clamp < 16.0) return fail(GCRF_EUNSUPPORTED, "transition weights too extreme for the FP32 device path");
+
+    std::vector<float> table((size_t)A + 1);
+    std::vector<double> table64((size_t)A + 1);
+    for (int32_t a = 0; a < A; ++a) {
+        const double d = state_w[(size_t)a * 2 + p] - state_w[(size_t)a * 2 + o];
+        if (!std::isfinite(d)) return fail(GCRF_EINVAL, "non-finite state weight for attribute %d", a);
+        table[a] = (float)d;
+        table64[a] = d;
+    }
+    table[A] = 0.0f;
+    table64[A] = 0.0;
+
+    gcrf_model *m = new (std::nothrow) gcrf_model();
+    if (!m) return fail(GCRF_ENOMEM, "out of host memory");
+    m->device = device;
+    m->num_sms = prop.multiProcessorCount;
+    m->A = A;
+    DeviceGuard guard(device);
+    auto cleanup = [&](int code) {
+        gcrf_model_destroy(m);
+        return code;
+    };
+    if ((err = cudaMalloc(reinterpret_cast<void **>(&m->d_table), table.size() * sizeof(float))) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaMalloc(table)"));
+    if ((err = cudaMemcpy(m->d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaMemcpy(table)"));
+    if ((err = cudaMalloc(reinterpret_cast<void **>(&m->d_table64), table64.size() * sizeof(double))) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaMalloc(table64)"));
+    if ((err = cudaMemcpy(m->d_table64, table64.data(), table64.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaMemcpy(table64)"));
+    m->m01 = m01;
+    m->m10 = m10;
+    m->m11 = m11;
+    if ((err = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaStreamCreate"));
+    m->stream = m->own_stream;
+    if ((err = cudaEventCreate(&m->ev_start)) != cudaSuccess) return cleanup(fail_cuda(err, "cudaEventCreate"));
+    if ((err = cudaEventCreate(&m->ev_stop)) != cudaSuccess) return cleanup(fail_cuda(err, "cudaEventCreate"));
+    m->dev.table = m->d_table;
+    m->dev.A = A;
+    m->dev.m01 = (float)m01;
+    m->dev.m10 = (float)m10;
+    m->dev.m11 = (float)m11;
+    m->dev.clamp = (float)clamp;
+    *out = m;
+    return GCRF_OK;
+}
+
+void gcrf_model_destroy(gcrf_model *m) {
+    if (!m) return;
+    DeviceGuard guard(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    m->b_contig.release();
+    m->b_gene.release();
+    m->b_attr.release();
+    m->b_out.release();
+    m->b_scratch.release();
+    if (m->d_table) cudaFree(m->d_table);
+    if (m->d_table64) cudaFree(m->d_table64);
+    if (m->ev_start) cudaEventDestroy(m->ev_start);
+    if (m->ev_stop) cudaEventDestroy(m->ev_stop);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    delete m;
+}
+
+int gcrf_model_set_stream(gcrf_model *m, void *cuda_stream) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    m->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : m->own_stream;
+    return GCRF_OK;
+}
+
+int gcrf_model_synchronize(gcrf_model *m) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    DeviceGuard guard(m->device);
+    GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    return GCRF_OK;
+}
+
+int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx,
+                            int64_t C, int64_t G, int64_t nnz, int32_t window, int32_t step, int32_t pad, void *out,
+                            uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    // gecco/_meta.py:127-130
+    if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
+    if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
+    DeviceGuard guard(m->device);
+    Batch b;
+    int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b);
+    if (rc != GCRF_OK || G == 0) return rc;
+
+    gcrf::WindowedArgs args{};
+    args.model = m->dev;
+    args.csr = b.csr;
+    args.out = b.d_out;
+    args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
+    args.window = window;
+    args.step = step;
+    args.pad = pad ? 1 : 0;
+    gcrf::WindowedPlan plan{};
+    cudaError_t err = gcrf::plan_windowed(args, m->num_sms, &plan);
+    if (err == cudaErrorInvalidValue) {
+        cudaGetLastError();
+        return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", window, m->A);
+    }
+    if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
+    GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    err = gcrf::launch_windowed(args, plan, m->stream, &m->launches);
+    if (err != cudaSuccess) return fail_cuda(err, "launch_windowed");
+    GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
+    m->timed = true;
+    return finish_batch(m, b, out);
+}
+
+int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx,
+                         int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    DeviceGuard guard(m->device);
+    Batch b;
+    int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b);
+    if (rc != GCRF_OK || G == 0) return rc;
+    GCRF_CUDA(m->b_scratch.reserve((size_t)G * 2 * sizeof(double)));
+    gcrf::ChainArgs args{};
+    args.model = m->dev;
+    args.csr = b.csr;
+    args.out = b.d_out;
+    args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
+    args.table64 = m->d_table64;
+    args.m01 = m->m01;
+    args.m10 = m->m10;
+    args.m11 = m->m11;
+    args.scratch = static_cast<double *>(m->b_scratch.ptr);
+    GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    cudaError_t err = gcrf::launch_chain(args, m->num_sms, m->stream, &m->launches);
+    if (err != cudaSuccess) return fail_cuda(err, "launch_chain");
+    GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
+    m->timed = true;
+    return finish_batch(m, b, out);
+}
+
+int gcrf_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(GCRF_EINVAL, "ptr is NULL");
+    *ptr = nullptr;
+    GCRF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return GCRF_OK;
+}
+
+int gcrf_host_free(void *ptr) {
+    if (!ptr) return GCRF_OK;
+    GCRF_CUDA(cudaFreeHost(ptr));
+    return GCRF_OK;
+}
+
+int64_t gcrf_model_launch_count(const gcrf_model *m) { return m ? m->launches : 0; }
+
+double gcrf_model_last_kernel_ms(gcrf_model *m) {
+    if (!m || !m->timed) return -1.0;
+    DeviceGuard guard(m->device);
+    if (cudaEventSynchronize(m->ev_stop) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ev_start, m->ev_stop) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+}  // extern "C"

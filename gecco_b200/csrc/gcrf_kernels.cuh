@@ -1,0 +1,70 @@
+// gcrf_kernels.cuh — device-side parameter blocks and launcher prototypes shared by the kernels
+// (gcrf_windowed.cu, gcrf_chain.cu) and the C ABI (gcrf_abi.cu).  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gcrf {
+
+// Two-label model folded for the device ("two-state simplifications"):
+// with o = the other label and p = pos_label, only
+//     delta_a = W[a][p] - W[a][o]                     (per attribute, table[a]; table[A] = 0)
+//     m01 = exp(T[o][p]-T[o][o]), m10 = exp(T[p][o]-T[o][o]), m11 = exp(T[p][p]-T[o][o])
+// matter for the marginal of p: messages are carried as odds ratios x[p]/x[o].
+struct ModelDev {
+    const float *table;  // [A+1] on device, table[A] = 0 is the slot of unknown attributes
+    int32_t A;
+    float m01, m10, m11;
+    float clamp;  // |delta_gene| is clamped to this before exp() so that odds stay finite in FP32
+};
+
+struct CsrDev {
+    const int32_t *contig_ptr;  // [C+1]
+    const int32_t *gene_ptr32;  // [G+1] or nullptr
+    const int64_t *gene_ptr64;  // [G+1] or nullptr
+    const int32_t *attr_idx;    // [nnz]
+    int64_t C, G, nnz;
+};
+
+struct WindowedArgs {
+    ModelDev model;
+    CsrDev csr;
+    void *out;        // double[G] or float[G]
+    int32_t out_f32;  // 0: double, 1: float
+    int32_t window, step, pad;
+};
+
+// Geometry of the fused windowed kernel, fixed on the host so that tests can query it.
+struct WindowedPlan {
+    int threads;          // CTA size
+    int tile_out;         // genes written per tile
+    int chunk;            // attribute ids staged per gather round (elements)
+    size_t smem_bytes;    // dynamic shared memory per CTA
+    int64_t num_tiles;
+    int grid;             // persistent CTAs
+    int tiles_per_cta;
+    int ctas_per_sm;
+};
+
+// Fills `plan` (queries occupancy on the current device); returns cudaSuccess or the failure.
+cudaError_t plan_windowed(const WindowedArgs &args, int num_sms, WindowedPlan *plan);
+
+// Enqueue the fused gather + windowed forward-backward + max-pool kernel.  *launches += kernels launched.
+cudaError_t launch_windowed(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream,
+                            int64_t *launches);
+
+struct ChainArgs {
+    ModelDev model;
+    CsrDev csr;
+    void *out;
+    int32_t out_f32;
+    const double *table64;  // [A+1] f64 twin of ModelDev::table (table64[A] = 0)
+    double m01, m10, m11;   // f64 twins of the folded transition odds
+    double *scratch;        // [2*G] device scratch: unary odds, then forward odds
+};
+
+// Whole-contig (un-windowed) marginals: unary gather kernel + block-per-contig 2x2 scan kernel.
+cudaError_t launch_chain(const ChainArgs &args, int num_sms, cudaStream_t stream, int64_t *launches);
+
+}  // namespace gcrf

@@ -1,0 +1,152 @@
+/*
+ * gecco_crf_b200.h — C ABI of libgecco_crf_b200.so: linear-chain CRF marginal inference for
+ * GECCO's ClusterCRF on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of the reference (zellerlab/GECCO v0.11.0): the body
+ * of gecco.crf.ClusterCRF.predict_probabilities (gecco/crf/__init__.py:148-273).  The reference
+ * crosses into native code at exactly one place on that path,
+ *     self.model.predict_marginals_single(feats[win])          gecco/crf/__init__.py:253
+ * (sklearn-crfsuite -> python-crfsuite Tagger.set()/Tagger.marginal() -> CRFsuite C), once per
+ * W-gene window.  The functions below replace that binding in bulk: the caller packs all contigs
+ * into CSR arrays once and gets every gene's max-pooled marginal back.
+ *
+ * Conventions
+ *   - plain C types only; the caller owns every buffer, the library owns only the handle;
+ *   - every function returns GCRF_OK (0) or a negative gcrf_status; gcrf_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - a handle is bound to one CUDA device and is not thread-safe; distinct handles are;
+ *   - there is NO CPU fallback: without a usable CUDA device gcrf_model_create fails with
+ *     GCRF_ENODEVICE.
+ *
+ * Data layout (all row pointers are int32 unless GCRF_FLAG_PTR64 is given)
+ *   contig_ptr[C+1]  genes of contig c are [contig_ptr[c], contig_ptr[c+1]); strictly increasing
+ *                    (a contig has >= 1 gene: itertools.groupby never yields an empty group,
+ *                    gecco/crf/__init__.py:204-206); contig_ptr[0] = 0, contig_ptr[C] = G
+ *   gene_ptr[G+1]    attribute ids of gene g are attr_idx[gene_ptr[g] .. gene_ptr[g+1]);
+ *                    a gene without domains is an empty row (the `{}` item of
+ *                    gecco/crf/features.py:31-35)
+ *   attr_idx[nnz]    attribute ids in [0, A); any id outside that range (use -1) is an attribute
+ *                    the model does not know and contributes nothing (python-crfsuite drops
+ *                    unknown attribute strings).  Ids must be unique within a gene: the reference
+ *                    builds a dict keyed by domain name (features.py:32), so duplicates collapse
+ *                    at feature extraction — the packer does that.
+ *   genes are ordered as the reference orders them: by contig, then by start (:199).
+ */
+#ifndef GECCO_CRF_B200_H
+#define GECCO_CRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCRF_ABI_VERSION 1
+
+typedef enum gcrf_status {
+    GCRF_OK = 0,
+    GCRF_EINVAL = -1,       /* bad argument (also: window/step rule of gecco/_meta.py:127-130) */
+    GCRF_ENODEVICE = -2,    /* no usable CUDA device / wrong architecture */
+    GCRF_ECUDA = -3,        /* a CUDA runtime call failed; see gcrf_last_error() */
+    GCRF_ENOMEM = -4,       /* host or device allocation failed */
+    GCRF_EUNSUPPORTED = -5  /* model shape not supported by the device path (e.g. L != 2) */
+} gcrf_status;
+
+/* flags of the marginal calls */
+#define GCRF_FLAG_DEVICE_PTRS 0x1u /* contig_ptr/gene_ptr/attr_idx/out are device pointers on the
+                                      handle's device; the call only enqueues work on the handle's
+                                      stream (gcrf_model_set_stream) and does not synchronise */
+#define GCRF_FLAG_OUT_F32     0x2u /* out is float[G] instead of double[G] */
+#define GCRF_FLAG_PTR64       0x4u /* gene_ptr is int64_t[G+1] (nnz >= 2^31); contig_ptr stays int32 */
+
+typedef struct gcrf_model gcrf_model;
+
+/* Library / ABI version (GCRF_ABI_VERSION of the build). */
+int gcrf_version(void);
+
+/* Message of the last error raised on the calling thread ("" if none). Never NULL. */
+const char *gcrf_last_error(void);
+
+/* Number of CUDA devices the library can see (0 if none / driver missing). */
+int gcrf_device_count(void);
+
+/*
+ * Create a model handle on CUDA device `device`.
+ *
+ * Replaces: unpickling the tagger and pycrfsuite.Tagger.open() behind
+ * ClusterCRF.trained() (gecco/crf/__init__.py:61-99).
+ *
+ *   state_w   [A][L] row-major state-feature weights, 0 where the model has no feature
+ *   trans_w   [L][L] transition weights, from -> to
+ *   pos_label id of the label whose marginal is reported (the id of '1', looked up by NAME by the
+ *             caller — gecco/crf/__init__.py:253 asks for p['1'])
+ * The device path supports L == 2 (GECCO's labels are '0'/'1'); other L -> GCRF_EUNSUPPORTED.
+ */
+int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double *trans_w,
+                      int32_t pos_label, int32_t device, gcrf_model **out);
+
+void gcrf_model_destroy(gcrf_model *model);
+
+/* Use `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) for all later work. */
+int gcrf_model_set_stream(gcrf_model *model, void *cuda_stream);
+
+/* Block until everything enqueued on the handle's stream has finished. */
+int gcrf_model_synchronize(gcrf_model *model);
+
+/*
+ * Per-gene cluster probability for a batch of contigs — the whole hot loop of
+ * ClusterCRF.predict_probabilities (gecco/crf/__init__.py:209-258) in one call:
+ *
+ *   for every contig with n genes
+ *     n <  window, pad != 0 : one window over delta/2 empty items + the genes + (delta+1)/2 empty
+ *                             items, delta = window - n              (:216-227, read-back :258)
+ *     n <  window, pad == 0 : the contig is skipped; its genes get NaN  (:228-234, :246-248 leave
+ *                             the genes without a probability)
+ *     n >= window           : windows [i, i+window) for i = 0, step, 2*step, ... while
+ *                             i + window <= n        (gecco/_meta.py:124-132)
+ *     out[g] = max over the windows covering g of P(y_g = pos_label | window), 0.0 if no window
+ *              covers g (possible only when step > 1)                 (:251-254)
+ *
+ * where P(.) is the first-order CRF marginal of CRFsuite (Tagger.marginal): unary scores are the
+ * sums of the state weights of the gene's attributes, see SURVEY.md Appendix B.
+ *
+ * Host-pointer mode (default): the call copies the inputs to the device, runs, copies `out` back
+ * and returns when `out` is complete.  Device-pointer mode: see GCRF_FLAG_DEVICE_PTRS.
+ * Result tolerance vs the f64 reference arithmetic: |dp| <= 1e-5 (FP32 device arithmetic;
+ * measured <= 2e-6, tests/test_gpu_parity.py).
+ */
+int gcrf_marginals_windowed(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
+                            const int32_t *attr_idx, int64_t C, int64_t G, int64_t nnz,
+                            int32_t window, int32_t step, int32_t pad, void *out, uint32_t flags);
+
+/*
+ * Primitive equal to predict_marginals_single() on whole rows: every contig is ONE chain of
+ * n items (no windows, no padding); out[g] = P(y_g = pos_label | whole contig).
+ * Replaces: sklearn_crfsuite.CRF.predict_marginals_single (call site gecco/crf/__init__.py:253)
+ * for callers that want the un-windowed marginal, and is the deep-chain path (BASELINE config 5).
+ */
+int gcrf_marginals_chain(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
+                         const int32_t *attr_idx, int64_t C, int64_t G, int64_t nnz, void *out,
+                         uint32_t flags);
+
+/*
+ * Pinned host memory helpers so that host-pointer calls can run their copies at PCIe speed
+ * (pageable buffers are accepted everywhere, they are just slower).
+ */
+int gcrf_host_alloc(void **ptr, uint64_t bytes);
+int gcrf_host_free(void *ptr);
+
+/* Number of kernel launches the handle has issued so far (for bench.py's gpu_launches). */
+int64_t gcrf_model_launch_count(const gcrf_model *model);
+
+/*
+ * Device time, in milliseconds, of the compute kernels of the LAST marginal call on this handle
+ * (CUDA events on the handle's stream around the kernels only, excluding copies).  Synchronises
+ * the stream.  Returns < 0 on error.
+ */
+double gcrf_model_last_kernel_ms(gcrf_model *model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GECCO_CRF_B200_H */

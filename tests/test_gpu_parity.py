@@ -1,0 +1,206 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerance: the north star asks for |dp| <= 1e-5 against Tagger.marginal(); the device computes in
+FP32, the oracle in f64.  TOL below is the bar written into the test.
+"""
+import numpy
+import pytest
+
+from conftest import pack_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def oracle(weights, batch, window=20, step=1, pad=True, nthreads=8):
+    from oracle import crf_oracle
+
+    p, _ = crf_oracle.marginals_windowed(weights.state_w, weights.trans_w, weights.label_id("1"), batch.contig_ptr,
+                                         batch.gene_ptr, batch.attr_idx, window, step, pad, nthreads=nthreads)
+    return p
+
+
+def assert_close(got, want, tol=TOL, what=""):
+    assert got.shape == want.shape
+    assert numpy.array_equal(numpy.isnan(got), numpy.isnan(want)), what
+    ok = ~numpy.isnan(want)
+    if ok.any():
+        err = numpy.abs(got[ok] - want[ok]).max()
+        assert err <= tol, f"{what}: max |dp| = {err:.3e}"
+        return err
+    return 0.0
+
+
+def test_golden_bgc0001866(engine, bgc, weights):
+    from test_oracle import _bgc_csr
+
+    packed, genes = _bgc_csr(bgc, weights)
+    p = engine.marginals_windowed(packed.contig_ptr, packed.gene_ptr, packed.attr_idx)
+    golden = numpy.array([g["average_p"] for g in genes])[packed.order]
+    assert_close(p, golden, what="python-crfsuite golden")
+
+
+def test_reference_loop_cases(engine, ref_cases, weights):
+    for case in ref_cases:
+        packed = pack_case(case, weights)
+        p = engine.marginals_windowed(packed.contig_ptr, packed.gene_ptr, packed.attr_idx, window=case["window"],
+                                      step=case["step"], pad=case["pad"])
+        want = numpy.array([numpy.nan if e["p"] is None else e["p"] for e in case["expected"]])
+        assert_close(p, want, what=case["name"])
+
+
+def test_mibig_real_features(engine, mibig, weights):
+    from gecco_b200.packer import pack_arrays
+
+    packed = pack_arrays(mibig["gene_contig"], mibig["dom_ptr"], mibig["dom_pfam"], weights)
+    p = engine.marginals_windowed(packed.contig_ptr, packed.gene_ptr, packed.attr_idx)
+    err = assert_close(p, mibig["ref_loop_prob"], what="mibig vs reference loop")
+    print(f"mibig max |dp| = {err:.3e}")
+
+
+@pytest.mark.parametrize("window,step,pad", [(20, 1, True), (20, 1, False), (20, 3, True), (5, 1, True), (5, 2, False),
+                                             (7, 7, True), (1, 1, True), (33, 4, True), (64, 1, True), (128, 5, True)])
+def test_ragged_edge_cases(engine, weights, window, step, pad):
+    from gecco_b200 import synth
+
+    batch = synth.ragged_edge_cases(len(weights.attrs))
+    want = oracle(weights, batch, window, step, pad)
+    got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window, step=step, pad=pad)
+    assert_close(got, want, what=f"W={window} step={step} pad={pad}")
+
+
+def test_f32_output_and_int64_pointers(engine, weights):
+    from gecco_b200 import synth
+
+    batch = synth.ragged_edge_cases(len(weights.attrs))
+    want = oracle(weights, batch)
+    got32 = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, f32=True)
+    assert got32.dtype == numpy.float32
+    assert_close(got32.astype(numpy.float64), want, what="f32 out")
+    lib_flags_ptr64 = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr.astype(numpy.int64), batch.attr_idx)
+    assert_close(lib_flags_ptr64, want, what="int64-able gene_ptr")
+
+
+def test_dense_config2_slice(engine, weights):
+    """BASELINE config 2 shape (Poisson(200) genes x Poisson(25) domains, 5 % unknown ids), 300 contigs."""
+    from gecco_b200 import synth
+
+    batch = synth.config2(len(weights.attrs), contigs=300)
+    want = oracle(weights, batch)
+    got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    err = assert_close(got, want, what="config2 slice")
+    print(f"config2 slice ({batch.G} genes, nnz {batch.nnz}) max |dp| = {err:.3e}")
+
+
+def test_sparse_ecoli_like(engine, weights):
+    from gecco_b200 import synth
+
+    batch = synth.config3_ecoli_like(len(weights.attrs))
+    assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx), oracle(weights, batch),
+                 what="config3")
+
+
+def test_metagenome_short_contigs(engine, weights):
+    """BASELINE config 4 shape: lognormal contig lengths, ~31 % shorter than the window -> padding path."""
+    from gecco_b200 import synth
+
+    batch = synth.config4(len(weights.attrs), contigs=4000, mean_domains=6.0)
+    for pad in (True, False):
+        assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, pad=pad),
+                     oracle(weights, batch, pad=pad), what=f"config4 pad={pad}")
+
+
+def test_long_contigs_windowed_and_chain(engine, weights):
+    """BASELINE config 5 shape (scaled): windows are per-window parallel; chain = whole-contig marginals."""
+    from gecco_b200 import synth
+    from oracle import crf_oracle
+
+    batch = synth.config5(len(weights.attrs), contigs=6, genes=5000)
+    assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx), oracle(weights, batch),
+                 what="config5 windowed")
+    got = engine.marginals_chain(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    for c in range(batch.C):
+        g0, g1 = int(batch.contig_ptr[c]), int(batch.contig_ptr[c + 1])
+        want = crf_oracle.chain_marginals(weights.state_w, weights.trans_w, batch.gene_ptr, batch.attr_idx, g0, g1)[:, 1]
+        assert_close(got[g0:g1], want, tol=1e-9, what=f"chain contig {c}")
+
+
+def test_chain_ragged(engine, weights):
+    from gecco_b200 import synth
+    from oracle import crf_oracle
+
+    batch = synth.ragged_edge_cases(len(weights.attrs))
+    got = engine.marginals_chain(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    for c in range(batch.C):
+        g0, g1 = int(batch.contig_ptr[c]), int(batch.contig_ptr[c + 1])
+        want = crf_oracle.chain_marginals(weights.state_w, weights.trans_w, batch.gene_ptr, batch.attr_idx, g0, g1)[:, 1]
+        assert_close(got[g0:g1], want, tol=1e-9, what=f"chain contig {c} (n={g1 - g0})")
+
+
+def test_window_equal_to_contig_is_the_chain(engine, weights):
+    """Size-independent property: one window covering a whole contig == the chain primitive."""
+    from gecco_b200 import synth
+
+    rng = numpy.random.default_rng(3)
+    batch = synth.make_batch(rng, numpy.full(50, 20), 5.0, len(weights.attrs))
+    a = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=20)
+    b = engine.marginals_chain(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    assert numpy.abs(a - b).max() <= TOL
+
+
+def test_extreme_unaries_stay_finite(engine, weights):
+    """Genes with every strongly positive / strongly negative attribute: |delta| far beyond the FP32 clamp."""
+    from gecco_b200.synth import CsrBatch
+
+    d = weights.state_w[:, 1] - weights.state_w[:, 0]
+    pos = numpy.flatnonzero(d > 1.0).astype(numpy.int32)
+    neg = numpy.flatnonzero(d < -1.0).astype(numpy.int32)
+    rows = []
+    for k in range(60):
+        rows.append(pos if k % 2 == 0 else neg)  # adversarial alternation
+    for k in range(40):
+        rows.append(pos)
+    for k in range(40):
+        rows.append(numpy.zeros(0, dtype=numpy.int32))
+    gene_ptr = numpy.cumsum([0] + [len(r) for r in rows]).astype(numpy.int32)
+    batch = CsrBatch(numpy.array([0, len(rows)], dtype=numpy.int32), gene_ptr, numpy.concatenate(rows))
+    want = oracle(weights, batch)
+    got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    assert numpy.isfinite(got).all()
+    assert_close(got, want, what="extreme unaries")
+
+
+def test_empty_batch_and_argument_errors(engine, weights):
+    from gecco_b200._lib import GcrfError
+
+    z = numpy.zeros(1, dtype=numpy.int32)
+    out = engine.marginals_windowed(z, z, numpy.zeros(0, dtype=numpy.int32))
+    assert out.shape == (0,)
+    one = numpy.array([0, 1], dtype=numpy.int32)
+    for window, step in [(0, 1), (5, 0), (5, 6)]:
+        with pytest.raises(GcrfError):
+            engine.marginals_windowed(one, numpy.array([0, 0], dtype=numpy.int32), numpy.zeros(0, dtype=numpy.int32),
+                                      window=window, step=step)
+    with pytest.raises(GcrfError):  # empty contig
+        engine.marginals_windowed(numpy.array([0, 0, 1], dtype=numpy.int32), numpy.array([0, 0], dtype=numpy.int32),
+                                  numpy.zeros(0, dtype=numpy.int32))
+
+
+def test_device_pointer_mode_matches_host_mode(engine, weights):
+    import torch
+    from gecco_b200 import synth
+
+    batch = synth.config2(len(weights.attrs), contigs=50)
+    host = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    dev = torch.device("cuda:0")
+    cp = torch.from_numpy(batch.contig_ptr).to(dev)
+    gp = torch.from_numpy(batch.gene_ptr).to(dev)
+    ai = torch.from_numpy(batch.attr_idx).to(dev)
+    out = torch.empty(batch.G, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), batch.C, batch.G, batch.nnz, out.data_ptr())
+    engine.synchronize()
+    assert numpy.array_equal(out.cpu().numpy(), host)
+    assert engine.last_kernel_ms() > 0
+    assert engine.launch_count > 0
