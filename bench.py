@@ -217,7 +217,11 @@ def run_ours(args) -> None:
     weights = load_weights()
     batch = make_batch(weights, args.contigs, seed=2 + rank)
     engine = CRFEngine(weights, device=local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated non-default stream: torch events only see the stream they are recorded on, and the
+    # default stream's handle (0) would make the engine fall back to its own stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     engine.set_stream(stream.cuda_stream)
 
     # ---- device-resident inputs

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -66,6 +67,7 @@ struct gcrf_model {
     int32_t A = 0;
     gcrf::ModelDev dev{};
     float *d_table = nullptr;
+    int32_t *d_table_fx = nullptr;
     double *d_table64 = nullptr;
     double m01 = 0, m10 = 0, m11 = 0;
     cudaStream_t own_stream = nullptr;
@@ -225,6 +227,17 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
     }
     table[A] = 0.0f;
     table64[A] = 0.0;
+    // fixed-point table: as many fraction bits as keep rows of up to 64 ids exact in wrapping int32 sums
+    double maxabs = 0.0;
+    for (int32_t a = 0; a < A; ++a) maxabs = std::fmax(maxabs, std::fabs(table64[a]));
+    int fx_bits = 24;
+    while (fx_bits > 8 && maxabs * 64.0 * std::ldexp(1.0, fx_bits) >= 2147483647.0) --fx_bits;
+    const double fx_one = std::ldexp(1.0, fx_bits);
+    std::vector<int32_t> table_fx((size_t)A + 1);
+    for (int32_t a = 0; a < A; ++a) table_fx[a] = (int32_t)std::llround(table64[a] * fx_one);
+    table_fx[A] = 0;
+    const double fx_nsafe_d = maxabs > 0 ? std::floor(2147483647.0 / (maxabs * fx_one + 1.0)) : 2147483647.0;
+    const int32_t fx_nsafe = (int32_t)std::fmin(fx_nsafe_d, 2147483647.0);
 
     gcrf_model *m = new (std::nothrow) gcrf_model();
     if (!m) return fail(GCRF_ENOMEM, "out of host memory");
@@ -240,6 +253,10 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
         return cleanup(fail_cuda(err, "cudaMalloc(table)"));
     if ((err = cudaMemcpy(m->d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cleanup(fail_cuda(err, "cudaMemcpy(table)"));
+    if ((err = cudaMalloc(reinterpret_cast<void **>(&m->d_table_fx), table_fx.size() * sizeof(int32_t))) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaMalloc(table_fx)"));
+    if ((err = cudaMemcpy(m->d_table_fx, table_fx.data(), table_fx.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaMemcpy(table_fx)"));
     if ((err = cudaMalloc(reinterpret_cast<void **>(&m->d_table64), table64.size() * sizeof(double))) != cudaSuccess)
         return cleanup(fail_cuda(err, "cudaMalloc(table64)"));
     if ((err = cudaMemcpy(m->d_table64, table64.data(), table64.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -258,6 +275,9 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
     m->dev.m10 = (float)m10;
     m->dev.m11 = (float)m11;
     m->dev.clamp = (float)clamp;
+    m->dev.table_fx = m->d_table_fx;
+    m->dev.fx_bits = fx_bits;
+    m->dev.fx_nsafe = fx_nsafe;
     *out = m;
     return GCRF_OK;
 }
@@ -273,6 +293,7 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_scratch.release();
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
+    if (m->d_table_fx) cudaFree(m->d_table_fx);
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -312,18 +333,42 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     args.window = window;
     args.step = step;
     args.pad = pad ? 1 : 0;
+    args.prof = nullptr;
+    // GCRF_PHASE_PROFILE=1: per-phase cycle counters of the streaming kernel, printed to stderr (tuning aid)
+    const char *prof_env = getenv("GCRF_PHASE_PROFILE");
+    const bool prof = prof_env && prof_env[0] == '1';
+    if (prof) {
+        GCRF_CUDA(m->b_scratch.reserve(16 * sizeof(unsigned long long)));
+        GCRF_CUDA(cudaMemsetAsync(m->b_scratch.ptr, 0, 16 * sizeof(unsigned long long), m->stream));
+        args.prof = static_cast<unsigned long long *>(m->b_scratch.ptr);
+    }
     gcrf::WindowedPlan plan{};
-    cudaError_t err = gcrf::plan_windowed(args, m->num_sms, &plan);
+    // GCRF_FORCE_GENERIC=1 routes W=20 through the generic kernel too (A/B testing of the two device paths)
+    const char *force = getenv("GCRF_FORCE_GENERIC");
+    const bool fast = gcrf::stream_supported(args) && !(force && force[0] == '1');
+    cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", window, m->A);
     }
     if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
     GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
-    err = gcrf::launch_windowed(args, plan, m->stream, &m->launches);
+    err = fast ? gcrf::launch_stream(args, plan, m->stream, &m->launches)
+               : gcrf::launch_windowed(args, plan, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_windowed");
     GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
     m->timed = true;
+    if (prof) {
+        unsigned long long h[16];
+        GCRF_CUDA(cudaMemcpyAsync(h, args.prof, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+        GCRF_CUDA(cudaStreamSynchronize(m->stream));
+        static const char *names[10] = {"setup", "wait_ids", "walk", "row_sums", "unary", "contig", "dp", "pool", "out", "-"};
+        unsigned long long tot = 0;
+        for (int k = 0; k < 9; ++k) tot += h[k];
+        fprintf(stderr, "[gcrf phases] ctas=%llu grid=%d tiles/cta=%d:", h[15], plan.grid, plan.tiles_per_cta);
+        for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%.1f%%", names[k], tot ? 100.0 * h[k] / tot : 0.0);
+        fprintf(stderr, " | cycles/cta=%.0f\n", h[15] ? (double)tot / h[15] : 0.0);
+    }
     return finish_batch(m, b, out);
 }
 

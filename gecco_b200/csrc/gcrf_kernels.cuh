@@ -17,6 +17,11 @@ struct ModelDev {
     int32_t A;
     float m01, m10, m11;
     float clamp;  // |delta_gene| is clamped to this before exp() so that odds stay finite in FP32
+    // fixed-point twin of `table` for the streaming kernel: table_fx[a] = round(delta_a * 2^fx_bits),
+    // table_fx[A] = 0.  Row sums are formed in wrapping int32 arithmetic, which is exact as long as a row
+    // has fewer than fx_nsafe ids (rows with more take a float path).
+    const int32_t *table_fx;
+    int32_t fx_bits, fx_nsafe;
 };
 
 struct CsrDev {
@@ -33,6 +38,7 @@ struct WindowedArgs {
     void *out;        // double[G] or float[G]
     int32_t out_f32;  // 0: double, 1: float
     int32_t window, step, pad;
+    unsigned long long *prof;  // optional [16] cycle accumulators per kernel phase (nullptr = off); tuning aid
 };
 
 // Geometry of the fused windowed kernel, fixed on the host so that tests can query it.
@@ -53,6 +59,11 @@ cudaError_t plan_windowed(const WindowedArgs &args, int num_sms, WindowedPlan *p
 // Enqueue the fused gather + windowed forward-backward + max-pool kernel.  *launches += kernels launched.
 cudaError_t launch_windowed(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream,
                             int64_t *launches);
+
+// Fast fused kernel for the compile-time window sizes (gcrf_stream.cu); same arguments and results.
+bool stream_supported(const WindowedArgs &args);
+cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan);
+cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches);
 
 struct ChainArgs {
     ModelDev model;

@@ -1,0 +1,697 @@
+// gcrf_stream.cu — the fast fused kernel for compile-time window sizes (W = 20 is GECCO's shipped model).
+//
+// Same contract as gcrf_windowed.cu (reference loop: gecco/crf/__init__.py:209-258, tagger arithmetic
+// SURVEY.md Appendix B) but organised around what the ncu captures showed to bound it on B200:
+// shared-memory wavefronts, issue slots and dependent-latency chains at low occupancy — not DRAM.
+//
+//   * One persistent CTA walks a contiguous run of tiles.  Tile = 2*NT window slots, `tile_out` output
+//     genes.  The unary odds u_g of the 2W-1 genes shared with the previous tile stay in shared memory
+//     (a ring), so every attribute id is fetched and resolved exactly once per CTA run.
+//   * attr_idx of the tile's NEW genes is brought in by ONE bulk-async copy (TMA, cp.async.bulk +
+//     mbarrier) issued while the previous tile's dynamic programme runs: no load instructions, no
+//     registers, latency off the critical path (measured: < 3 % of CTA time spent waiting).
+//   * Segmented sums without any per-id boundary logic (a per-thread branch there diverges in every
+//     warp): thread t walks ids [K t, K t + K) of the staged range with 16-byte shared loads (K = 4*odd
+//     keeps them bank-conflict free), resolves each id through a FIXED-POINT delta table and overwrites
+//     it in place with the thread's running prefix sum.  A row sum is then a difference of prefixes
+//     (plus whole-thread totals when a row straddles threads) in wrapping int32 arithmetic: exact, and
+//     order-independent.  Rows with >= fx_nsafe ids could wrap and take a float path from global memory.
+//   * Dynamic programme on odds ratios, two adjacent windows per thread packed in f32x2 registers
+//     (FFMA2/FMUL2 halve the issue slots; MUFU.RCP stays scalar).  Each thread finds the contig of its
+//     own two window slots with one search.  Invalid window slots run with m01 and u_0 masked to zero,
+//     which pins their odds to exactly 0 — the neutral element of the max-pool — so the pool needs no
+//     range logic at all.
+//   * Padded short contigs (:216-227) and skipped ones (pad = 0) are handled by a slow path that a tile
+//     only enters when it actually holds a contig shorter than the window.
+#include "gcrf_kernels.cuh"
+
+#include <climits>
+#include <cstdlib>
+
+namespace gcrf {
+
+namespace {
+
+constexpr int kWalk = 52;  // ids walked per thread and staging round (4 * odd: conflict-free LDS.128)
+
+__host__ __device__ constexpr int round_up4s(int x) { return (x + 3) & ~3; }
+
+template <int W, int NT>
+struct StreamTiling {
+    static constexpr int kSlots = 2 * NT;          // window slots per tile
+    static constexpr int kCap = NT * kWalk;        // ids staged per round
+    static constexpr int kPitch = NT + 16;         // pool pitch: odd and even genes land 16 banks apart
+    static constexpr int lo = W;                   // local index of the first output gene
+    static constexpr int tile_out = (kSlots - W) & ~3;
+    static constexpr int ng = kSlots + W - 1;      // genes staged per tile
+    static constexpr int keep = ng - tile_out;     // genes carried over from the previous tile
+    int off_idx, off_pool, off_u0, off_u1, off_q, off_sp, off_cp, off_stat, words;
+    __host__ __device__ explicit StreamTiling(int A) {
+        int o = round_up4s(A + 1);
+        off_idx = o; o += kCap + 4;
+        off_pool = o; o += round_up4s((W + 1) * kPitch);
+        off_u0 = o; o += round_up4s(ng + 2);
+        off_u1 = o; o += round_up4s(ng + 2);
+        off_q = o; o += round_up4s(ng + 2);
+        off_sp = o; o += round_up4s(ng + 3);
+        off_cp = o; o += round_up4s(ng + 4);
+        off_stat = o; o += round_up4s((ng + 8) / 4);
+        words = o;
+    }
+    __host__ __device__ size_t bytes() const { return sizeof(float) * (size_t)words; }
+};
+
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// exp(x) for |x| <= ~40 with ~2e-7 relative error: exponent split in two floats, one MUFU.EX2
+__device__ __forceinline__ float exp_fast(float x) {
+    const float l2e_hi = 1.44269502162933349609375f, l2e_lo = 1.925963033500011e-8f;
+    const float t = x * l2e_hi;
+    const float lo = fmaf(x, l2e_hi, -t) + x * l2e_lo;
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return fmaf(r, lo * 0.693147180559945f, r);
+}
+
+// x / kWalk for 0 <= x < 13376 (kWalk = 52): one multiply and one shift
+__device__ __forceinline__ int walk_thread(int x) {
+    static_assert(kWalk == 52, "magic constant is for 52");
+    return (int)(((unsigned)x * 10083u) >> 19);
+}
+
+__device__ __forceinline__ int lookup(const int *sTab, int32_t id, uint32_t A) {
+    return sTab[min((uint32_t)id, A)];  // ids outside [0, A) (e.g. -1) hit the zero slot A
+}
+
+// ---- mbarrier / bulk-async copy (TMA) wrappers ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    // order earlier generic-proxy accesses to the buffer (the -1 masks, the walk's stores) before the async write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Largest c in [0, C) with contig_ptr[c] <= g (g >= 0), one warp, 32 probes per round.
+__device__ int64_t warp_find_contig(const int32_t *contig_ptr, int64_t C, int64_t g, int lane) {
+    int64_t lo = 0, hi = C;
+    while (hi - lo > 1) {
+        const int64_t span = hi - lo;
+        const int64_t st = (span + 32) / 33;
+        const int64_t probe = lo + (int64_t)(lane + 1) * st;
+        const bool ok = probe < hi && (int64_t)__ldg(contig_ptr + probe) <= g;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+        const int64_t nhi = lo + (int64_t)(cnt + 1) * st;
+        lo += (int64_t)cnt * st;
+        hi = nhi < hi ? nhi : hi;
+    }
+    return lo;
+}
+
+// Largest k in [0, kmax] with sCp[k] <= j.  Requires sCp[0] <= j and sCp[kmax + 1] > j.
+__device__ __forceinline__ int find_slice_contig(const int *sCp, int j, int kmax) {
+    int k = 0, hi = kmax + 1;
+    while (hi - k > 1) {
+        const int mid = (k + hi) >> 1;
+        if (sCp[mid] <= j) k = mid; else hi = mid;
+    }
+    return k;
+}
+
+// Window of a padded short contig (gecco/crf/__init__.py:216-227): n < W genes starting at local gene j,
+// (W-n)/2 empty items in front and the rest behind; writes the odds of its n genes to sQ.
+template <int W>
+__device__ __noinline__ void padded_window(const float *sU0, float *sQ, int j, int n, float m01, float m10, float m11) {
+    const int front = (W - n) >> 1;
+    float ra[W];
+    float rr = 0.f;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const int p = q - front;
+        const float u = (p >= 0 && p < n) ? sU0[j + p] : 1.0f;
+        rr = q == 0 ? u : (fmaf(rr, m11, m01) * u) * rcp_fast(fmaf(rr, m10, 1.0f));
+        ra[q] = rr;
+    }
+    float ss = 1.0f;
+#pragma unroll
+    for (int q = W - 1; q >= 0; --q) {
+        const int p = q - front;
+        const bool real = p >= 0 && p < n;
+        if (real) sQ[j + p] = ra[q] * ss;
+        if (q > 0) {
+            const float w = (real ? sU0[j + p] : 1.0f) * ss;
+            ss = fmaf(w, m11, m10) * rcp_fast(fmaf(w, m01, 1.0f));
+        }
+    }
+}
+
+// bytes of one staging round of a range of `total` ids counted from its 16-byte aligned start
+template <int kCap>
+__device__ __forceinline__ uint32_t round_bytes(int64_t total) {
+    const int64_t padded = (total + 3) & ~(int64_t)3;
+    return (uint32_t)(4 * (padded < kCap ? padded : (int64_t)kCap));
+}
+
+// New genes of a tile: global genes [ga, gb).  The first tile of a CTA run stages everything it needs,
+// later tiles only the genes the previous tile did not cover.
+template <int W, int NT>
+__device__ __forceinline__ void new_gene_range(int tile, bool first, int G, int &ga, int &gb) {
+    using T = StreamTiling<W, NT>;
+    const int Gs = tile * T::tile_out - T::lo;
+    ga = max(0, min(G, Gs + (first ? 0 : T::keep)));
+    gb = max(0, min(G, Gs + T::ng));
+}
+
+// phase timing (tuning aid): thread 0 accumulates SM-clock cycles between marks when args.prof is set
+#define GCRF_MARK(slot)                                   \
+    do {                                                  \
+        if (prof_on && tid == 0) {                        \
+            const long long now__ = clock64();            \
+            prof_acc[slot] += now__ - prof_last;          \
+            prof_last = now__;                            \
+        }                                                 \
+    } while (0)
+
+template <int W, int NT, int MINB, typename PtrT>
+__global__ void __launch_bounds__(NT, MINB)
+stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const int num_tiles, const int tiles_per_cta) {
+    using T = StreamTiling<W, NT>;
+    constexpr int kCap = T::kCap, kPitch = T::kPitch;
+    constexpr int kRows = (T::ng + 1 + NT - 1) / NT;   // row pointers per thread, first tile of a run
+    constexpr int kNew = (T::tile_out + 1 + NT - 1) / NT;  // row pointers per thread, later tiles
+    constexpr int kCpRows = (T::ng + 2 + NT - 1) / NT;  // contig slice entries per thread
+    static_assert(kNew <= kRows, "tile geometry");
+    const CsrDev &csr = args.csr;
+    const T tl(args.model.A);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t A = (uint32_t)args.model.A;
+    const float m01 = args.model.m01, m10 = args.model.m10, m11 = args.model.m11;
+    const float clampv = args.model.clamp;
+    const float fx_inv = __int_as_float((127 - args.model.fx_bits) << 23);  // 2^-fx_bits
+    const int fx_nsafe = args.model.fx_nsafe;
+    const int step = args.step;
+    const int G = (int)csr.G;
+
+    extern __shared__ __align__(16) float smem[];
+    int *sTab = reinterpret_cast<int *>(smem);
+    int32_t *sIdx = reinterpret_cast<int32_t *>(smem + tl.off_idx);
+    float *sPool = smem + tl.off_pool;
+    float *sU0 = smem + tl.off_u0;  // sU0[j] = u of local gene j
+    float *sU1 = smem + tl.off_u1;  // sU1[j] = u of local gene j + 1 (so odd pairs are 8-byte aligned too)
+    float *sQ = smem + tl.off_q;    // odds of genes of padded short contigs
+    int *sP = reinterpret_cast<int *>(smem + tl.off_sp);   // staged-range coordinates of the new genes' rows
+    int *sCp = reinterpret_cast<int *>(smem + tl.off_cp);  // contig_ptr slice in local gene coordinates
+    unsigned char *sStat = reinterpret_cast<unsigned char *>(smem + tl.off_stat);
+    __shared__ __align__(8) uint64_t sBar;
+    __shared__ int64_t sCursor;
+    __shared__ int sShort;
+
+    const int tile_begin = blockIdx.x * tiles_per_cta;
+    const int tile_end = min(num_tiles, tile_begin + tiles_per_cta);
+    if (tile_begin >= tile_end) return;
+    const bool prof_on = args.prof != nullptr;
+    long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_last = prof_on ? clock64() : 0;
+
+    for (int a = tid; a <= (int)A; a += NT) sTab[a] = __ldg(args.model.table_fx + a);
+    if (tid == 0) {
+        mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t bar_parity = 0;
+
+    // ---- prologue: ranges of the first tile, its first staging round, its contig cursor
+    int ga, gb;
+    new_gene_range<W, NT>(tile_begin, true, G, ga, gb);
+    int64_t pa = (int64_t)__ldg(gene_ptr + ga), pb = (int64_t)__ldg(gene_ptr + gb);
+    __syncthreads();  // barrier initialised
+    if (tid == 0) {
+        const int64_t a0 = pa & ~(int64_t)3;
+        const uint32_t bytes = round_bytes<kCap>(pb - a0);
+        if (bytes) {
+            mbar_expect_tx(&sBar, bytes);
+            tma_load_1d(sIdx, csr.attr_idx + a0, bytes, &sBar);
+        } else {
+            mbar_arrive(&sBar);
+        }
+    }
+    if (warp == 0) {
+        const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
+        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0, lane);
+        if (lane == 0) sCursor = c;
+    }
+    // row pointers of the new genes, prefetched one tile ahead in registers
+    PtrT rowreg[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int t = tid + r * NT;
+        rowreg[r] = t <= gb - ga ? __ldg(gene_ptr + ga + t) : 0;
+    }
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const bool first = tile == tile_begin;
+        const int T0 = tile * T::tile_out;
+        const int Gs = T0 - T::lo;  // global index of local gene 0 (negative only for tile 0)
+        const int nout = min(G - T0, T::tile_out);
+        const int nn = gb - ga;     // new genes this tile
+        const int jn0 = ga - Gs;    // local index of the first new gene
+        const int jlo = max(0, -Gs);           // first existing local gene
+        const int jhi = min(T::ng, G - Gs);    // one past the last existing local gene
+        const int64_t a0 = pa & ~(int64_t)3;
+        const int total = (int)(pb - a0);  // staged-range length (ids), counted from the aligned start
+        const bool has_next = tile + 1 < tile_end;
+
+        GCRF_MARK(8);
+        __syncthreads();  // previous tile is done with sP / sCp / sPool; sCursor is written
+        if (tid == 0) sShort = 0;
+        // ---- A. row pointers of the new genes -> staged-range coordinates.  Row 0 starts at 0 so that the
+        //         (at most 3) ids in front of the aligned start fold into it — they are masked to -1 below.
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            if (r < kNew || first) {
+                const int t = tid + r * NT;
+                if (t <= nn) sP[t] = t == 0 ? 0 : (int)((int64_t)rowreg[r] - a0);
+            }
+        }
+        // ---- B. loads consumed later in the tile: contig slice, next tile's ranges and row pointers
+        const int64_t c_first = sCursor;
+        int cpreg[kCpRows];
+#pragma unroll
+        for (int r = 0; r < kCpRows; ++r) {
+            const int k = tid + r * NT;
+            const int64_t c = c_first + k;
+            cpreg[r] = (k <= T::ng + 1 && c <= csr.C) ? __ldg(csr.contig_ptr + c) - Gs : INT_MAX;
+        }
+        int nga = 0, ngb = 0;
+        int64_t npa = 0, npb = 0;
+        PtrT nrow[kNew];
+        if (has_next) {
+            new_gene_range<W, NT>(tile + 1, false, G, nga, ngb);
+            npa = (int64_t)__ldg(gene_ptr + nga);
+            npb = (int64_t)__ldg(gene_ptr + ngb);
+#pragma unroll
+            for (int r = 0; r < kNew; ++r) {
+                const int t = tid + r * NT;
+                nrow[r] = t <= ngb - nga ? __ldg(gene_ptr + nga + t) : 0;
+            }
+        }
+        // ring: carry the odds of the genes shared with the previous tile
+        float carry0 = 0.f, carry1 = 0.f;
+        if (!first && tid < T::keep) {
+            carry0 = sU0[tid + T::tile_out];
+            carry1 = sU1[tid + T::tile_out];
+        }
+        __syncthreads();
+        if (!first && tid < T::keep) {
+            sU0[tid] = carry0;
+            if (tid < T::keep - 1) sU1[tid] = carry1;
+        }
+        GCRF_MARK(0);
+
+        // ---- C. gather: staged ids -> per-row fixed-point sums
+        int gsum[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) gsum[r] = 0;
+        for (int cb = 0; cb < total || cb == 0; cb += kCap) {
+            if (cb > 0) {  // rare: more ids than one staging round holds — fetch the next round now
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t bytes = round_bytes<kCap>(total - cb);
+                    mbar_expect_tx(&sBar, bytes);
+                    tma_load_1d(sIdx, csr.attr_idx + a0 + cb, bytes, &sBar);
+                }
+            }
+            mbar_wait(&sBar, bar_parity);
+            bar_parity ^= 1;
+            if (cb == 0 && tid < (int)(pa - a0)) sIdx[tid] = -1;  // ids in front of the first new row
+            __syncthreads();
+            GCRF_MARK(1);
+            const int hi = min(total, cb + kCap);
+            // walk: ids -> running prefix of their fixed-point deltas, in place
+            {
+                const int x0 = cb + tid * kWalk;
+                int4 *v = reinterpret_cast<int4 *>(sIdx + tid * kWalk);
+                int run = 0;
+                if (x0 + kWalk <= hi) {
+#pragma unroll
+                    for (int i = 0; i < kWalk / 4; ++i) {
+                        int4 id = v[i];
+                        run += lookup(sTab, id.x, A); id.x = run;
+                        run += lookup(sTab, id.y, A); id.y = run;
+                        run += lookup(sTab, id.z, A); id.z = run;
+                        run += lookup(sTab, id.w, A); id.w = run;
+                        v[i] = id;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; x0 + 4 * i < hi; ++i) {
+                        int4 id = v[i];
+                        run += lookup(sTab, id.x, A); id.x = run;
+                        run += lookup(sTab, id.y, A); id.y = run;
+                        run += lookup(sTab, id.z, A); id.z = run;
+                        run += lookup(sTab, id.w, A); id.w = run;
+                        v[i] = id;
+                    }
+                }
+            }
+            __syncthreads();
+            GCRF_MARK(2);
+            // rows: prefix differences, plus the totals of the threads a row runs through
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (r < kNew || first) {
+                    const int t = tid + r * NT;
+                    if (t < nn) {
+                        const int s = max(sP[t], cb) - cb, e = min(sP[t + 1], hi) - cb;  // round-local [s, e)
+                        if (e > s) {
+                            const int q0 = walk_thread(s), q1 = walk_thread(e - 1);
+                            int v = sIdx[e - 1];
+                            if (s != q0 * kWalk) v -= sIdx[s - 1];
+                            if (q1 > q0) {
+                                v += sIdx[(q0 + 1) * kWalk - 1];
+#pragma unroll 1
+                                for (int q = q0 + 2; q <= q1; ++q) v += sIdx[q * kWalk - 1];  // rows > 52 ids
+                            }
+                            gsum[r] += v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // sIdx free again
+        GCRF_MARK(3);
+        // ---- stage the next tile's ids while this tile's dynamic programme runs
+        if (has_next && tid == 0) {
+            const int64_t na0 = npa & ~(int64_t)3;
+            const uint32_t bytes = round_bytes<kCap>(npb - na0);
+            if (bytes) {
+                mbar_expect_tx(&sBar, bytes);
+                tma_load_1d(sIdx, csr.attr_idx + na0, bytes, &sBar);
+            } else {
+                mbar_arrive(&sBar);
+            }
+        }
+
+        // ---- D. unary odds of the new genes
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            if (r < kNew || first) {
+                const int t = tid + r * NT;
+                if (t < nn) {
+                    float delta = (float)gsum[r] * fx_inv;
+                    if (sP[t + 1] - sP[t] >= fx_nsafe) {
+                        // a row this long could wrap the int32 sum: float sum straight from global memory
+                        const int64_t rb = (int64_t)__ldg(gene_ptr + ga + t), re = (int64_t)__ldg(gene_ptr + ga + t + 1);
+                        delta = 0.f;
+                        for (int64_t p = rb; p < re; ++p)
+                            delta += __ldg(args.model.table + min((uint32_t)__ldg(csr.attr_idx + p), A));
+                    }
+                    const float u = exp_fast(fminf(fmaxf(delta, -clampv), clampv));
+                    const int j = jn0 + t;
+                    sU0[j] = u;
+                    if (j >= 1) sU1[j - 1] = u;
+                }
+            }
+        }
+        if (jlo > 0 || jhi < T::ng) {
+            // local genes that do not exist (before gene 0 / after gene G-1) are neutral: u = 1
+            for (int j = tid; j < T::ng + 1; j += NT) {
+                if (j < jlo || j >= jhi) {
+                    sU0[j] = 1.0f;
+                    if (j >= 1) sU1[j - 1] = 1.0f;
+                }
+            }
+        }
+        // contig slice -> shared
+#pragma unroll
+        for (int r = 0; r < kCpRows; ++r) {
+            const int k = tid + r * NT;
+            if (k <= T::ng + 1) sCp[k] = cpreg[r];
+        }
+        __syncthreads();
+        GCRF_MARK(4);
+
+        // ---- does the tile hold a contig shorter than the window?  (CTA-uniform; rare on long contigs)
+        //      and how many contigs start inside it (bounds every later contig search)
+#pragma unroll
+        for (int r = 0; r < kCpRows; ++r) {
+            const int k = tid + r * NT;
+            if (k <= T::ng) {
+                const int a = sCp[k], b = sCp[k + 1];
+                if (a < jhi && b > jlo && b != INT_MAX && b - a < W) sShort = 1;
+                // cursor of the next tile: contig containing its first staged gene (local gene tile_out)
+                if (has_next && a <= T::tile_out && T::tile_out < b) sCursor = c_first + k;
+            }
+        }
+        // contig starts are a prefix of the slice: counting them among the first NT entries is exact unless all
+        // of those are starts (a tile full of 1-2 gene contigs), in which case the search stays unbounded
+        int kt = __syncthreads_count(tid >= 1 && sCp[tid] < T::ng);
+        if (kt >= NT - 1) kt = T::ng;
+        const bool has_short = sShort != 0;
+        if (has_short) {
+            // per staged gene: status (1 = padded short contig, 2 = skipped short contig) and the padded windows
+#pragma unroll 1
+            for (int j = tid; j < T::ng; j += NT) {
+                unsigned char stat = 0;
+                if (j >= jlo && j < jhi) {
+                    const int k = find_slice_contig(sCp, j, kt);
+                    const int c0 = sCp[k], n = sCp[k + 1] - c0;
+                    if (n < W) {
+                        stat = args.pad ? 1 : 2;  // pad = 0: :228-234, the contig's genes keep "no probability"
+                        // owner of the padded window: the contig's first gene — always staged when one of its
+                        // genes is an output gene (c0 >= j - (W-2) >= 2 for j >= lo)
+                        if (args.pad && j == c0 && j < T::lo + nout) padded_window<W>(sU0, sQ, j, n, m01, m10, m11);
+                    }
+                }
+                sStat[j] = stat;
+            }
+            __syncthreads();
+        }
+        GCRF_MARK(5);
+
+        // ---- E. two adjacent windows per thread, packed f32x2
+        {
+            const int b0 = 2 * tid;
+            // contig of slot b0 (or of the first existing gene, for the slots in front of gene 0)
+            float va = 0.f, vb = 0.f;
+            if (b0 + 1 >= jlo && b0 < jhi) {
+                const int js = max(b0, jlo);
+                int k = 0;
+                if (kt <= 4) {
+                    // few contigs start inside the tile (the usual case): count the starts at or before js
+#pragma unroll
+                    for (int i = 1; i <= 4; ++i) k += (i <= kt && sCp[i] <= js) ? 1 : 0;
+                } else {
+                    k = find_slice_contig(sCp, js, kt);
+                }
+                int c0 = sCp[k], c1 = sCp[k + 1];
+                if (b0 >= jlo) va = (c1 - c0 >= W && b0 <= c1 - W && (step == 1 || (b0 - c0) % step == 0)) ? 1.f : 0.f;
+                const int b1 = b0 + 1;
+                if (b1 >= c1) {  // the second slot opens the next contig
+                    c0 = c1;
+                    c1 = sCp[k + 2];
+                }
+                if (b1 < jhi) vb = (c1 - c0 >= W && b1 <= c1 - W && (step == 1 || (b1 - c0) % step == 0)) ? 1.f : 0.f;
+            }
+            if (va + vb > 0.f) {
+                auto upair = [&](int k) -> float2 {
+                    return (k & 1) ? *reinterpret_cast<const float2 *>(&sU1[b0 + k - 1])
+                                   : *reinterpret_cast<const float2 *>(&sU0[b0 + k]);
+                };
+                const float2 M01 = make_float2(m01 * va, m01 * vb);  // masked: an invalid slot keeps odds == 0
+                const float2 M10 = make_float2(m10, m10), M11 = make_float2(m11, m11), ONE = make_float2(1.f, 1.f);
+                const float2 B01 = make_float2(m01, m01);
+                // The forward chain R_k (odds of alpha) and the backward chain S_k (odds of beta) are independent:
+                // run them side by side, first halves stored, second halves combined with the stored other half.
+                constexpr int H = W / 2;  // positions [0, H) meet positions [H, W)
+                static_assert(W % 2 == 0 && W >= 4, "packed DP assumes an even window");
+                float2 ra[H], sb[H];      // ra[k] = R_k for k < H;  sb[i] = S_{H+i}
+                auto fwd = [&](float2 R, int k) -> float2 {
+                    const float2 num = __ffma2_rn(R, M11, M01);
+                    const float2 den = __ffma2_rn(R, M10, ONE);
+                    const float2 inv = make_float2(rcp_fast(den.x), rcp_fast(den.y));
+                    return __fmul2_rn(__fmul2_rn(num, upair(k)), inv);
+                };
+                auto bwd = [&](float2 S, int k) -> float2 {  // S_{k+1} -> S_k
+                    const float2 Wv = __fmul2_rn(upair(k + 1), S);
+                    const float2 num = __ffma2_rn(Wv, M11, M10);
+                    const float2 den = __ffma2_rn(Wv, B01, ONE);
+                    const float2 inv = make_float2(rcp_fast(den.x), rcp_fast(den.y));
+                    return __fmul2_rn(num, inv);
+                };
+                float2 R = __fmul2_rn(upair(0), make_float2(va, vb));
+                float2 S = ONE;
+                ra[0] = R;
+                sb[H - 1] = S;
+#pragma unroll
+                for (int k = 1; k < H; ++k) {
+                    R = fwd(R, k);
+                    ra[k] = R;
+                    S = bwd(S, W - 1 - k);
+                    sb[H - 1 - k] = S;
+                }
+                // second halves: Q_k = R_k S_k upward from H, downward from H-1; m[j] = max(q_a[j], q_b[j-1])
+                R = fwd(R, H);
+                S = bwd(S, H - 1);
+                float2 Qup = __fmul2_rn(R, sb[0]);       // Q_H
+                float2 Qdn = __fmul2_rn(ra[H - 1], S);   // Q_{H-1}
+                sPool[H * kPitch + tid] = fmaxf(Qup.x, Qdn.y);
+#pragma unroll
+                for (int i = 1; i < H; ++i) {
+                    R = fwd(R, H + i);
+                    const float2 Qu = __fmul2_rn(R, sb[i]);           // Q_{H+i}
+                    sPool[(H + i) * kPitch + tid] = fmaxf(Qu.x, Qup.y);
+                    Qup = Qu;
+                    S = bwd(S, H - 1 - i);
+                    const float2 Qd = __fmul2_rn(ra[H - 1 - i], S);   // Q_{H-1-i}
+                    sPool[(H - i) * kPitch + tid] = fmaxf(Qdn.x, Qd.y);
+                    Qdn = Qd;
+                }
+                sPool[W * kPitch + tid] = Qup.y;  // m[W] = q_b[W-1]
+                sPool[tid] = Qdn.x;               // m[0] = q_a[0]
+            } else {
+#pragma unroll
+                for (int k = 0; k <= W; ++k) sPool[k * kPitch + tid] = 0.f;
+            }
+        }
+        __syncthreads();
+        GCRF_MARK(6);
+
+        // ---- F. two output genes per thread: max over the covering windows, odds -> probability
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int g = T::lo + tid + rep * NT;  // local gene
+            if (g < T::lo + nout) {
+                const int stat = has_short ? (int)sStat[g] : 0;
+                float q = 0.f;
+                if (stat == 0) {
+                    // rows j = par, par+2, ... of column (g-j)/2: a constant stride of 2*pitch-1 words
+                    const int par = g & 1;
+                    const float *col = sPool + par * kPitch + ((g - par) >> 1);
+#pragma unroll
+                    for (int i = 0; 2 * i < W; ++i) q = fmaxf(q, col[i * (2 * kPitch - 1)]);
+                    if (!par || (W & 1)) q = fmaxf(q, col[((W - par) / 2) * (2 * kPitch - 1)]);
+                } else if (stat == 1) {
+                    q = sQ[g];
+                }
+                float p = q * rcp_fast(1.0f + q);
+                if (stat == 2) p = __int_as_float(0x7fc00000);
+                const int gg = Gs + g;
+                if (args.out_f32) static_cast<float *>(args.out)[gg] = p;
+                else static_cast<double *>(args.out)[gg] = (double)p;
+            }
+        }
+        GCRF_MARK(7);
+
+        // rotate the prefetched ranges
+        ga = nga; gb = ngb; pa = npa; pb = npb;
+#pragma unroll
+        for (int r = 0; r < kNew; ++r) rowreg[r] = nrow[r];
+    }
+    if (prof_on && tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) atomicAdd(args.prof + k, (unsigned long long)prof_acc[k]);
+        atomicAdd(args.prof + 15, 1ull);
+    }
+}
+
+template <int W, int NT, int MINB, typename PtrT>
+cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
+    const StreamTiling<W, NT> tl(A);
+    *bytes = tl.bytes();
+    auto kernel = stream_kernel<W, NT, MINB, PtrT>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.bytes());
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, NT, tl.bytes());
+}
+
+// CTA shape of the streaming kernel: GCRF_STREAM_THREADS=128|256 overrides the default (tuning knob).
+int stream_threads() {
+    const char *env = getenv("GCRF_STREAM_THREADS");
+    if (env && atoi(env) == 256) return 256;
+    if (env && atoi(env) == 128) return 128;
+    return 128;
+}
+
+}  // namespace
+
+bool stream_supported(const WindowedArgs &args) {
+    if (args.window != 20) return false;
+    const StreamTiling<20, 256> tl(args.model.A);
+    if (tl.bytes() > 110 * 1024) return false;
+    // tile arithmetic is 32-bit: G + one tile of slack must fit
+    return args.csr.G < 0x7fff0000;
+}
+
+cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
+    int per_sm = 0;
+    size_t bytes = 0;
+    const int nt = stream_threads();
+    const bool p64 = args.csr.gene_ptr64 != nullptr;
+    cudaError_t err;
+    if (nt == 256) err = p64 ? configure_stream<20, 256, 2, int64_t>(args.model.A, &per_sm, &bytes)
+                             : configure_stream<20, 256, 2, int32_t>(args.model.A, &per_sm, &bytes);
+    else err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &per_sm, &bytes)
+                   : configure_stream<20, 128, 4, int32_t>(args.model.A, &per_sm, &bytes);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    plan->threads = nt;
+    plan->tile_out = nt == 256 ? StreamTiling<20, 256>::tile_out : StreamTiling<20, 128>::tile_out;
+    plan->chunk = nt * kWalk;
+    plan->smem_bytes = bytes;
+    plan->num_tiles = (args.csr.G + plan->tile_out - 1) / plan->tile_out;
+    plan->ctas_per_sm = per_sm;
+    int64_t grid = (int64_t)num_sms * per_sm;
+    if (grid > plan->num_tiles) grid = plan->num_tiles;
+    if (grid < 1) grid = 1;
+    plan->tiles_per_cta = (int)((plan->num_tiles + grid - 1) / grid);
+    // drop CTAs that would get no tile (the last ones when tiles_per_cta rounds up)
+    plan->grid = (int)((plan->num_tiles + plan->tiles_per_cta - 1) / plan->tiles_per_cta);
+    return cudaSuccess;
+}
+
+cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches) {
+    if (args.csr.G <= 0) return cudaSuccess;
+    const int nt_ = (int)plan.num_tiles, tpc = plan.tiles_per_cta;
+    const bool p64 = args.csr.gene_ptr64 != nullptr;
+    if (plan.threads == 256) {
+        if (p64) stream_kernel<20, 256, 2, int64_t><<<plan.grid, 256, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
+        else stream_kernel<20, 256, 2, int32_t><<<plan.grid, 256, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
+    } else {
+        if (p64) stream_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
+        else stream_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
+    }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace gcrf

@@ -67,6 +67,13 @@ __device__ __forceinline__ int4 ld_stream_v4(const int32_t *p) {
     return r;
 }
 
+// a * (1/b) with one MUFU.RCP; operands here are positive and far from the FP32 range limits
+__device__ __forceinline__ float fast_div(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
+}
+
 __device__ __forceinline__ float lookup(const float *sTab, int32_t id, uint32_t A) {
     return sTab[min((uint32_t)id, A)];  // ids outside [0, A) (e.g. -1) hit the zero slot A
 }
@@ -110,7 +117,7 @@ __device__ __forceinline__ void dp_window(const float *__restrict__ sU, float *_
         for (int k = 1; k < WT; ++k) {
             const float u = unary(k);
             const float num = fmaf(r, m11, m01), den = fmaf(r, m10, 1.0f);
-            r = __fdividef(num * u, den);
+            r = fast_div(num * u, den);
             ra[k] = r;
         }
         float s = 1.0f;
@@ -118,7 +125,7 @@ __device__ __forceinline__ void dp_window(const float *__restrict__ sU, float *_
 #pragma unroll
         for (int k = WT - 2; k >= 0; --k) {
             const float w = unary(k + 1) * s;
-            s = __fdividef(fmaf(w, m11, m10), fmaf(w, m01, 1.0f));
+            s = fast_div(fmaf(w, m11, m10), fmaf(w, m01, 1.0f));
             pool[k * kThreads + tid] = ra[k] * s;
         }
     } else {
@@ -127,13 +134,13 @@ __device__ __forceinline__ void dp_window(const float *__restrict__ sU, float *_
         for (int k = 1; k < W; ++k) {
             const float u = unary(k);
             const float num = fmaf(r, m11, m01), den = fmaf(r, m10, 1.0f);
-            r = __fdividef(num * u, den);
+            r = fast_div(num * u, den);
             pool[k * kThreads + tid] = r;
         }
         float s = 1.0f;
         for (int k = W - 2; k >= 0; --k) {
             const float w = unary(k + 1) * s;
-            s = __fdividef(fmaf(w, m11, m10), fmaf(w, m01, 1.0f));
+            s = fast_div(fmaf(w, m11, m10), fmaf(w, m01, 1.0f));
             pool[k * kThreads + tid] *= s;
         }
     }
@@ -166,15 +173,14 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
     int64_t tile_end = tile_begin + tiles_per_cta;
     if (tile_end > num_tiles) tile_end = num_tiles;
 
+    const int G = (int)csr.G;  // G < 2^31 (checked on the host): tile arithmetic stays 32-bit
     int64_t c_first = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-        const int64_t T0 = tile * tl.tile_out;
-        const int lo = (int)(T0 < W - 1 ? T0 : W - 1);  // halo genes in front of the tile
-        const int64_t Gs = T0 - lo;                     // first gene staged
-        const int nout = (int)((csr.G - T0) < tl.tile_out ? (csr.G - T0) : tl.tile_out);
-        int64_t ngt64 = (int64_t)lo + nout + W - 1;     // genes staged: halo + tile + halo
-        if (ngt64 > csr.G - Gs) ngt64 = csr.G - Gs;
-        const int ngt = (int)ngt64;
+        const int T0 = (int)tile * tl.tile_out;
+        const int lo = T0 < W - 1 ? T0 : W - 1;  // halo genes in front of the tile
+        const int Gs = T0 - lo;                  // first gene staged
+        const int nout = min(G - T0, tl.tile_out);
+        const int ngt = min(lo + nout + W - 1, G - Gs);  // genes staged: halo + tile + halo
 
         // ---- A. gene_ptr slice, rebased to the first attribute of the tile
         const int64_t p0 = load_gene_ptr(csr, Gs);
@@ -191,7 +197,7 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
         c_first = sCursor;
         for (int k = tid; k <= ngt + 1; k += kThreads) {
             const int64_t c = c_first + k;
-            sCp[k] = c <= csr.C ? (int)((int64_t)__ldg(csr.contig_ptr + c) - Gs) : INT_MAX;
+            sCp[k] = c <= csr.C ? __ldg(csr.contig_ptr + c) - Gs : INT_MAX;
         }
         __syncthreads();  // sTab, sPtr, sCp visible
 
@@ -212,46 +218,57 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
         }
 
         // ---- C. gather: per-gene sums of delta over the tile's attribute ids
-        const int64_t p1 = p0 + sPtr[ngt];
+        const int tile_nnz = sPtr[ngt];
         const int j1 = tid + kThreads;  // second gene owned by this thread (ng_max < 2*threads)
         float acc0 = 0.0f, acc1 = 0.0f;
-        if (p1 > p0) {
-            const int64_t a0 = p0 & ~(int64_t)3;  // attr_idx is 16-byte aligned (checked on host)
-            for (int64_t cb = a0; cb < p1; cb += kChunk) {
-                int64_t span = p1 - cb;
-                if (span > kChunk) span = kChunk;
-                const int nvec = (int)((span + 3) >> 2);
-                for (int v = tid; v < nvec; v += kThreads) {
-                    const int64_t e = cb + 4 * (int64_t)v;
-                    int4 id;
-                    if (e + 4 <= csr.nnz) {
-                        id = ld_stream_v4(csr.attr_idx + e);
-                    } else {
-                        id.x = e + 0 < csr.nnz ? __ldg(csr.attr_idx + e + 0) : -1;
-                        id.y = e + 1 < csr.nnz ? __ldg(csr.attr_idx + e + 1) : -1;
-                        id.z = e + 2 < csr.nnz ? __ldg(csr.attr_idx + e + 2) : -1;
-                        id.w = -1;
+        if (tile_nnz > 0) {
+            const int mis = (int)(p0 & 3);  // attr_idx is 16-byte aligned (checked on host): start on a vector
+            const int32_t *src = csr.attr_idx + (p0 - mis);
+            const int64_t avail = csr.nnz - (p0 - mis);  // elements readable from src
+            const int total = tile_nnz + mis;            // elements to stage, counted from src
+            for (int cb = 0; cb < total; cb += kChunk) {
+                const int span = min(total - cb, kChunk);
+                const int nvec = (span + 3) >> 2;
+                const int64_t safe64 = (avail - cb) >> 2;  // full vectors inside attr_idx
+                const int safe = safe64 < nvec ? (int)safe64 : nvec;
+                constexpr int kBatch = 4;
+                for (int v0 = tid; v0 < nvec; v0 += kBatch * kThreads) {
+                    int4 id[kBatch];
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        const int v = v0 + b * kThreads;
+                        id[b] = make_int4(-1, -1, -1, -1);
+                        if (v < safe) {
+                            id[b] = ld_stream_v4(src + cb + 4 * v);
+                        } else if (v < nvec) {
+                            const int64_t e = (int64_t)cb + 4 * v;
+                            if (e + 0 < avail) id[b].x = __ldg(src + e + 0);
+                            if (e + 1 < avail) id[b].y = __ldg(src + e + 1);
+                            if (e + 2 < avail) id[b].z = __ldg(src + e + 2);
+                        }
                     }
-                    float4 d;
-                    d.x = lookup(sTab, id.x, A);
-                    d.y = lookup(sTab, id.y, A);
-                    d.z = lookup(sTab, id.z, A);
-                    d.w = lookup(sTab, id.w, A);
-                    reinterpret_cast<float4 *>(sBig)[v] = d;
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        const int v = v0 + b * kThreads;
+                        if (v < nvec) {
+                            float4 d;
+                            d.x = lookup(sTab, id[b].x, A);
+                            d.y = lookup(sTab, id[b].y, A);
+                            d.z = lookup(sTab, id[b].z, A);
+                            d.w = lookup(sTab, id[b].w, A);
+                            reinterpret_cast<float4 *>(sBig)[v] = d;
+                        }
+                    }
                 }
                 __syncthreads();
-                const int64_t cbase = cb - p0;  // chunk start relative to the tile's first attribute
+                const int cbase = cb - mis;  // chunk start relative to the tile's first attribute
                 if (tid < ngt) {
-                    int64_t s = sPtr[tid] - cbase, e = sPtr[tid + 1] - cbase;
-                    s = s < 0 ? 0 : s;
-                    e = e > kChunk ? kChunk : e;
-                    for (int p = (int)s; p < (int)e; ++p) acc0 += sBig[p];
+                    const int s = max(sPtr[tid] - cbase, 0), e = min(sPtr[tid + 1] - cbase, kChunk);
+                    for (int p = s; p < e; ++p) acc0 += sBig[p];
                 }
                 if (j1 < ngt) {
-                    int64_t s = sPtr[j1] - cbase, e = sPtr[j1 + 1] - cbase;
-                    s = s < 0 ? 0 : s;
-                    e = e > kChunk ? kChunk : e;
-                    for (int p = (int)s; p < (int)e; ++p) acc1 += sBig[p];
+                    const int s = max(sPtr[j1] - cbase, 0), e = min(sPtr[j1 + 1] - cbase, kChunk);
+                    for (int p = s; p < e; ++p) acc1 += sBig[p];
                 }
                 __syncthreads();
             }
@@ -308,20 +325,19 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
             } else {
                 skipped = true;  // :228-234 — contig too short and padding disabled
             }
-            float p = __fdividef(q, 1.0f + q);
+            float p = fast_div(q, 1.0f + q);
             if (skipped) p = __int_as_float(0x7fc00000);
-            const int64_t g = T0 + (tid - lo);
+            const int g = T0 + (tid - lo);
             if (args.out_f32) static_cast<float *>(args.out)[g] = p;
             else static_cast<double *>(args.out)[g] = (double)p;
         }
 
         // ---- cursor for the next tile: its first staged gene lies inside this tile's contig slice
         {
-            const int64_t T1 = T0 + tl.tile_out;
-            const int64_t next_gs = T1 - (T1 < W - 1 ? T1 : W - 1);
-            const int64_t x = next_gs - Gs;
+            const int T1 = T0 + tl.tile_out;
+            const int x = T1 - (W - 1) - Gs;  // first staged gene of the next tile, in this tile's coordinates
             for (int k = tid; k <= ngt; k += kThreads)
-                if ((int64_t)sCp[k] <= x && x < (int64_t)sCp[k + 1]) sCursor = c_first + k;
+                if (sCp[k] <= x && x < sCp[k + 1]) sCursor = c_first + k;
         }
         __syncthreads();  // sCursor written, pool and slices free for the next tile
     }

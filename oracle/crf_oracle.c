@@ -212,7 +212,8 @@ static int contig_windowed(const oracle_model *m, oracle_ctx *ctx, int64_t *item
         forward_backward(m, ctx, W);
         for (int32_t k = 0; k < W; ++k) {
             const double p = marginal(ctx, m->L, k, pos_label);
-            if (p > prob[i + k]) prob[i + k] = p; /* numpy.maximum(probabilities[win], marginals) */
+            /* numpy.maximum(probabilities[win], marginals): NaN propagates */
+            if (p > prob[i + k] || p != p) prob[i + k] = p;
         }
         ++*windows_done;
     }

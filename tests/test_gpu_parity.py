@@ -154,8 +154,13 @@ def test_extreme_unaries_stay_finite(engine, weights):
     from gecco_b200.synth import CsrBatch
 
     d = weights.state_w[:, 1] - weights.state_w[:, 0]
-    pos = numpy.flatnonzero(d > 1.0).astype(numpy.int32)
-    neg = numpy.flatnonzero(d < -1.0).astype(numpy.int32)
+    # strongest attributes whose summed |scores| stay below ~300, i.e. inside f64 exp() range (CRFsuite
+    # itself overflows beyond 709) but an order of magnitude past the device's FP32 clamp
+    order = numpy.argsort(-d)
+    pos = order[:int(numpy.searchsorted(numpy.cumsum(numpy.abs(weights.state_w[order]).max(axis=1)), 300.0))].astype(numpy.int32)
+    order = numpy.argsort(d)
+    neg = order[:int(numpy.searchsorted(numpy.cumsum(numpy.abs(weights.state_w[order]).max(axis=1)), 300.0))].astype(numpy.int32)
+    assert d[pos].sum() > 150 and d[neg].sum() < -60
     rows = []
     for k in range(60):
         rows.append(pos if k % 2 == 0 else neg)  # adversarial alternation
@@ -169,6 +174,27 @@ def test_extreme_unaries_stay_finite(engine, weights):
     got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
     assert numpy.isfinite(got).all()
     assert_close(got, want, what="extreme unaries")
+
+
+def test_rows_longer_than_the_fixed_point_guard(engine, weights):
+    """Genes with hundreds of distinct domains (the reference fixture has 834 raw rows in one gene): the
+    streaming kernel's wrapping int32 row sums hand such rows to its float path."""
+    from gecco_b200.synth import CsrBatch
+
+    rng = numpy.random.default_rng(9)
+    # weakest attributes first, so that even 1,200 of them keep |score| inside f64 exp() range (CRFsuite
+    # itself returns NaN beyond that)
+    weakest = numpy.argsort(numpy.abs(weights.state_w).max(axis=1))
+    rows = []
+    for k in range(300):
+        n = [0, 3, 25, 105, 106, 107, 150, 400, 834, 1200][k % 10]
+        pool = weakest[:max(n, 60) + 40] if n > 25 else numpy.arange(len(weights.attrs))
+        rows.append(numpy.sort(rng.choice(pool, size=n, replace=False)).astype(numpy.int32))
+    gene_ptr = numpy.cumsum([0] + [len(r) for r in rows]).astype(numpy.int32)
+    batch = CsrBatch(numpy.array([0, 120, 300], dtype=numpy.int32), gene_ptr, numpy.concatenate(rows))
+    want = oracle(weights, batch)
+    got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    assert_close(got, want, what="huge rows")
 
 
 def test_empty_batch_and_argument_errors(engine, weights):
