@@ -8,5 +8,6 @@ sm_100a kernels behind a C ABI, ``include/gecco_crf_b200.h``) and the drop-in ``
 __version__ = "0.1.0"
 
 from .model_io import CRFWeights, load_model  # noqa: F401
+from .crf import ClusterCRF  # noqa: F401
 
-__all__ = ["CRFWeights", "load_model", "__version__"]
+__all__ = ["ClusterCRF", "CRFWeights", "load_model", "__version__"]
