@@ -7,6 +7,7 @@ raise.  The CPU oracle under ``oracle/`` is test infrastructure and is never imp
 from __future__ import annotations
 
 import ctypes
+import os
 import pathlib
 from typing import Optional
 
@@ -48,7 +49,9 @@ class GcrfError(RuntimeError):
 
 
 def library_path() -> pathlib.Path:
-    return pathlib.Path(__file__).resolve().parent / "libgecco_crf_b200.so"
+    # GCRF_TUNING_LIB=1 selects the build with phase timers / ablation switches (tools/quick_kernel_time.py)
+    name = "libgecco_crf_b200_tuning.so" if os.environ.get("GCRF_TUNING_LIB") == "1" else "libgecco_crf_b200.so"
+    return pathlib.Path(__file__).resolve().parent / name
 
 
 _lib: Optional[ctypes.CDLL] = None

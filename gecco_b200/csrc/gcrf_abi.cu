@@ -233,7 +233,7 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
     int fx_bits = 24;
     while (fx_bits > 8 && maxabs * 64.0 * std::ldexp(1.0, fx_bits) >= 2147483647.0) --fx_bits;
     const double fx_one = std::ldexp(1.0, fx_bits);
-    std::vector<int32_t> table_fx((size_t)A + 1);
+    std::vector<int32_t> table_fx((size_t)A + 4, 0);  // padded: the kernel bulk-copies it in 16-byte units
     for (int32_t a = 0; a < A; ++a) table_fx[a] = (int32_t)std::llround(table64[a] * fx_one);
     table_fx[A] = 0;
     const double fx_nsafe_d = maxabs > 0 ? std::floor(2147483647.0 / (maxabs * fx_one + 1.0)) : 2147483647.0;
@@ -334,6 +334,10 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     args.step = step;
     args.pad = pad ? 1 : 0;
     args.prof = nullptr;
+    {
+        const char *skip = getenv("GCRF_DEBUG_SKIP");  // results are WRONG when set: timing experiments only
+        args.debug_skip = skip ? atoi(skip) : 0;
+    }
     // GCRF_PHASE_PROFILE=1: per-phase cycle counters of the streaming kernel, printed to stderr (tuning aid)
     const char *prof_env = getenv("GCRF_PHASE_PROFILE");
     const bool prof = prof_env && prof_env[0] == '1';
@@ -362,7 +366,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         unsigned long long h[16];
         GCRF_CUDA(cudaMemcpyAsync(h, args.prof, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
         GCRF_CUDA(cudaStreamSynchronize(m->stream));
-        static const char *names[10] = {"setup", "wait_ids", "walk", "row_sums", "unary", "contig", "dp", "pool", "out", "-"};
+        static const char *names[10] = {"setup", "wait_ids", "walk", "unary", "contig", "short", "dp", "pool", "loop", "-"};
         unsigned long long tot = 0;
         for (int k = 0; k < 9; ++k) tot += h[k];
         fprintf(stderr, "[gcrf phases] ctas=%llu grid=%d tiles/cta=%d:", h[15], plan.grid, plan.tiles_per_cta);

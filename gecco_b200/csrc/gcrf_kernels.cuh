@@ -39,6 +39,7 @@ struct WindowedArgs {
     int32_t out_f32;  // 0: double, 1: float
     int32_t window, step, pad;
     unsigned long long *prof;  // optional [16] cycle accumulators per kernel phase (nullptr = off); tuning aid
+    int32_t debug_skip;        // tuning aid (GCRF_DEBUG_SKIP): 1 = skip the walk, 2 = skip the DP, 4 = skip pool/output
 };
 
 // Geometry of the fused windowed kernel, fixed on the host so that tests can query it.

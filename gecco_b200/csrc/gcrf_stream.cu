@@ -1,28 +1,35 @@
 // gcrf_stream.cu — the fast fused kernel for compile-time window sizes (W = 20 is GECCO's shipped model).
 //
 // Same contract as gcrf_windowed.cu (reference loop: gecco/crf/__init__.py:209-258, tagger arithmetic
-// SURVEY.md Appendix B) but organised around what the ncu captures showed to bound it on B200:
-// shared-memory wavefronts, issue slots and dependent-latency chains at low occupancy — not DRAM.
+// SURVEY.md Appendix B) but organised around what the ncu captures and ablation runs showed to bound it on
+// B200: shared-memory wavefronts (table look-ups), per-thread bookkeeping instructions and dependent-latency
+// chains at 4 warps per scheduler — not DRAM.
 //
 //   * One persistent CTA walks a contiguous run of tiles.  Tile = 2*NT window slots, `tile_out` output
 //     genes.  The unary odds u_g of the 2W-1 genes shared with the previous tile stay in shared memory
-//     (a ring), so every attribute id is fetched and resolved exactly once per CTA run.
+//     (a ring; the run's very first halo is gathered in the prologue), so every attribute id is fetched
+//     and resolved exactly once per CTA run.
 //   * attr_idx of the tile's NEW genes is brought in by ONE bulk-async copy (TMA, cp.async.bulk +
 //     mbarrier) issued while the previous tile's dynamic programme runs: no load instructions, no
-//     registers, latency off the critical path (measured: < 3 % of CTA time spent waiting).
+//     registers, latency off the critical path (measured: < 5 % of CTA time spent waiting).
 //   * Segmented sums without any per-id boundary logic (a per-thread branch there diverges in every
 //     warp): thread t walks ids [K t, K t + K) of the staged range with 16-byte shared loads (K = 4*odd
 //     keeps them bank-conflict free), resolves each id through a FIXED-POINT delta table and overwrites
 //     it in place with the thread's running prefix sum.  A row sum is then a difference of prefixes
 //     (plus whole-thread totals when a row straddles threads) in wrapping int32 arithmetic: exact, and
-//     order-independent.  Rows with >= fx_nsafe ids could wrap and take a float path from global memory.
+//     order-independent.  Rows with >= fx_nsafe ids could wrap and take a float path from global memory;
+//     tiles whose ids do not fit one staging round take a direct row-per-thread path.
 //   * Dynamic programme on odds ratios, two adjacent windows per thread packed in f32x2 registers
-//     (FFMA2/FMUL2 halve the issue slots; MUFU.RCP stays scalar).  Each thread finds the contig of its
-//     own two window slots with one search.  Invalid window slots run with m01 and u_0 masked to zero,
-//     which pins their odds to exactly 0 — the neutral element of the max-pool — so the pool needs no
-//     range logic at all.
+//     (FFMA2/FMUL2 halve the issue slots; MUFU.RCP stays scalar), forward and backward chains advancing
+//     together.  Each thread finds the contig of its own two window slots.  Invalid window slots run with
+//     m01 and u_0 masked to zero, which pins their odds to exactly 0 — the neutral element of the
+//     max-pool — so the pool needs no range logic at all.
 //   * Padded short contigs (:216-227) and skipped ones (pad = 0) are handled by a slow path that a tile
 //     only enters when it actually holds a contig shorter than the window.
+//   * Three CTA barriers per tile.
+//
+// Build with -DGCRF_TUNING to compile the phase timers (GCRF_PHASE_PROFILE=1) and the ablation switches
+// (GCRF_DEBUG_SKIP) in; the production build carries neither.
 #include "gcrf_kernels.cuh"
 
 #include <climits>
@@ -39,12 +46,14 @@ __host__ __device__ constexpr int round_up4s(int x) { return (x + 3) & ~3; }
 template <int W, int NT>
 struct StreamTiling {
     static constexpr int kSlots = 2 * NT;          // window slots per tile
-    static constexpr int kCap = NT * kWalk;        // ids staged per round
+    static constexpr int kCap = NT * kWalk;        // ids staged per tile
     static constexpr int kPitch = NT + 16;         // pool pitch: odd and even genes land 16 banks apart
     static constexpr int lo = W;                   // local index of the first output gene
     static constexpr int tile_out = (kSlots - W) & ~3;
     static constexpr int ng = kSlots + W - 1;      // genes staged per tile
     static constexpr int keep = ng - tile_out;     // genes carried over from the previous tile
+    static_assert(tile_out + 1 <= 2 * NT, "two row pointers per thread must cover a tile's new genes");
+    static_assert(keep <= NT, "the ring carry is one gene per thread");
     int off_idx, off_pool, off_u0, off_u1, off_q, off_sp, off_cp, off_stat, words;
     __host__ __device__ explicit StreamTiling(int A) {
         int o = round_up4s(A + 1);
@@ -53,7 +62,7 @@ struct StreamTiling {
         off_u0 = o; o += round_up4s(ng + 2);
         off_u1 = o; o += round_up4s(ng + 2);
         off_q = o; o += round_up4s(ng + 2);
-        off_sp = o; o += round_up4s(ng + 3);
+        off_sp = o; o += round_up4s(tile_out + 3);
         off_cp = o; o += round_up4s(ng + 4);
         off_stat = o; o += round_up4s((ng + 8) / 4);
         words = o;
@@ -121,6 +130,21 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  : "memory");
 }
 
+// Stage ids [pa, pb) (from their 16-byte aligned start) if they fit one round; otherwise only arrive, and the
+// tile takes the direct path.
+template <int kCap>
+__device__ __forceinline__ void stage_ids(int32_t *sIdx, const int32_t *attr_idx, int64_t pa, int64_t pb, uint64_t *bar) {
+    const int64_t a0 = pa & ~(int64_t)3;
+    const int64_t total = pb - a0;
+    if (total > 0 && total <= kCap) {
+        const uint32_t bytes = (uint32_t)(4 * ((total + 3) & ~(int64_t)3));
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(sIdx, attr_idx + a0, bytes, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
 // Largest c in [0, C) with contig_ptr[c] <= g (g >= 0), one warp, 32 probes per round.
 __device__ int64_t warp_find_contig(const int32_t *contig_ptr, int64_t C, int64_t g, int lane) {
     int64_t lo = 0, hi = C;
@@ -145,6 +169,16 @@ __device__ __forceinline__ int find_slice_contig(const int *sCp, int j, int kmax
         if (sCp[mid] <= j) k = mid; else hi = mid;
     }
     return k;
+}
+
+// Unary odds of one gene straight from global memory (prologue halo, oversized tiles, very long rows).
+template <typename PtrT>
+__device__ __noinline__ float direct_unary(const PtrT *gene_ptr, const int32_t *attr_idx, const float *table, uint32_t A,
+                                           int g, float clampv) {
+    const int64_t rb = (int64_t)__ldg(gene_ptr + g), re = (int64_t)__ldg(gene_ptr + g + 1);
+    float delta = 0.f;
+    for (int64_t p = rb; p < re; ++p) delta += __ldg(table + min((uint32_t)__ldg(attr_idx + p), A));
+    return exp_fast(fminf(fmaxf(delta, -clampv), clampv));
 }
 
 // Window of a padded short contig (gecco/crf/__init__.py:216-227): n < W genes starting at local gene j,
@@ -174,24 +208,7 @@ __device__ __noinline__ void padded_window(const float *sU0, float *sQ, int j, i
     }
 }
 
-// bytes of one staging round of a range of `total` ids counted from its 16-byte aligned start
-template <int kCap>
-__device__ __forceinline__ uint32_t round_bytes(int64_t total) {
-    const int64_t padded = (total + 3) & ~(int64_t)3;
-    return (uint32_t)(4 * (padded < kCap ? padded : (int64_t)kCap));
-}
-
-// New genes of a tile: global genes [ga, gb).  The first tile of a CTA run stages everything it needs,
-// later tiles only the genes the previous tile did not cover.
-template <int W, int NT>
-__device__ __forceinline__ void new_gene_range(int tile, bool first, int G, int &ga, int &gb) {
-    using T = StreamTiling<W, NT>;
-    const int Gs = tile * T::tile_out - T::lo;
-    ga = max(0, min(G, Gs + (first ? 0 : T::keep)));
-    gb = max(0, min(G, Gs + T::ng));
-}
-
-// phase timing (tuning aid): thread 0 accumulates SM-clock cycles between marks when args.prof is set
+#ifdef GCRF_TUNING
 #define GCRF_MARK(slot)                                   \
     do {                                                  \
         if (prof_on && tid == 0) {                        \
@@ -200,19 +217,20 @@ __device__ __forceinline__ void new_gene_range(int tile, bool first, int G, int 
             prof_last = now__;                            \
         }                                                 \
     } while (0)
+#define GCRF_SKIP(bit) (args.debug_skip & (bit))
+#else
+#define GCRF_MARK(slot) do { } while (0)
+#define GCRF_SKIP(bit) false
+#endif
 
 template <int W, int NT, int MINB, typename PtrT>
 __global__ void __launch_bounds__(NT, MINB)
 stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const int num_tiles, const int tiles_per_cta) {
     using T = StreamTiling<W, NT>;
     constexpr int kCap = T::kCap, kPitch = T::kPitch;
-    constexpr int kRows = (T::ng + 1 + NT - 1) / NT;   // row pointers per thread, first tile of a run
-    constexpr int kNew = (T::tile_out + 1 + NT - 1) / NT;  // row pointers per thread, later tiles
-    constexpr int kCpRows = (T::ng + 2 + NT - 1) / NT;  // contig slice entries per thread
-    static_assert(kNew <= kRows, "tile geometry");
     const CsrDev &csr = args.csr;
     const T tl(args.model.A);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const uint32_t A = (uint32_t)args.model.A;
     const float m01 = args.model.m01, m10 = args.model.m10, m11 = args.model.m11;
     const float clampv = args.model.clamp;
@@ -231,215 +249,209 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
     int *sP = reinterpret_cast<int *>(smem + tl.off_sp);   // staged-range coordinates of the new genes' rows
     int *sCp = reinterpret_cast<int *>(smem + tl.off_cp);  // contig_ptr slice in local gene coordinates
     unsigned char *sStat = reinterpret_cast<unsigned char *>(smem + tl.off_stat);
-    __shared__ __align__(8) uint64_t sBar;
+    __shared__ __align__(8) uint64_t sBar, sBarTab;
     __shared__ int64_t sCursor;
     __shared__ int sShort;
 
     const int tile_begin = blockIdx.x * tiles_per_cta;
     const int tile_end = min(num_tiles, tile_begin + tiles_per_cta);
     if (tile_begin >= tile_end) return;
+#ifdef GCRF_TUNING
     const bool prof_on = args.prof != nullptr;
     long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_last = prof_on ? clock64() : 0;
+#endif
 
-    for (int a = tid; a <= (int)A; a += NT) sTab[a] = __ldg(args.model.table_fx + a);
+    // ---- prologue -------------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&sBar, 1);
+        mbar_init(&sBarTab, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // delta table -> shared in one bulk copy (a per-thread copy loop costs ~20 dependent global round trips);
+        // the device table is padded to a multiple of 16 bytes
+        const uint32_t tab_bytes = (uint32_t)(4 * round_up4s((int)A + 1));
+        mbar_expect_tx(&sBarTab, tab_bytes);
+        tma_load_1d(sTab, args.model.table_fx, tab_bytes, &sBarTab);
     }
-    uint32_t bar_parity = 0;
-
-    // ---- prologue: ranges of the first tile, its first staging round, its contig cursor
-    int ga, gb;
-    new_gene_range<W, NT>(tile_begin, true, G, ga, gb);
-    int64_t pa = (int64_t)__ldg(gene_ptr + ga), pb = (int64_t)__ldg(gene_ptr + gb);
-    __syncthreads();  // barrier initialised
-    if (tid == 0) {
-        const int64_t a0 = pa & ~(int64_t)3;
-        const uint32_t bytes = round_bytes<kCap>(pb - a0);
-        if (bytes) {
-            mbar_expect_tx(&sBar, bytes);
-            tma_load_1d(sIdx, csr.attr_idx + a0, bytes, &sBar);
-        } else {
-            mbar_arrive(&sBar);
+    if (tid < 32) {
+        const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
+        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0, tid);
+        if (tid == 0) sCursor = c;
+    }
+    // New genes of a tile = local genes [keep, ng).  The run's first halo [0, keep) is gathered right here into the
+    // slots the first tile's ring carry will read: its ids are one contiguous range, every thread resolves a
+    // strided share of it and adds the fixed-point deltas to its row's accumulator (integer atomics: exact).
+    const int Gs0 = tile_begin * T::tile_out - T::lo;
+    {
+        int *hrow = sP;                                   // keep + 1 row pointers, relative to the first one
+        int *hacc = reinterpret_cast<int *>(sPool);       // keep accumulators
+        const int h0 = max(0, min(G, Gs0)), h1 = max(0, min(G, Gs0 + T::keep));  // existing halo genes [h0, h1)
+        const int64_t hp0 = (int64_t)__ldg(gene_ptr + h0);
+        if (tid <= h1 - h0) hrow[tid] = (int)((int64_t)__ldg(gene_ptr + h0 + tid) - hp0);
+        if (tid < T::keep) hacc[tid] = 0;
+        __syncthreads();  // mbarriers initialised, row pointers, zeroed accumulators
+        mbar_wait(&sBarTab, 0);  // delta table has landed
+        const int hn = h1 - h0, hids = hn > 0 ? hrow[hn] : 0;
+        for (int x = tid; x < hids; x += NT) {
+            int row = 0, hi = hn;  // largest row with hrow[row] <= x
+            while (hi - row > 1) {
+                const int mid = (row + hi) >> 1;
+                if (hrow[mid] <= x) row = mid; else hi = mid;
+            }
+            atomicAdd(&hacc[row], lookup(sTab, __ldg(csr.attr_idx + hp0 + x), A));
+        }
+        __syncthreads();
+        if (tid < T::keep) {
+            const int g = Gs0 + tid;
+            float u = 1.0f;  // genes before gene 0 / after gene G-1 are neutral
+            if (g >= h0 && g < h1) {
+                const int r = g - h0;
+                u = hrow[r + 1] - hrow[r] < fx_nsafe
+                        ? exp_fast(fminf(fmaxf((float)hacc[r] * fx_inv, -clampv), clampv))
+                        : direct_unary(gene_ptr, csr.attr_idx, args.model.table, A, g, clampv);
+            }
+            sU0[T::tile_out + tid] = u;
+            if (tid >= 1) sU1[T::tile_out + tid - 1] = u;
         }
     }
-    if (warp == 0) {
-        const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
-        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0, lane);
-        if (lane == 0) sCursor = c;
-    }
-    // row pointers of the new genes, prefetched one tile ahead in registers
-    PtrT rowreg[kRows];
+    int ga = max(0, min(G, Gs0 + T::keep)), gb = max(0, min(G, Gs0 + T::ng));
+    int64_t pa = (int64_t)__ldg(gene_ptr + ga), pb = (int64_t)__ldg(gene_ptr + gb);
+    PtrT rowreg[2];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
+    for (int r = 0; r < 2; ++r) {
         const int t = tid + r * NT;
         rowreg[r] = t <= gb - ga ? __ldg(gene_ptr + ga + t) : 0;
     }
+    __syncthreads();  // mbarrier initialised, delta table staged, cursor and halo written
+    if (tid == 0) stage_ids<kCap>(sIdx, csr.attr_idx, pa, pb, &sBar);
+    uint32_t bar_parity = 0;
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const bool first = tile == tile_begin;
-        const int T0 = tile * T::tile_out;
-        const int Gs = T0 - T::lo;  // global index of local gene 0 (negative only for tile 0)
-        const int nout = min(G - T0, T::tile_out);
+        const int Gs = tile * T::tile_out - T::lo;  // global index of local gene 0 (negative only for tile 0)
+        const int nout = min(G - (Gs + T::lo), T::tile_out);
         const int nn = gb - ga;     // new genes this tile
-        const int jn0 = ga - Gs;    // local index of the first new gene
+        const int jn0 = ga - Gs;    // local index of the first new gene (= keep, except at the batch edges)
         const int jlo = max(0, -Gs);           // first existing local gene
         const int jhi = min(T::ng, G - Gs);    // one past the last existing local gene
         const int64_t a0 = pa & ~(int64_t)3;
-        const int total = (int)(pb - a0);  // staged-range length (ids), counted from the aligned start
+        const int64_t total64 = pb - a0;       // staged-range length (ids) from the aligned start
+        const bool staged = total64 <= kCap;   // CTA-uniform: the usual case
+        const int total = staged ? (int)total64 : 0;
         const bool has_next = tile + 1 < tile_end;
 
         GCRF_MARK(8);
-        __syncthreads();  // previous tile is done with sP / sCp / sPool; sCursor is written
+        // Three CTA barriers per tile: after the walk, after the unary odds (a counting barrier) and after the
+        // DP.  Everything written before the first one (sP, the ring carry, sShort, sCp) was last read before
+        // the previous tile's DP barrier or is read only by its writer.
         if (tid == 0) sShort = 0;
         // ---- A. row pointers of the new genes -> staged-range coordinates.  Row 0 starts at 0 so that the
         //         (at most 3) ids in front of the aligned start fold into it — they are masked to -1 below.
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            if (r < kNew || first) {
-                const int t = tid + r * NT;
-                if (t <= nn) sP[t] = t == 0 ? 0 : (int)((int64_t)rowreg[r] - a0);
-            }
+        for (int r = 0; r < 2; ++r) {
+            const int t = tid + r * NT;
+            if (t <= nn) sP[t] = t == 0 ? 0 : (int)((int64_t)rowreg[r] - a0);
         }
         // ---- B. loads consumed later in the tile: contig slice, next tile's ranges and row pointers
         const int64_t c_first = sCursor;
-        int cpreg[kCpRows];
-#pragma unroll
-        for (int r = 0; r < kCpRows; ++r) {
-            const int k = tid + r * NT;
-            const int64_t c = c_first + k;
-            cpreg[r] = (k <= T::ng + 1 && c <= csr.C) ? __ldg(csr.contig_ptr + c) - Gs : INT_MAX;
-        }
+        int cp0 = INT_MAX;
+        if (c_first + tid <= csr.C && !GCRF_SKIP(64)) cp0 = __ldg(csr.contig_ptr + c_first + tid) - Gs;
         int nga = 0, ngb = 0;
         int64_t npa = 0, npb = 0;
-        PtrT nrow[kNew];
-        if (has_next) {
-            new_gene_range<W, NT>(tile + 1, false, G, nga, ngb);
+        PtrT nrow[2] = {0, 0};
+        if (has_next && !GCRF_SKIP(128)) {
+            nga = max(0, min(G, Gs + T::tile_out + T::keep));
+            ngb = max(0, min(G, Gs + T::tile_out + T::ng));
             npa = (int64_t)__ldg(gene_ptr + nga);
             npb = (int64_t)__ldg(gene_ptr + ngb);
 #pragma unroll
-            for (int r = 0; r < kNew; ++r) {
+            for (int r = 0; r < 2; ++r) {
                 const int t = tid + r * NT;
                 nrow[r] = t <= ngb - nga ? __ldg(gene_ptr + nga + t) : 0;
             }
         }
-        // ring: carry the odds of the genes shared with the previous tile
-        float carry0 = 0.f, carry1 = 0.f;
-        if (!first && tid < T::keep) {
-            carry0 = sU0[tid + T::tile_out];
-            carry1 = sU1[tid + T::tile_out];
-        }
-        __syncthreads();
-        if (!first && tid < T::keep) {
-            sU0[tid] = carry0;
-            if (tid < T::keep - 1) sU1[tid] = carry1;
+        // ring: carry the odds of the genes shared with the previous tile; source [tile_out, tile_out+keep) and
+        // destination [0, keep) do not overlap
+        if (tid < T::keep) {
+            const float c0 = sU0[tid + T::tile_out];
+            sU0[tid] = c0;
+            if (tid >= 1) sU1[tid - 1] = c0;
         }
         GCRF_MARK(0);
 
         // ---- C. gather: staged ids -> per-row fixed-point sums
-        int gsum[kRows];
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) gsum[r] = 0;
-        for (int cb = 0; cb < total || cb == 0; cb += kCap) {
-            if (cb > 0) {  // rare: more ids than one staging round holds — fetch the next round now
-                __syncthreads();
-                if (tid == 0) {
-                    const uint32_t bytes = round_bytes<kCap>(total - cb);
-                    mbar_expect_tx(&sBar, bytes);
-                    tma_load_1d(sIdx, csr.attr_idx + a0 + cb, bytes, &sBar);
-                }
-            }
-            mbar_wait(&sBar, bar_parity);
-            bar_parity ^= 1;
-            if (cb == 0 && tid < (int)(pa - a0)) sIdx[tid] = -1;  // ids in front of the first new row
-            __syncthreads();
-            GCRF_MARK(1);
-            const int hi = min(total, cb + kCap);
+        if (!GCRF_SKIP(32)) mbar_wait(&sBar, bar_parity);
+        bar_parity ^= 1;
+        // ids in front of the first new row sit in thread 0's own walk range: no barrier needed
+        if (tid == 0 && staged)
+            for (int i = 0; i < (int)(pa - a0); ++i) sIdx[i] = -1;
+        // contig slice -> shared (loaded at the top of the tile; visible after the walk's barrier)
+        sCp[tid] = cp0;
+        if (tid == NT - 1) sCp[NT] = INT_MAX;  // sentinel unless the rest of the slice gets loaded below
+        GCRF_MARK(1);
+        if (!GCRF_SKIP(1)) {
             // walk: ids -> running prefix of their fixed-point deltas, in place
-            {
-                const int x0 = cb + tid * kWalk;
-                int4 *v = reinterpret_cast<int4 *>(sIdx + tid * kWalk);
-                int run = 0;
-                if (x0 + kWalk <= hi) {
+            const int x0 = tid * kWalk;
+            int4 *v = reinterpret_cast<int4 *>(sIdx + x0);
+            int run = 0;
+            if (x0 + kWalk <= total) {
 #pragma unroll
-                    for (int i = 0; i < kWalk / 4; ++i) {
-                        int4 id = v[i];
-                        run += lookup(sTab, id.x, A); id.x = run;
-                        run += lookup(sTab, id.y, A); id.y = run;
-                        run += lookup(sTab, id.z, A); id.z = run;
-                        run += lookup(sTab, id.w, A); id.w = run;
-                        v[i] = id;
-                    }
-                } else {
+                for (int i = 0; i < kWalk / 4; ++i) {
+                    int4 id = v[i];
+                    run += lookup(sTab, id.x, A); id.x = run;
+                    run += lookup(sTab, id.y, A); id.y = run;
+                    run += lookup(sTab, id.z, A); id.z = run;
+                    run += lookup(sTab, id.w, A); id.w = run;
+                    v[i] = id;
+                }
+            } else {
 #pragma unroll 1
-                    for (int i = 0; x0 + 4 * i < hi; ++i) {
-                        int4 id = v[i];
-                        run += lookup(sTab, id.x, A); id.x = run;
-                        run += lookup(sTab, id.y, A); id.y = run;
-                        run += lookup(sTab, id.z, A); id.z = run;
-                        run += lookup(sTab, id.w, A); id.w = run;
-                        v[i] = id;
-                    }
+                for (int i = 0; x0 + 4 * i < total; ++i) {
+                    int4 id = v[i];
+                    run += lookup(sTab, id.x, A); id.x = run;
+                    run += lookup(sTab, id.y, A); id.y = run;
+                    run += lookup(sTab, id.z, A); id.z = run;
+                    run += lookup(sTab, id.w, A); id.w = run;
+                    v[i] = id;
                 }
             }
+        }
+        // a tile that holds more contigs than one slice entry per thread covers (contigs of 1-2 genes): load the rest
+        const bool wide_slice = __syncthreads_or(tid == NT - 1 && cp0 < T::ng) != 0;
+        if (wide_slice) {
+            for (int k = NT + tid; k <= T::ng + 1; k += NT)
+                sCp[k] = c_first + k <= csr.C ? __ldg(csr.contig_ptr + c_first + k) - Gs : INT_MAX;
             __syncthreads();
-            GCRF_MARK(2);
-            // rows: prefix differences, plus the totals of the threads a row runs through
+        }
+        GCRF_MARK(2);
+
+        // ---- D. row sums -> unary odds of the new genes
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                if (r < kNew || first) {
-                    const int t = tid + r * NT;
-                    if (t < nn) {
-                        const int s = max(sP[t], cb) - cb, e = min(sP[t + 1], hi) - cb;  // round-local [s, e)
-                        if (e > s) {
-                            const int q0 = walk_thread(s), q1 = walk_thread(e - 1);
-                            int v = sIdx[e - 1];
-                            if (s != q0 * kWalk) v -= sIdx[s - 1];
-                            if (q1 > q0) {
-                                v += sIdx[(q0 + 1) * kWalk - 1];
+        for (int r = 0; r < 2; ++r) {
+            const int t = tid + r * NT;
+            if (t < nn && !GCRF_SKIP(8)) {
+                const int s = sP[t], e = sP[t + 1];
+                float u;
+                if (staged && e - s < fx_nsafe) {
+                    // prefix difference, plus the totals of the threads the row runs through
+                    int v = 0;
+                    if (e > s) {
+                        const int q0 = walk_thread(s), q1 = walk_thread(e - 1);
+                        v = sIdx[e - 1];
+                        if (s != q0 * kWalk) v -= sIdx[s - 1];
+                        if (q1 > q0) {
+                            v += sIdx[(q0 + 1) * kWalk - 1];
 #pragma unroll 1
-                                for (int q = q0 + 2; q <= q1; ++q) v += sIdx[q * kWalk - 1];  // rows > 52 ids
-                            }
-                            gsum[r] += v;
+                            for (int q = q0 + 2; q <= q1; ++q) v += sIdx[q * kWalk - 1];  // rows > 52 ids
                         }
                     }
+                    u = exp_fast(fminf(fmaxf((float)v * fx_inv, -clampv), clampv));
+                } else {
+                    // a row long enough to wrap the int32 sum, or a tile whose ids exceed one staging round
+                    u = direct_unary(gene_ptr, csr.attr_idx, args.model.table, A, ga + t, clampv);
                 }
-            }
-        }
-        __syncthreads();  // sIdx free again
-        GCRF_MARK(3);
-        // ---- stage the next tile's ids while this tile's dynamic programme runs
-        if (has_next && tid == 0) {
-            const int64_t na0 = npa & ~(int64_t)3;
-            const uint32_t bytes = round_bytes<kCap>(npb - na0);
-            if (bytes) {
-                mbar_expect_tx(&sBar, bytes);
-                tma_load_1d(sIdx, csr.attr_idx + na0, bytes, &sBar);
-            } else {
-                mbar_arrive(&sBar);
-            }
-        }
-
-        // ---- D. unary odds of the new genes
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            if (r < kNew || first) {
-                const int t = tid + r * NT;
-                if (t < nn) {
-                    float delta = (float)gsum[r] * fx_inv;
-                    if (sP[t + 1] - sP[t] >= fx_nsafe) {
-                        // a row this long could wrap the int32 sum: float sum straight from global memory
-                        const int64_t rb = (int64_t)__ldg(gene_ptr + ga + t), re = (int64_t)__ldg(gene_ptr + ga + t + 1);
-                        delta = 0.f;
-                        for (int64_t p = rb; p < re; ++p)
-                            delta += __ldg(args.model.table + min((uint32_t)__ldg(csr.attr_idx + p), A));
-                    }
-                    const float u = exp_fast(fminf(fmaxf(delta, -clampv), clampv));
-                    const int j = jn0 + t;
-                    sU0[j] = u;
-                    if (j >= 1) sU1[j - 1] = u;
-                }
+                const int j = jn0 + t;
+                sU0[j] = u;
+                if (j >= 1) sU1[j - 1] = u;
             }
         }
         if (jlo > 0 || jhi < T::ng) {
@@ -451,32 +463,24 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 }
             }
         }
-        // contig slice -> shared
-#pragma unroll
-        for (int r = 0; r < kCpRows; ++r) {
-            const int k = tid + r * NT;
-            if (k <= T::ng + 1) sCp[k] = cpreg[r];
-        }
-        __syncthreads();
-        GCRF_MARK(4);
+        GCRF_MARK(3);
 
-        // ---- does the tile hold a contig shorter than the window?  (CTA-uniform; rare on long contigs)
-        //      and how many contigs start inside it (bounds every later contig search)
-#pragma unroll
-        for (int r = 0; r < kCpRows; ++r) {
-            const int k = tid + r * NT;
-            if (k <= T::ng) {
-                const int a = sCp[k], b = sCp[k + 1];
-                if (a < jhi && b > jlo && b != INT_MAX && b - a < W) sShort = 1;
-                // cursor of the next tile: contig containing its first staged gene (local gene tile_out)
-                if (has_next && a <= T::tile_out && T::tile_out < b) sCursor = c_first + k;
-            }
+        // ---- does the tile hold a contig shorter than the window (CTA-uniform; rare on long contigs), which
+        //      contig holds the next tile's first staged gene, how many contigs start inside the tile
+        for (int k = tid; k <= (wide_slice ? T::ng : NT - 1); k += NT) {
+            const int a = sCp[k], b = sCp[k + 1];
+            if (a < jhi && b > jlo && b != INT_MAX && b - a < W) sShort = 1;
+            if (has_next && a <= T::tile_out && T::tile_out < b) sCursor = c_first + k;
         }
         // contig starts are a prefix of the slice: counting them among the first NT entries is exact unless all
-        // of those are starts (a tile full of 1-2 gene contigs), in which case the search stays unbounded
+        // of those are starts, in which case the searches below stay unbounded.  The barrier also publishes
+        // sU0/sU1 and retires the last readers of sIdx.
         int kt = __syncthreads_count(tid >= 1 && sCp[tid] < T::ng);
         if (kt >= NT - 1) kt = T::ng;
         const bool has_short = sShort != 0;
+        // ---- stage the next tile's ids while this tile's dynamic programme runs
+        if (has_next && tid == 0 && !GCRF_SKIP(32)) stage_ids<kCap>(sIdx, csr.attr_idx, npa, npb, &sBar);
+        GCRF_MARK(4);
         if (has_short) {
             // per staged gene: status (1 = padded short contig, 2 = skipped short contig) and the padded windows
 #pragma unroll 1
@@ -522,6 +526,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 }
                 if (b1 < jhi) vb = (c1 - c0 >= W && b1 <= c1 - W && (step == 1 || (b1 - c0) % step == 0)) ? 1.f : 0.f;
             }
+            if (GCRF_SKIP(2)) va = vb = 0.f;
             if (va + vb > 0.f) {
                 auto upair = [&](int k) -> float2 {
                     return (k & 1) ? *reinterpret_cast<const float2 *>(&sU1[b0 + k - 1])
@@ -590,7 +595,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
             const int g = T::lo + tid + rep * NT;  // local gene
-            if (g < T::lo + nout) {
+            if (g < T::lo + nout && !GCRF_SKIP(4)) {
                 const int stat = has_short ? (int)sStat[g] : 0;
                 float q = 0.f;
                 if (stat == 0) {
@@ -614,14 +619,16 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
 
         // rotate the prefetched ranges
         ga = nga; gb = ngb; pa = npa; pb = npb;
-#pragma unroll
-        for (int r = 0; r < kNew; ++r) rowreg[r] = nrow[r];
+        rowreg[0] = nrow[0];
+        rowreg[1] = nrow[1];
     }
+#ifdef GCRF_TUNING
     if (prof_on && tid == 0) {
 #pragma unroll
         for (int k = 0; k < 10; ++k) atomicAdd(args.prof + k, (unsigned long long)prof_acc[k]);
         atomicAdd(args.prof + 15, 1ull);
     }
+#endif
 }
 
 template <int W, int NT, int MINB, typename PtrT>
@@ -634,20 +641,12 @@ cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, NT, tl.bytes());
 }
 
-// CTA shape of the streaming kernel: GCRF_STREAM_THREADS=128|256 overrides the default (tuning knob).
-int stream_threads() {
-    const char *env = getenv("GCRF_STREAM_THREADS");
-    if (env && atoi(env) == 256) return 256;
-    if (env && atoi(env) == 128) return 128;
-    return 128;
-}
-
 }  // namespace
 
 bool stream_supported(const WindowedArgs &args) {
     if (args.window != 20) return false;
-    const StreamTiling<20, 256> tl(args.model.A);
-    if (tl.bytes() > 110 * 1024) return false;
+    const StreamTiling<20, 128> tl(args.model.A);
+    if (tl.bytes() > 100 * 1024) return false;
     // tile arithmetic is 32-bit: G + one tile of slack must fit
     return args.csr.G < 0x7fff0000;
 }
@@ -655,18 +654,14 @@ bool stream_supported(const WindowedArgs &args) {
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
     int per_sm = 0;
     size_t bytes = 0;
-    const int nt = stream_threads();
     const bool p64 = args.csr.gene_ptr64 != nullptr;
-    cudaError_t err;
-    if (nt == 256) err = p64 ? configure_stream<20, 256, 2, int64_t>(args.model.A, &per_sm, &bytes)
-                             : configure_stream<20, 256, 2, int32_t>(args.model.A, &per_sm, &bytes);
-    else err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &per_sm, &bytes)
-                   : configure_stream<20, 128, 4, int32_t>(args.model.A, &per_sm, &bytes);
+    cudaError_t err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &per_sm, &bytes)
+                          : configure_stream<20, 128, 4, int32_t>(args.model.A, &per_sm, &bytes);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    plan->threads = nt;
-    plan->tile_out = nt == 256 ? StreamTiling<20, 256>::tile_out : StreamTiling<20, 128>::tile_out;
-    plan->chunk = nt * kWalk;
+    plan->threads = 128;
+    plan->tile_out = StreamTiling<20, 128>::tile_out;
+    plan->chunk = 128 * kWalk;
     plan->smem_bytes = bytes;
     plan->num_tiles = (args.csr.G + plan->tile_out - 1) / plan->tile_out;
     plan->ctas_per_sm = per_sm;
@@ -682,14 +677,10 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
 cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches) {
     if (args.csr.G <= 0) return cudaSuccess;
     const int nt_ = (int)plan.num_tiles, tpc = plan.tiles_per_cta;
-    const bool p64 = args.csr.gene_ptr64 != nullptr;
-    if (plan.threads == 256) {
-        if (p64) stream_kernel<20, 256, 2, int64_t><<<plan.grid, 256, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
-        else stream_kernel<20, 256, 2, int32_t><<<plan.grid, 256, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
-    } else {
-        if (p64) stream_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
-        else stream_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
-    }
+    if (args.csr.gene_ptr64)
+        stream_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
+    else
+        stream_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -93,6 +93,15 @@ def test_dense_config2_slice(engine, weights):
     print(f"config2 slice ({batch.G} genes, nnz {batch.nnz}) max |dp| = {err:.3e}")
 
 
+def test_tiles_larger_than_one_staging_round(engine, weights):
+    """~40 domains per gene: a tile's ids exceed the streaming kernel's staging buffer -> direct path."""
+    from gecco_b200 import synth
+
+    batch = synth.config2(len(weights.attrs), contigs=40, mean_domains=40.0)
+    assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx), oracle(weights, batch),
+                 what="oversized tiles")
+
+
 def test_sparse_ecoli_like(engine, weights):
     from gecco_b200 import synth
 
