@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "gcrf_model_synchronize",
     "gcrf_marginals_windowed",
     "gcrf_marginals_chain",
+    "gcrf_model_set_vocabulary",
+    "gcrf_features_from_accessions",
     "gcrf_host_alloc",
     "gcrf_host_free",
     "gcrf_model_launch_count",
@@ -88,6 +90,10 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_marginals_windowed.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, u32]
     lib.gcrf_marginals_chain.restype = ctypes.c_int
     lib.gcrf_marginals_chain.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp, u32]
+    lib.gcrf_model_set_vocabulary.restype = ctypes.c_int
+    lib.gcrf_model_set_vocabulary.argtypes = [vp, vp, i32]
+    lib.gcrf_features_from_accessions.restype = ctypes.c_int
+    lib.gcrf_features_from_accessions.argtypes = [vp, vp, vp, i64, i64, vp, u32]
     lib.gcrf_host_alloc.restype = ctypes.c_int
     lib.gcrf_host_alloc.argtypes = [ctypes.POINTER(vp), u64]
     lib.gcrf_host_free.restype = ctypes.c_int
@@ -147,6 +153,20 @@ class CRFEngine:
         _check(self._lib, self._lib.gcrf_model_create(state_w.ctypes.data, A, L, trans_w.ctypes.data, pos,
                                                      self.device, ctypes.byref(handle)))
         self._handle = handle
+        self.has_vocabulary = False
+        # Pfam-style attribute names ("PF" + digits): hand the integer vocabulary to the device so that feature
+        # extraction (accession -> attribute id, repeats inside a gene dropped) can run there
+        accs = []
+        for name in weights.attrs:
+            if len(name) > 2 and name[:2] == "PF" and name[2:].isdigit():
+                accs.append(int(name[2:]))
+            else:
+                accs = None
+                break
+        if accs is not None and len(set(accs)) == len(accs):
+            arr = numpy.asarray(accs, dtype=numpy.int32)
+            _check(self._lib, self._lib.gcrf_model_set_vocabulary(self._handle, arr.ctypes.data if len(arr) else None, len(arr)))
+            self.has_vocabulary = True
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
@@ -214,6 +234,23 @@ class CRFEngine:
         _check(self._lib, self._lib.gcrf_marginals_chain(
             self._handle, contig_ptr.ctypes.data, gene_ptr.ctypes.data, attr_idx.ctypes.data if nnz else None,
             C, G, nnz, out.ctypes.data if G else None, flags))
+        return out
+
+    def features_from_accessions(self, accession, gene_ptr) -> numpy.ndarray:
+        """Integer domain accessions (row by row, domain-start order) -> attribute ids, -1 for unknown accessions
+        and for repeats inside a gene (``gcrf_features_from_accessions``, host buffers, blocking)."""
+        accession = numpy.ascontiguousarray(accession, dtype=numpy.int32)
+        gene_ptr = numpy.asarray(gene_ptr)
+        flags = 0
+        if gene_ptr.dtype == numpy.int64 and gene_ptr.size and int(gene_ptr[-1]) > 0x7FFFFFFF:
+            gene_ptr = numpy.ascontiguousarray(gene_ptr, dtype=numpy.int64)
+            flags = GCRF_FLAG_PTR64
+        else:
+            gene_ptr = numpy.ascontiguousarray(gene_ptr, dtype=numpy.int32)
+        out = numpy.empty(len(accession), dtype=numpy.int32)
+        _check(self._lib, self._lib.gcrf_features_from_accessions(
+            self._handle, accession.ctypes.data if len(accession) else None, gene_ptr.ctypes.data,
+            len(gene_ptr) - 1, len(accession), out.ctypes.data if len(out) else None, flags))
         return out
 
     # ------------------------------------------------------------------ device-pointer calls

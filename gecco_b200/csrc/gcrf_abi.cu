@@ -68,6 +68,8 @@ struct gcrf_model {
     gcrf::ModelDev dev{};
     float *d_table = nullptr;
     int32_t *d_table_fx = nullptr;
+    int32_t *d_lut = nullptr;  // accession -> attribute id (gcrf_model_set_vocabulary)
+    int32_t lut_size = 0;
     double *d_table64 = nullptr;
     double m01 = 0, m10 = 0, m11 = 0;
     cudaStream_t own_stream = nullptr;
@@ -294,6 +296,7 @@ void gcrf_model_destroy(gcrf_model *m) {
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
     if (m->d_table_fx) cudaFree(m->d_table_fx);
+    if (m->d_lut) cudaFree(m->d_lut);
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -400,6 +403,69 @@ int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *g
     GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
     m->timed = true;
     return finish_batch(m, b, out);
+}
+
+int gcrf_model_set_vocabulary(gcrf_model *m, const int32_t *accession_of_attr, int32_t A) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (A != m->A) return fail(GCRF_EINVAL, "vocabulary has %d entries, the model has %d attributes", A, m->A);
+    if (A > 0 && !accession_of_attr) return fail(GCRF_EINVAL, "accession_of_attr is NULL");
+    int32_t max_acc = -1;
+    for (int32_t a = 0; a < A; ++a) {
+        if (accession_of_attr[a] < 0) return fail(GCRF_EINVAL, "negative accession for attribute %d", a);
+        if (accession_of_attr[a] > max_acc) max_acc = accession_of_attr[a];
+    }
+    if (max_acc > (1 << 26)) return fail(GCRF_EUNSUPPORTED, "accessions above 2^26 need a hashed vocabulary");
+    std::vector<int32_t> lut((size_t)max_acc + 1, -1);
+    for (int32_t a = 0; a < A; ++a) {
+        if (lut[accession_of_attr[a]] != -1) return fail(GCRF_EINVAL, "accession %d appears twice", accession_of_attr[a]);
+        lut[accession_of_attr[a]] = a;
+    }
+    DeviceGuard guard(m->device);
+    if (m->d_lut) cudaFree(m->d_lut);
+    m->d_lut = nullptr;
+    m->lut_size = 0;
+    if (lut.empty()) return GCRF_OK;
+    GCRF_CUDA(cudaMalloc(reinterpret_cast<void **>(&m->d_lut), lut.size() * sizeof(int32_t)));
+    GCRF_CUDA(cudaMemcpy(m->d_lut, lut.data(), lut.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    m->lut_size = (int32_t)lut.size();
+    return GCRF_OK;
+}
+
+int gcrf_features_from_accessions(gcrf_model *m, const int32_t *accession, const void *gene_ptr, int64_t G, int64_t nnz,
+                                  int32_t *attr_idx_out, uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (!m->d_lut && m->A > 0) return fail(GCRF_EINVAL, "gcrf_model_set_vocabulary has not been called");
+    if (G < 0 || nnz < 0) return fail(GCRF_EINVAL, "negative size");
+    if (G == 0 || nnz == 0) return GCRF_OK;
+    if (!accession || !gene_ptr || !attr_idx_out) return fail(GCRF_EINVAL, "NULL array");
+    const bool ptr64 = (flags & GCRF_FLAG_PTR64) != 0;
+    DeviceGuard guard(m->device);
+    const int32_t *d_acc = accession;
+    const void *d_ptr = gene_ptr;
+    int32_t *d_out = attr_idx_out;
+    const bool host = (flags & GCRF_FLAG_DEVICE_PTRS) == 0;
+    if (host) {
+        const int64_t last = ptr64 ? static_cast<const int64_t *>(gene_ptr)[G] : static_cast<const int32_t *>(gene_ptr)[G];
+        if (last != nnz) return fail(GCRF_EINVAL, "gene_ptr must end at nnz");
+        const size_t gene_bytes = (size_t)(G + 1) * (ptr64 ? 8 : 4);
+        GCRF_CUDA(m->b_gene.reserve(gene_bytes));
+        GCRF_CUDA(m->b_attr.reserve((size_t)nnz * 4 + 16));
+        GCRF_CUDA(m->b_scratch.reserve((size_t)nnz * 4));
+        GCRF_CUDA(cudaMemcpyAsync(m->b_gene.ptr, gene_ptr, gene_bytes, cudaMemcpyHostToDevice, m->stream));
+        GCRF_CUDA(cudaMemcpyAsync(m->b_scratch.ptr, accession, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
+        d_acc = static_cast<const int32_t *>(m->b_scratch.ptr);
+        d_ptr = m->b_gene.ptr;
+        d_out = static_cast<int32_t *>(m->b_attr.ptr);
+    }
+    cudaError_t err = gcrf::launch_features(d_acc, ptr64 ? nullptr : static_cast<const int32_t *>(d_ptr),
+                                            ptr64 ? static_cast<const int64_t *>(d_ptr) : nullptr, G, m->d_lut,
+                                            m->lut_size, d_out, m->num_sms, m->stream, &m->launches);
+    if (err != cudaSuccess) return fail_cuda(err, "launch_features");
+    if (host) {
+        GCRF_CUDA(cudaMemcpyAsync(attr_idx_out, d_out, (size_t)nnz * 4, cudaMemcpyDeviceToHost, m->stream));
+        GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return GCRF_OK;
 }
 
 int gcrf_host_alloc(void **ptr, uint64_t bytes) {

@@ -79,4 +79,9 @@ struct ChainArgs {
 // Whole-contig (un-windowed) marginals: unary gather kernel + block-per-contig 2x2 scan kernel.
 cudaError_t launch_chain(const ChainArgs &args, int num_sms, cudaStream_t stream, int64_t *launches);
 
+// accession -> attribute id with the reference's set semantics (repeats inside a gene and unknown accessions -> -1)
+cudaError_t launch_features(const int32_t *accession, const int32_t *gene_ptr32, const int64_t *gene_ptr64, int64_t G,
+                            const int32_t *lut, int32_t lut_size, int32_t *attr_idx_out, int num_sms,
+                            cudaStream_t stream, int64_t *launches);
+
 }  // namespace gcrf

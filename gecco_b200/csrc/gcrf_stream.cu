@@ -652,12 +652,22 @@ bool stream_supported(const WindowedArgs &args) {
 }
 
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
-    int per_sm = 0;
-    size_t bytes = 0;
+    // the kernel attribute / occupancy query depend on (device, A, pointer width) only: cache them per thread
+    struct Cached { int device = -1, A = -1, p64 = -1, per_sm = 0; size_t bytes = 0; };
+    static thread_local Cached cache;
+    int device = 0;
+    cudaGetDevice(&device);
     const bool p64 = args.csr.gene_ptr64 != nullptr;
-    cudaError_t err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &per_sm, &bytes)
-                          : configure_stream<20, 128, 4, int32_t>(args.model.A, &per_sm, &bytes);
-    if (err != cudaSuccess) return err;
+    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64) {
+        int q = 0;
+        size_t b = 0;
+        cudaError_t err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &q, &b)
+                              : configure_stream<20, 128, 4, int32_t>(args.model.A, &q, &b);
+        if (err != cudaSuccess) return err;
+        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.per_sm = q; cache.bytes = b;
+    }
+    const int per_sm = cache.per_sm;
+    const size_t bytes = cache.bytes;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     plan->threads = 128;
     plan->tile_out = StreamTiling<20, 128>::tile_out;

@@ -130,6 +130,23 @@ int gcrf_marginals_chain(gcrf_model *model, const int32_t *contig_ptr, const voi
                          uint32_t flags);
 
 /*
+ * On-device feature extraction (gecco/crf/features.py:13-35 + the attribute dictionary of the tagger).
+ *
+ * gcrf_model_set_vocabulary: accession_of_attr[a] is the integer accession of attribute a (for Pfam, the
+ * number in "PF00109" -> 109); accessions must be >= 0 and distinct.  Replaces: the CQDB string -> id
+ * dictionary python-crfsuite consults for every attribute of every item (Tagger.set()).
+ *
+ * gcrf_features_from_accessions: accession[nnz] holds, row by row (gene_ptr), the accessions of the
+ * domain rows of every gene in domain-start order; attr_idx_out[p] receives the attribute id, or -1 when
+ * the accession is not in the model or repeats an earlier row of the same gene — a gene's features are
+ * a dict keyed by domain name (features.py:32), so repeats collapse.  gene_ptr is unchanged: the -1
+ * entries are simply ignored by gcrf_marginals_*.  Honours GCRF_FLAG_DEVICE_PTRS and GCRF_FLAG_PTR64.
+ */
+int gcrf_model_set_vocabulary(gcrf_model *model, const int32_t *accession_of_attr, int32_t A);
+int gcrf_features_from_accessions(gcrf_model *model, const int32_t *accession, const void *gene_ptr,
+                                  int64_t G, int64_t nnz, int32_t *attr_idx_out, uint32_t flags);
+
+/*
  * Pinned host memory helpers so that host-pointer calls can run their copies at PCIe speed
  * (pageable buffers are accepted everywhere, they are just slower).
  */

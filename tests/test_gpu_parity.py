@@ -239,3 +239,27 @@ def test_device_pointer_mode_matches_host_mode(engine, weights):
     assert numpy.array_equal(out.cpu().numpy(), host)
     assert engine.last_kernel_ms() > 0
     assert engine.launch_count > 0
+
+
+def test_feature_extraction_on_device(engine, mibig, weights):
+    """Accession -> attribute id on device with the reference's set semantics: running the marginals on its output
+    (unknown / repeated rows marked -1, row pointers untouched) equals the host packer + oracle on the real fixture."""
+    from gecco_b200.packer import pack_arrays
+
+    assert engine.has_vocabulary
+    dom_ptr, dom_pfam = mibig["dom_ptr"], mibig["dom_pfam"]
+    ids = engine.features_from_accessions(dom_pfam, dom_ptr)
+    packed = pack_arrays(mibig["gene_contig"], dom_ptr, dom_pfam, weights)
+    assert int((ids >= 0).sum()) == packed.nnz == 16261  # 25,446 rows, 19,083 in the vocabulary, 16,261 after the per-gene set
+    # same sets per gene, in the same order
+    keep = ids >= 0
+    gene_of = numpy.repeat(numpy.arange(len(dom_ptr) - 1), numpy.diff(dom_ptr))
+    assert numpy.array_equal(ids[keep], packed.attr_idx)
+    assert numpy.array_equal(numpy.bincount(gene_of[keep], minlength=len(dom_ptr) - 1), numpy.diff(packed.gene_ptr))
+    p = engine.marginals_windowed(packed.contig_ptr, dom_ptr, ids)
+    assert_close(p, mibig["ref_loop_prob"], what="device features + marginals vs reference loop")
+    # repeats and unknown accessions
+    acc = numpy.array([109, 109, 99999, 5, 109, 5, 2801], dtype=numpy.int32)
+    out = engine.features_from_accessions(acc, numpy.array([0, 5, 7], dtype=numpy.int32))
+    ix = weights.attr_index
+    assert out.tolist() == [ix["PF00109"], -1, -1, ix["PF00005"], -1, ix["PF00005"], ix["PF02801"]]
