@@ -54,7 +54,7 @@ struct StreamTiling {
     static constexpr int keep = ng - tile_out;     // genes carried over from the previous tile
     static_assert(tile_out + 1 <= 2 * NT, "two row pointers per thread must cover a tile's new genes");
     static_assert(keep <= NT, "the ring carry is one gene per thread");
-    int off_idx, off_pool, off_u0, off_u1, off_q, off_sp, off_cp, off_cp2, off_stat, words;
+    int off_idx, off_pool, off_u0, off_u1, off_q, off_sp, off_cp, off_stat, words;
     __host__ __device__ explicit StreamTiling(int A) {
         int o = round_up4s(A + 1);
         off_idx = o; o += kCap + 4;
@@ -64,7 +64,6 @@ struct StreamTiling {
         off_q = o; o += round_up4s(ng + 2);
         off_sp = o; o += round_up4s(tile_out + 3);
         off_cp = o; o += round_up4s(ng + 4);
-        off_cp2 = o; o += round_up4s(ng + 4);  // second slice buffer of the pipelined kernel
         off_stat = o; o += round_up4s((ng + 8) / 4);
         words = o;
     }
@@ -385,9 +384,6 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         // ids in front of the first new row sit in thread 0's own walk range: no barrier needed
         if (tid == 0 && staged)
             for (int i = 0; i < (int)(pa - a0); ++i) sIdx[i] = -1;
-        // contig slice -> shared (loaded at the top of the tile; visible after the walk's barrier)
-        sCp[tid] = cp0;
-        if (tid == NT - 1) sCp[NT] = INT_MAX;  // sentinel unless the rest of the slice gets loaded below
         GCRF_MARK(1);
         if (!GCRF_SKIP(1)) {
             // walk: ids -> running prefix of their fixed-point deltas, in place
@@ -416,6 +412,9 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 }
             }
         }
+        // contig slice -> shared (its load was issued at the top of the tile; visible after the barrier)
+        sCp[tid] = cp0;
+        if (tid == NT - 1) sCp[NT] = INT_MAX;  // sentinel unless the rest of the slice gets loaded below
         // a tile that holds more contigs than one slice entry per thread covers (contigs of 1-2 genes): load the rest
         const bool wide_slice = __syncthreads_or(tid == NT - 1 && cp0 < T::ng) != 0;
         if (wide_slice) {
@@ -632,385 +631,11 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
 #endif
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Pipelined variant: iteration `it` gathers tile n = it and runs the dynamic programme of tile d = it - 1.
-// The prefix walk (shared-memory bound) and the DP (FMA / MUFU bound) of two different tiles sit in ONE
-// straight-line block, so every warp always has work for both kinds of pipe in flight — the instruction-level
-// version of doubling the occupancy, which shared memory and registers do not allow (4 warps per scheduler).
-// Two CTA barriers per iteration.  The unary-odds ring needs no second buffer: the halo travels through a
-// register across the first barrier; the contig slice is double-buffered (validity of a thread's two window
-// slots is computed one iteration ahead and kept in registers).
 template <int W, int NT, int MINB, typename PtrT>
-__global__ void __launch_bounds__(NT, MINB)
-stream2_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const int num_tiles, const int tiles_per_cta) {
-    using T = StreamTiling<W, NT>;
-    constexpr int kCap = T::kCap, kPitch = T::kPitch;
-    constexpr int H = W / 2;
-    static_assert(W % 2 == 0 && W >= 4, "packed DP assumes an even window");
-    const CsrDev &csr = args.csr;
-    const T tl(args.model.A);
-    const int tid = threadIdx.x;
-    const uint32_t A = (uint32_t)args.model.A;
-    const float m01 = args.model.m01, m10 = args.model.m10, m11 = args.model.m11;
-    const float clampv = args.model.clamp;
-    const float fx_inv = __int_as_float((127 - args.model.fx_bits) << 23);  // 2^-fx_bits
-    const int fx_nsafe = args.model.fx_nsafe;
-    const int step = args.step;
-    const int G = (int)csr.G;
-
-    extern __shared__ __align__(16) float smem[];
-    int *sTab = reinterpret_cast<int *>(smem);
-    int32_t *sIdx = reinterpret_cast<int32_t *>(smem + tl.off_idx);
-    float *sPool = smem + tl.off_pool;
-    float *sU0 = smem + tl.off_u0;
-    float *sU1 = smem + tl.off_u1;
-    float *sQ = smem + tl.off_q;
-    int *sP = reinterpret_cast<int *>(smem + tl.off_sp);
-    int *sCpBase = reinterpret_cast<int *>(smem + tl.off_cp);  // two slice buffers, off_cp2 - off_cp words apart
-    unsigned char *sStat = reinterpret_cast<unsigned char *>(smem + tl.off_stat);
-    __shared__ __align__(8) uint64_t sBar, sBarTab;
-    __shared__ int64_t sCursor;
-    __shared__ int sShort[2];  // "tile holds a short contig", double-buffered like the slice
-
-    const int tile_begin = blockIdx.x * tiles_per_cta;
-    const int tile_end = min(num_tiles, tile_begin + tiles_per_cta);
-    if (tile_begin >= tile_end) return;
-
-    // ---- prologue (as in stream_kernel) -------------------------------------------------------------------
-    if (tid == 0) {
-        mbar_init(&sBar, 1);
-        mbar_init(&sBarTab, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t tab_bytes = (uint32_t)(4 * round_up4s((int)A + 1));
-        mbar_expect_tx(&sBarTab, tab_bytes);
-        tma_load_1d(sTab, args.model.table_fx, tab_bytes, &sBarTab);
-    }
-    if (tid < 32) {
-        const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
-        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0, tid);
-        if (tid == 0) sCursor = c;
-    }
-    const int Gs0 = tile_begin * T::tile_out - T::lo;
-    {
-        int *hrow = sP;
-        int *hacc = reinterpret_cast<int *>(sPool);
-        const int h0 = max(0, min(G, Gs0)), h1 = max(0, min(G, Gs0 + T::keep));
-        const int64_t hp0 = (int64_t)__ldg(gene_ptr + h0);
-        if (tid <= h1 - h0) hrow[tid] = (int)((int64_t)__ldg(gene_ptr + h0 + tid) - hp0);
-        if (tid < T::keep) hacc[tid] = 0;
-        __syncthreads();
-        mbar_wait(&sBarTab, 0);
-        const int hn = h1 - h0, hids = hn > 0 ? hrow[hn] : 0;
-        for (int x = tid; x < hids; x += NT) {
-            int row = 0, hi = hn;
-            while (hi - row > 1) {
-                const int mid = (row + hi) >> 1;
-                if (hrow[mid] <= x) row = mid; else hi = mid;
-            }
-            atomicAdd(&hacc[row], lookup(sTab, __ldg(csr.attr_idx + hp0 + x), A));
-        }
-        __syncthreads();
-        if (tid < T::keep) {
-            const int g = Gs0 + tid;
-            float u = 1.0f;
-            if (g >= h0 && g < h1) {
-                const int r = g - h0;
-                u = hrow[r + 1] - hrow[r] < fx_nsafe
-                        ? exp_fast(fminf(fmaxf((float)hacc[r] * fx_inv, -clampv), clampv))
-                        : direct_unary(gene_ptr, csr.attr_idx, args.model.table, A, g, clampv);
-            }
-            sU0[T::tile_out + tid] = u;  // where the first iteration's halo read looks
-        }
-    }
-    int ga = max(0, min(G, Gs0 + T::keep)), gb = max(0, min(G, Gs0 + T::ng));
-    int64_t pa = (int64_t)__ldg(gene_ptr + ga), pb = (int64_t)__ldg(gene_ptr + gb);
-    PtrT rowreg[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int t = tid + r * NT;
-        rowreg[r] = t <= gb - ga ? __ldg(gene_ptr + ga + t) : 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        stage_ids<kCap>(sIdx, csr.attr_idx, pa, pb, &sBar);
-        sShort[0] = 0;
-        sShort[1] = 0;
-    }
-    uint32_t bar_parity = 0;
-
-    // state of the tile whose DP runs in the next iteration
-    float va_d = 0.f, vb_d = 0.f;
-    bool short_d = false;
-
-    const float2 M10 = make_float2(m10, m10), M11 = make_float2(m11, m11), ONE = make_float2(1.f, 1.f);
-    const float2 B01 = make_float2(m01, m01);
-    const int b0 = 2 * tid;
-
-    for (int it = tile_begin; it <= tile_end; ++it) {
-        const bool gn = it < tile_end;    // a tile to gather
-        const bool dd = it > tile_begin;  // a tile whose DP / pool runs
-        int *sCp = sCpBase + (it & 1) * (tl.off_cp2 - tl.off_cp);
-        // geometry of tile n
-        const int Gs = it * T::tile_out - T::lo;
-        const int nout = min(G - (Gs + T::lo), T::tile_out);
-        const int nn = gn ? gb - ga : 0;
-        const int jn0 = ga - Gs;
-        const int jlo = max(0, -Gs);
-        const int jhi = min(T::ng, G - Gs);
-        const int64_t a0 = pa & ~(int64_t)3;
-        const int64_t total64 = pb - a0;
-        const bool staged = gn && total64 <= kCap;
-        const bool has_next = it + 1 < tile_end;
-
-        // ---- phase 1 ---------------------------------------------------------------------------------------
-        int cp0 = INT_MAX;
-        int nga = 0, ngb = 0;
-        int64_t npa = 0, npb = 0, c_first = 0;
-        PtrT nrow[2] = {0, 0};
-        float carry = 1.0f;
-        if (gn) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int t = tid + r * NT;
-                if (t <= nn) sP[t] = t == 0 ? 0 : (int)((int64_t)rowreg[r] - a0);
-            }
-            c_first = sCursor;
-            if (c_first + tid <= csr.C) cp0 = __ldg(csr.contig_ptr + c_first + tid) - Gs;
-            if (has_next) {
-                nga = max(0, min(G, Gs + T::tile_out + T::keep));
-                ngb = max(0, min(G, Gs + T::tile_out + T::ng));
-                npa = (int64_t)__ldg(gene_ptr + nga);
-                npb = (int64_t)__ldg(gene_ptr + ngb);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int t = tid + r * NT;
-                    nrow[r] = t <= ngb - nga ? __ldg(gene_ptr + nga + t) : 0;
-                }
-            }
-            // halo of tile n = tail of the previous tile (or the prologue's gather); it is written back after the
-            // barrier, when the previous tile's DP no longer reads the ring
-            if (tid < T::keep) carry = sU0[tid + T::tile_out];
-            mbar_wait(&sBar, bar_parity);
-            bar_parity ^= 1;
-            if (tid == 0 && staged)
-                for (int i = 0; i < (int)(pa - a0); ++i) sIdx[i] = -1;
-        }
-        {
-            // One straight-line block: walk of tile n interleaved with the DP of tile d.  Both run unconditionally —
-            // without a tile to gather the walk chews on stale ids (every look-up is clamped), without a tile to
-            // finish the DP writes a pool nobody reads — so that the scheduler sees independent work for the
-            // shared-memory pipe and for the FMA / MUFU pipes at the same time.
-            int4 *v = reinterpret_cast<int4 *>(sIdx + tid * kWalk);
-            int run = 0;
-            auto walk_vec = [&](int i) {
-                int4 id = v[i];
-                run += lookup(sTab, id.x, A); id.x = run;
-                run += lookup(sTab, id.y, A); id.y = run;
-                run += lookup(sTab, id.z, A); id.z = run;
-                run += lookup(sTab, id.w, A); id.w = run;
-                v[i] = id;
-            };
-            auto upair = [&](int k) -> float2 {
-                return (k & 1) ? *reinterpret_cast<const float2 *>(&sU1[b0 + k - 1])
-                               : *reinterpret_cast<const float2 *>(&sU0[b0 + k]);
-            };
-            const float2 M01 = make_float2(m01 * va_d, m01 * vb_d);  // masked: an invalid slot keeps odds == 0
-            auto fwd = [&](float2 R, int k) -> float2 {
-                const float2 num = __ffma2_rn(R, M11, M01);
-                const float2 den = __ffma2_rn(R, M10, ONE);
-                const float2 inv = make_float2(rcp_fast(den.x), rcp_fast(den.y));
-                return __fmul2_rn(__fmul2_rn(num, upair(k)), inv);
-            };
-            auto bwd = [&](float2 S, int k) -> float2 {  // S_{k+1} -> S_k
-                const float2 Wv = __fmul2_rn(upair(k + 1), S);
-                const float2 num = __ffma2_rn(Wv, M11, M10);
-                const float2 den = __ffma2_rn(Wv, B01, ONE);
-                const float2 inv = make_float2(rcp_fast(den.x), rcp_fast(den.y));
-                return __fmul2_rn(num, inv);
-            };
-            constexpr int NV = kWalk / 4;  // 13 walk vectors spread over the 2*(H-1)+1 DP steps
-            float2 ra[H], sb[H];
-            float2 R = __fmul2_rn(upair(0), make_float2(va_d, vb_d));
-            float2 S = ONE;
-            ra[0] = R;
-            sb[H - 1] = S;
-            int wv = 0;
-#pragma unroll
-            for (int k = 1; k < H; ++k) {
-                if (wv < NV) walk_vec(wv++);
-                R = fwd(R, k);
-                ra[k] = R;
-                S = bwd(S, W - 1 - k);
-                sb[H - 1 - k] = S;
-            }
-            if (wv < NV) walk_vec(wv++);
-            R = fwd(R, H);
-            S = bwd(S, H - 1);
-            float2 Qup = __fmul2_rn(R, sb[0]);
-            float2 Qdn = __fmul2_rn(ra[H - 1], S);
-            sPool[H * kPitch + tid] = fmaxf(Qup.x, Qdn.y);
-#pragma unroll
-            for (int i = 1; i < H; ++i) {
-                if (wv < NV) walk_vec(wv++);
-                R = fwd(R, H + i);
-                const float2 Qu = __fmul2_rn(R, sb[i]);
-                sPool[(H + i) * kPitch + tid] = fmaxf(Qu.x, Qup.y);
-                Qup = Qu;
-                S = bwd(S, H - 1 - i);
-                const float2 Qd = __fmul2_rn(ra[H - 1 - i], S);
-                sPool[(H - i) * kPitch + tid] = fmaxf(Qdn.x, Qd.y);
-                Qdn = Qd;
-            }
-#pragma unroll
-            for (; wv < NV; ++wv) walk_vec(wv);
-            sPool[W * kPitch + tid] = Qup.y;
-            sPool[tid] = Qdn.x;
-        }
-        sCp[tid] = cp0;
-        if (tid == NT - 1) sCp[NT] = INT_MAX;
-        const bool wide_slice = __syncthreads_or(gn && tid == NT - 1 && cp0 < T::ng) != 0;  // barrier 1
-        if (wide_slice) {
-            for (int k = NT + tid; k <= T::ng + 1; k += NT)
-                sCp[k] = c_first + k <= csr.C ? __ldg(csr.contig_ptr + c_first + k) - Gs : INT_MAX;
-            __syncthreads();
-        }
-
-        // ---- phase 2 ---------------------------------------------------------------------------------------
-        if (dd) {
-            // pool + output of tile d (its geometry: one tile earlier)
-            const int Gs_d = Gs - T::tile_out;
-            const int nout_d = min(G - (Gs_d + T::lo), T::tile_out);
-#pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {
-                const int g = T::lo + tid + rep * NT;
-                if (g < T::lo + nout_d) {
-                    const int stat = short_d ? (int)sStat[g] : 0;
-                    float q = 0.f;
-                    if (stat == 0) {
-                        const int par = g & 1;
-                        const float *col = sPool + par * kPitch + ((g - par) >> 1);
-#pragma unroll
-                        for (int i = 0; 2 * i < W; ++i) q = fmaxf(q, col[i * (2 * kPitch - 1)]);
-                        if (!par || (W & 1)) q = fmaxf(q, col[((W - par) / 2) * (2 * kPitch - 1)]);
-                    } else if (stat == 1) {
-                        q = sQ[g];
-                    }
-                    float p = q * rcp_fast(1.0f + q);
-                    if (stat == 2) p = __int_as_float(0x7fc00000);
-                    const int gg = Gs_d + g;
-                    if (args.out_f32) static_cast<float *>(args.out)[gg] = p;
-                    else static_cast<double *>(args.out)[gg] = (double)p;
-                }
-            }
-        }
-        if (gn) {
-            if (tid < T::keep) {
-                sU0[tid] = carry;
-                if (tid >= 1) sU1[tid - 1] = carry;
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int t = tid + r * NT;
-                if (t < nn) {
-                    const int s = sP[t], e = sP[t + 1];
-                    float u;
-                    if (staged && e - s < fx_nsafe) {
-                        int vsum = 0;
-                        if (e > s) {
-                            const int q0 = walk_thread(s), q1 = walk_thread(e - 1);
-                            vsum = sIdx[e - 1];
-                            if (s != q0 * kWalk) vsum -= sIdx[s - 1];
-                            if (q1 > q0) {
-                                vsum += sIdx[(q0 + 1) * kWalk - 1];
-#pragma unroll 1
-                                for (int q = q0 + 2; q <= q1; ++q) vsum += sIdx[q * kWalk - 1];
-                            }
-                        }
-                        u = exp_fast(fminf(fmaxf((float)vsum * fx_inv, -clampv), clampv));
-                    } else {
-                        u = direct_unary(gene_ptr, csr.attr_idx, args.model.table, A, ga + t, clampv);
-                    }
-                    const int j = jn0 + t;
-                    sU0[j] = u;
-                    if (j >= 1) sU1[j - 1] = u;
-                }
-            }
-            if (jlo > 0 || jhi < T::ng) {
-                for (int j = tid; j < T::ng + 1; j += NT) {
-                    if (j < jlo || j >= jhi) {
-                        sU0[j] = 1.0f;
-                        if (j >= 1) sU1[j - 1] = 1.0f;
-                    }
-                }
-            }
-            for (int k = tid; k <= (wide_slice ? T::ng : NT - 1); k += NT) {
-                const int a = sCp[k], b = sCp[k + 1];
-                if (a < jhi && b > jlo && b != INT_MAX && b - a < W) sShort[it & 1] = 1;
-                if (has_next && a <= T::tile_out && T::tile_out < b) sCursor = c_first + k;
-            }
-        }
-        int kt = __syncthreads_count(gn && tid >= 1 && sCp[tid] < T::ng);  // barrier 2
-        if (gn) {
-            if (kt >= NT - 1) kt = T::ng;
-            const bool has_short = sShort[it & 1] != 0;
-            if (tid == 0) sShort[(it + 1) & 1] = 0;  // the next iteration sets it after its barrier 1
-            if (has_next && tid == 0) stage_ids<kCap>(sIdx, csr.attr_idx, npa, npb, &sBar);
-            if (has_short) {
-#pragma unroll 1
-                for (int j = tid; j < T::ng; j += NT) {
-                    unsigned char stat = 0;
-                    if (j >= jlo && j < jhi) {
-                        const int k = find_slice_contig(sCp, j, kt);
-                        const int c0 = sCp[k], n = sCp[k + 1] - c0;
-                        if (n < W) {
-                            stat = args.pad ? 1 : 2;
-                            if (args.pad && j == c0 && j < T::lo + nout) padded_window<W>(sU0, sQ, j, n, m01, m10, m11);
-                        }
-                    }
-                    sStat[j] = stat;
-                }
-                // no barrier needed here: sStat / sQ are read in the next iteration's phase 2, after its barrier 1
-            }
-            // validity of this thread's two window slots, used by the DP in the next iteration
-            va_d = 0.f;
-            vb_d = 0.f;
-            if (b0 + 1 >= jlo && b0 < jhi) {
-                const int js = max(b0, jlo);
-                int k = 0;
-                if (kt <= 4) {
-#pragma unroll
-                    for (int i = 1; i <= 4; ++i) k += (i <= kt && sCp[i] <= js) ? 1 : 0;
-                } else {
-                    k = find_slice_contig(sCp, js, kt);
-                }
-                int c0 = sCp[k], c1 = sCp[k + 1];
-                if (b0 >= jlo) va_d = (c1 - c0 >= W && b0 <= c1 - W && (step == 1 || (b0 - c0) % step == 0)) ? 1.f : 0.f;
-                const int b1 = b0 + 1;
-                if (b1 >= c1) {
-                    c0 = c1;
-                    c1 = sCp[k + 2];
-                }
-                if (b1 < jhi) vb_d = (c1 - c0 >= W && b1 <= c1 - W && (step == 1 || (b1 - c0) % step == 0)) ? 1.f : 0.f;
-            }
-            short_d = has_short;
-            ga = nga; gb = ngb; pa = npa; pb = npb;
-            rowreg[0] = nrow[0];
-            rowreg[1] = nrow[1];
-        }
-    }
-}
-
-// GCRF_STREAM_VARIANT=1 selects the phase-serial kernel, 2 (default) the pipelined one (A/B knob)
-int stream_variant() {
-    const char *env = getenv("GCRF_STREAM_VARIANT");
-    return (env && env[0] == '1') ? 1 : 2;
-}
-
-template <int W, int NT, int MINB, typename PtrT>
-cudaError_t configure_stream(int A, int variant, int *ctas_per_sm, size_t *bytes) {
+cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
     const StreamTiling<W, NT> tl(A);
     *bytes = tl.bytes();
-    auto kernel = variant == 1 ? stream_kernel<W, NT, MINB, PtrT> : stream2_kernel<W, NT, MINB, PtrT>;
+    auto kernel = stream_kernel<W, NT, MINB, PtrT>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.bytes());
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, NT, tl.bytes());
@@ -1028,20 +653,18 @@ bool stream_supported(const WindowedArgs &args) {
 
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
     // the kernel attribute / occupancy query depend on (device, A, pointer width) only: cache them per thread
-    struct Cached { int device = -1, A = -1, p64 = -1, variant = -1, per_sm = 0; size_t bytes = 0; };
+    struct Cached { int device = -1, A = -1, p64 = -1, per_sm = 0; size_t bytes = 0; };
     static thread_local Cached cache;
     int device = 0;
     cudaGetDevice(&device);
     const bool p64 = args.csr.gene_ptr64 != nullptr;
-    const int variant = stream_variant();
-    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64 || cache.variant != variant) {
+    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64) {
         int q = 0;
         size_t b = 0;
-        cudaError_t err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, variant, &q, &b)
-                              : configure_stream<20, 128, 4, int32_t>(args.model.A, variant, &q, &b);
+        cudaError_t err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &q, &b)
+                              : configure_stream<20, 128, 4, int32_t>(args.model.A, &q, &b);
         if (err != cudaSuccess) return err;
-        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.variant = variant;
-        cache.per_sm = q; cache.bytes = b;
+        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.per_sm = q; cache.bytes = b;
     }
     const int per_sm = cache.per_sm;
     const size_t bytes = cache.bytes;
@@ -1064,17 +687,10 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
 cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches) {
     if (args.csr.G <= 0) return cudaSuccess;
     const int nt_ = (int)plan.num_tiles, tpc = plan.tiles_per_cta;
-    if (stream_variant() == 1) {
-        if (args.csr.gene_ptr64)
-            stream_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
-        else
-            stream_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
-    } else {
-        if (args.csr.gene_ptr64)
-            stream2_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
-        else
-            stream2_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
-    }
+    if (args.csr.gene_ptr64)
+        stream_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
+    else
+        stream_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
