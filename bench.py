@@ -277,10 +277,12 @@ def run_ours(args) -> None:
 
     # ---- per-launch kernel time (events inside the ABI around the kernel only), separate pass
     kernel_ms = []
+    engine.set_timing(True)
     for _ in range(min(args.steps, 10)):
         step_device()
         kernel_ms.append(engine.last_kernel_ms())
     kernel_ms_avg = sum(kernel_ms) / len(kernel_ms)
+    engine.set_timing(False)
     if rank == 0:
         time.sleep(0.2)
         sampler.stop()

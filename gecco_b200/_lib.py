@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "gcrf_host_alloc",
     "gcrf_host_free",
     "gcrf_model_launch_count",
+    "gcrf_model_set_timing",
     "gcrf_model_last_kernel_ms",
 )
 
@@ -100,6 +101,8 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_host_free.argtypes = [vp]
     lib.gcrf_model_launch_count.restype = i64
     lib.gcrf_model_launch_count.argtypes = [vp]
+    lib.gcrf_model_set_timing.restype = ctypes.c_int
+    lib.gcrf_model_set_timing.argtypes = [vp, i32]
     lib.gcrf_model_last_kernel_ms.restype = ctypes.c_double
     lib.gcrf_model_last_kernel_ms.argtypes = [vp]
     _lib = lib
@@ -279,6 +282,10 @@ class CRFEngine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.gcrf_model_launch_count(self._handle))
+
+    def set_timing(self, enable: bool) -> None:
+        """Bracket the kernels of later calls with CUDA events (needed by ``last_kernel_ms``; off by default)."""
+        _check(self._lib, self._lib.gcrf_model_set_timing(self._handle, int(bool(enable))))
 
     def last_kernel_ms(self) -> float:
         return float(self._lib.gcrf_model_last_kernel_ms(self._handle))

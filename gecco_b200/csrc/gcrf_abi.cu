@@ -76,6 +76,7 @@ struct gcrf_model {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
+    bool timing = false;  // record events around the kernels (gcrf_model_set_timing)
     int64_t launches = 0;
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
 };
@@ -359,12 +360,12 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", window, m->A);
     }
     if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
-    GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
     err = fast ? gcrf::launch_stream(args, plan, m->stream, &m->launches)
                : gcrf::launch_windowed(args, plan, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_windowed");
-    GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-    m->timed = true;
+    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
+    m->timed = m->timing;
     if (prof) {
         unsigned long long h[16];
         GCRF_CUDA(cudaMemcpyAsync(h, args.prof, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
@@ -397,11 +398,11 @@ int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *g
     args.m10 = m->m10;
     args.m11 = m->m11;
     args.scratch = static_cast<double *>(m->b_scratch.ptr);
-    GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
     cudaError_t err = gcrf::launch_chain(args, m->num_sms, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_chain");
-    GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-    m->timed = true;
+    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
+    m->timed = m->timing;
     return finish_batch(m, b, out);
 }
 
@@ -482,6 +483,13 @@ int gcrf_host_free(void *ptr) {
 }
 
 int64_t gcrf_model_launch_count(const gcrf_model *m) { return m ? m->launches : 0; }
+
+int gcrf_model_set_timing(gcrf_model *m, int32_t enable) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    m->timing = enable != 0;
+    if (!m->timing) m->timed = false;
+    return GCRF_OK;
+}
 
 double gcrf_model_last_kernel_ms(gcrf_model *m) {
     if (!m || !m->timed) return -1.0;

@@ -263,6 +263,9 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
 #endif
 
     // ---- prologue -------------------------------------------------------------------------------------
+    // Programmatic dependent launch: let the next kernel in the stream start its own prologue while this grid
+    // drains, and do not touch the batch (which the previous kernel may still be producing) before it completed.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
         mbar_init(&sBar, 1);
         mbar_init(&sBarTab, 1);
@@ -273,6 +276,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         mbar_expect_tx(&sBarTab, tab_bytes);
         tma_load_1d(sTab, args.model.table_fx, tab_bytes, &sBarTab);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads the batch
     if (tid < 32) {
         const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
         const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0, tid);
@@ -687,12 +691,23 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
 cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches) {
     if (args.csr.G <= 0) return cudaSuccess;
     const int nt_ = (int)plan.num_tiles, tpc = plan.tiles_per_cta;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // pairs with griddepcontrol.* in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err;
     if (args.csr.gene_ptr64)
-        stream_kernel<20, 128, 4, int64_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr64, nt_, tpc);
+        err = cudaLaunchKernelEx(&cfg, stream_kernel<20, 128, 4, int64_t>, args, args.csr.gene_ptr64, nt_, tpc);
     else
-        stream_kernel<20, 128, 4, int32_t><<<plan.grid, 128, plan.smem_bytes, stream>>>(args, args.csr.gene_ptr32, nt_, tpc);
+        err = cudaLaunchKernelEx(&cfg, stream_kernel<20, 128, 4, int32_t>, args, args.csr.gene_ptr32, nt_, tpc);
     if (launches) *launches += 1;
-    return cudaGetLastError();
+    return err;
 }
 
 }  // namespace gcrf

@@ -157,10 +157,12 @@ int gcrf_host_free(void *ptr);
 int64_t gcrf_model_launch_count(const gcrf_model *model);
 
 /*
- * Device time, in milliseconds, of the compute kernels of the LAST marginal call on this handle
- * (CUDA events on the handle's stream around the kernels only, excluding copies).  Synchronises
- * the stream.  Returns < 0 on error.
+ * Kernel timing.  With timing enabled (off by default: the two event records sit between back-to-back
+ * launches) every marginal call brackets its compute kernels with CUDA events on the handle's stream;
+ * gcrf_model_last_kernel_ms returns the device time in milliseconds of the LAST such call (kernels only,
+ * no copies), synchronising the stream, or < 0 when timing was off or on error.
  */
+int gcrf_model_set_timing(gcrf_model *model, int32_t enable);
 double gcrf_model_last_kernel_ms(gcrf_model *model);
 
 #ifdef __cplusplus

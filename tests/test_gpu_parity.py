@@ -234,10 +234,13 @@ def test_device_pointer_mode_matches_host_mode(engine, weights):
     ai = torch.from_numpy(batch.attr_idx).to(dev)
     out = torch.empty(batch.G, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    assert engine.last_kernel_ms() < 0  # timing is off by default
+    engine.set_timing(True)
     engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), batch.C, batch.G, batch.nnz, out.data_ptr())
     engine.synchronize()
     assert numpy.array_equal(out.cpu().numpy(), host)
     assert engine.last_kernel_ms() > 0
+    engine.set_timing(False)
     assert engine.launch_count > 0
 
 

@@ -28,6 +28,7 @@ def main():
     A = len(w.attrs)
     dev = torch.device("cuda:0")
     eng = CRFEngine(w, 0)
+    eng.set_timing(True)
     configs = [
         ("config2 dense 10k contigs", lambda: synth.config2(A)),
         ("config2 shape, 1.4 domains/gene (real-data density)", lambda: synth.config2(A, mean_domains=1.4)),

@@ -16,6 +16,7 @@ mean_domains = float(os.environ.get("QK_DOMAINS", "25"))
 b = synth.config2(len(w.attrs), mean_domains=mean_domains)
 dev = torch.device("cuda:0")
 eng = CRFEngine(w, 0)
+eng.set_timing(True)
 cp = torch.from_numpy(b.contig_ptr).to(dev); gp = torch.from_numpy(b.gene_ptr).to(dev); ai = torch.from_numpy(b.attr_idx).to(dev)
 out = torch.empty(b.G, dtype=torch.float64, device=dev)
 
