@@ -102,6 +102,20 @@ def test_tiles_larger_than_one_staging_round(engine, weights):
                  what="oversized tiles")
 
 
+def test_tiles_full_of_tiny_contigs(engine, weights):
+    """Contigs of 1-3 genes: every 236-gene tile holds > 127 contigs (the streaming kernel's wide contig slice and
+    unbounded contig search), every window is a padded one (or skipped without padding)."""
+    from gecco_b200 import synth
+
+    rng = numpy.random.default_rng(21)
+    lens = rng.integers(1, 4, size=3000)
+    lens[::97] = 25  # a few regular contigs in between
+    batch = synth.make_batch(rng, lens, 3.0, len(weights.attrs), 0.05)
+    for pad in (True, False):
+        assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, pad=pad),
+                     oracle(weights, batch, pad=pad), what=f"tiny contigs pad={pad}")
+
+
 def test_sparse_ecoli_like(engine, weights):
     from gecco_b200 import synth
 

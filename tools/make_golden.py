@@ -242,5 +242,65 @@ def main(ref_dir: str = "/root/reference") -> None:
     print(f"ref_loop_cases: {len(cases)} cases")
 
 
+def make_refine_golden(ref_dir: str = "/root/reference") -> None:
+    """Next row N1: the REFERENCE'S OWN ``gecco.refine.ClusterRefiner`` on random gene tables
+    (probabilities incl. missing ones, annotated / unannotated genes) -> ``tests/golden/refine_cases.json``."""
+    ref = pathlib.Path(ref_dir)
+    crfmod, modelmod, SeqRecord = import_reference_crf(ref)
+    import gecco.refine
+
+    rng = numpy.random.default_rng(31)
+    cases = []
+    settings = [dict(threshold=0.8, n_cds=3, edge_distance=0, trim=True),   # the CLI defaults (--cds 3)
+                dict(threshold=0.8, n_cds=5, edge_distance=0, trim=True),   # the class defaults
+                dict(threshold=0.5, n_cds=1, edge_distance=0, trim=False),
+                dict(threshold=0.8, n_cds=3, edge_distance=2, trim=True),
+                dict(threshold=0.3, n_cds=2, edge_distance=5, trim=False),
+                dict(threshold=0.6, n_cds=4, edge_distance=1, trim=True)]
+    for k in range(24):
+        kw = settings[k % len(settings)]
+        contigs = []
+        genes = []
+        for c in range(int(rng.integers(1, 6))):
+            cid = f"ctg{int(rng.integers(0, 1000)):03d}_{c}"
+            src = SeqRecord(id=cid)
+            n = int(rng.integers(1, 60))
+            # runs of high / low probability so that clusters actually appear
+            probs = []
+            state = rng.random() < 0.4
+            for _ in range(n):
+                if rng.random() < 0.12:
+                    state = not state
+                probs.append(float(numpy.clip(rng.normal(0.93 if state else 0.2, 0.12), 0, 1)))
+            none_mode = rng.random()
+            cg = []
+            for i in range(n):
+                p = probs[i]
+                if none_mode < 0.25 and rng.random() < 0.15:
+                    p = None
+                if none_mode > 0.9:
+                    p = None  # a contig skipped by predict_probabilities(pad=False)
+                annotated = bool(rng.random() < 0.6)
+                doms = [modelmod.Domain("PF00001", 1, 10, "Pfam", 1e-20, 1e-20)] if annotated else []
+                gene = modelmod.Gene(src, 100 + 1000 * i, 900 + 1000 * i, modelmod.Strand.Coding,
+                                     modelmod.Protein(f"{cid}_{i + 1}", None, doms), _probability=p)
+                genes.append(gene)
+                cg.append({"id": gene.id, "p": p, "annotated": annotated})
+            contigs.append({"id": cid, "genes": cg})
+        shuffled = list(genes)
+        rng.shuffle(shuffled)
+        refiner = gecco.refine.ClusterRefiner(criterion="gecco", **kw)
+        clusters = list(refiner.iter_clusters(shuffled))
+        cases.append({"settings": kw, "contigs": contigs,
+                      "clusters": [{"id": cl.id, "genes": [g.id for g in cl.genes]} for cl in clusters]})
+    out = ROOT / "tests" / "golden" / "refine_cases.json"
+    out.write_text(json.dumps({"cases": cases}, indent=0) + "\n")
+    print(f"refine_cases: {len(cases)} cases, {sum(len(c['clusters']) for c in cases)} clusters")
+
+
 if __name__ == "__main__":
-    main(*sys.argv[1:])
+    if len(sys.argv) > 1 and sys.argv[1] == "refine":
+        make_refine_golden(*sys.argv[2:])
+    else:
+        main(*sys.argv[1:])
+        make_refine_golden(*sys.argv[1:])
