@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import pathlib
-from typing import Optional
+from typing import List, Optional, Tuple
 
 import numpy
 
@@ -20,6 +20,8 @@ __all__ = ["CRFEngine", "GcrfError", "load_library", "library_path", "EXPORTED_S
 GCRF_FLAG_DEVICE_PTRS = 0x1
 GCRF_FLAG_OUT_F32 = 0x2
 GCRF_FLAG_PTR64 = 0x4
+GCRF_FLAG_PROB_F32 = 0x8
+GCRF_FLAG_RESET_PER_CONTIG = 0x10
 
 # every symbol include/gecco_crf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTED_SYMBOLS = (
@@ -34,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "gcrf_marginals_chain",
     "gcrf_model_set_vocabulary",
     "gcrf_features_from_accessions",
+    "gcrf_segments",
     "gcrf_host_alloc",
     "gcrf_host_free",
     "gcrf_model_launch_count",
@@ -95,6 +98,9 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_model_set_vocabulary.argtypes = [vp, vp, i32]
     lib.gcrf_features_from_accessions.restype = ctypes.c_int
     lib.gcrf_features_from_accessions.argtypes = [vp, vp, vp, i64, i64, vp, u32]
+    lib.gcrf_segments.restype = ctypes.c_int
+    lib.gcrf_segments.argtypes = [vp, vp, vp, vp, i64, i64, ctypes.c_double, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64,
+                                  ctypes.POINTER(i64), u32]
     lib.gcrf_host_alloc.restype = ctypes.c_int
     lib.gcrf_host_alloc.argtypes = [ctypes.POINTER(vp), u64]
     lib.gcrf_host_free.restype = ctypes.c_int
@@ -138,6 +144,27 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class Segments:
+    """Clusters found by ``gcrf_segments``: parallel arrays, one entry per cluster, in the reference's order."""
+
+    def __init__(self, capacity: int):
+        n = max(1, int(capacity))
+        self.contig = numpy.zeros(n, dtype=numpy.int32)
+        self.begin = numpy.zeros(n, dtype=numpy.int32)
+        self.end = numpy.zeros(n, dtype=numpy.int32)
+        self.ordinal = numpy.zeros(n, dtype=numpy.int32)
+        self.average_p = numpy.zeros(n, dtype=numpy.float64)
+        self.max_p = numpy.zeros(n, dtype=numpy.float64)
+
+    def truncated(self, n: int) -> "Segments":
+        for name in ("contig", "begin", "end", "ordinal", "average_p", "max_p"):
+            setattr(self, name, getattr(self, name)[:n])
+        return self
+
+    def __len__(self) -> int:
+        return len(self.contig)
 
 
 class CRFEngine:
@@ -255,6 +282,41 @@ class CRFEngine:
             self._handle, accession.ctypes.data if len(accession) else None, gene_ptr.ctypes.data,
             len(gene_ptr) - 1, len(accession), out.ctypes.data if len(out) else None, flags))
         return out
+
+    def segments(self, contig_ptr, prob, annotated, *, threshold: float = 0.8, n_cds: int = 5, edge_distance: int = 0,
+                 trim: bool = True, reset_per_contig: bool = False, capacity: Optional[int] = None) -> "Segments":
+        """Threshold + contiguous-segment extraction (``gcrf_segments``; ``gecco/refine.py:120-200``, criterion
+        "gecco") on per-gene probabilities (NaN = no probability) and annotation marks; host buffers, blocking.
+        ``reset_per_contig``: one ``iter_clusters`` call per contig, as ``gecco run`` does (``_common.py:616-618``)."""
+        contig_ptr = numpy.ascontiguousarray(contig_ptr, dtype=numpy.int32)
+        prob = numpy.asarray(prob)
+        flags = GCRF_FLAG_RESET_PER_CONTIG if reset_per_contig else 0
+        if prob.dtype == numpy.float32:
+            prob = numpy.ascontiguousarray(prob)
+            flags |= GCRF_FLAG_PROB_F32
+        else:
+            prob = numpy.ascontiguousarray(prob, dtype=numpy.float64)
+        annotated = numpy.ascontiguousarray(numpy.asarray(annotated) != 0, dtype=numpy.uint8)
+        C, G = len(contig_ptr) - 1, len(prob)
+        if len(annotated) != G:
+            raise ValueError("prob and annotated must have one entry per gene")
+        cap = int(capacity) if capacity is not None else max(1024, G // (8 * max(1, int(n_cds))))
+        while True:
+            seg = Segments(cap)
+            n = ctypes.c_int64(0)
+            _check(self._lib, self._lib.gcrf_segments(
+                self._handle, contig_ptr.ctypes.data, prob.ctypes.data if G else None,
+                annotated.ctypes.data if G else None, C, G, float(threshold), int(n_cds), int(edge_distance),
+                int(bool(trim)), seg.contig.ctypes.data, seg.begin.ctypes.data, seg.end.ctypes.data,
+                seg.ordinal.ctypes.data, seg.average_p.ctypes.data, seg.max_p.ctypes.data, cap, ctypes.byref(n), flags))
+            if n.value <= cap:
+                return seg.truncated(n.value)
+            cap = int(n.value)  # more clusters than the arrays hold: once more with room for all of them
+
+    def extract_segments(self, contig_ptr, prob, annotated, **kwargs) -> List[Tuple[int, int, int]]:
+        """``[(contig, first_gene, last_gene + 1), ...]`` in the reference's order (see ``segments``)."""
+        seg = self.segments(contig_ptr, prob, annotated, **kwargs)
+        return list(zip(seg.contig.tolist(), seg.begin.tolist(), seg.end.tolist()))
 
     # ------------------------------------------------------------------ device-pointer calls
     def set_stream(self, cuda_stream: Optional[int]) -> None:

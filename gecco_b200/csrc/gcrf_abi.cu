@@ -79,6 +79,7 @@ struct gcrf_model {
     bool timing = false;  // record events around the kernels (gcrf_model_set_timing)
     int64_t launches = 0;
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
+    DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
 };
 
 namespace {
@@ -294,6 +295,8 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_attr.release();
     m->b_out.release();
     m->b_scratch.release();
+    m->b_ann.release();
+    m->b_seg.release();
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
     if (m->d_table_fx) cudaFree(m->d_table_fx);
@@ -465,6 +468,99 @@ int gcrf_features_from_accessions(gcrf_model *m, const int32_t *accession, const
     if (host) {
         GCRF_CUDA(cudaMemcpyAsync(attr_idx_out, d_out, (size_t)nnz * 4, cudaMemcpyDeviceToHost, m->stream));
         GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return GCRF_OK;
+}
+
+int gcrf_segments(gcrf_model *m, const int32_t *contig_ptr, const void *prob, const uint8_t *annotated, int64_t C, int64_t G,
+                  double threshold, int32_t n_cds, int32_t edge_distance, int32_t trim, int32_t *seg_contig,
+                  int32_t *seg_begin, int32_t *seg_end, int32_t *seg_ordinal, double *seg_avg_p, double *seg_max_p,
+                  int64_t capacity, int64_t *n_segments, uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (!n_segments) return fail(GCRF_EINVAL, "n_segments is NULL");
+    *n_segments = 0;
+    if (C < 0 || G < 0 || capacity < 0) return fail(GCRF_EINVAL, "negative size");
+    if (G > 0x7fffffff - 1024) return fail(GCRF_EINVAL, "G must fit in int32 (shard the batch)");
+    if ((C == 0) != (G == 0) || C > G) return fail(GCRF_EINVAL, "C and G are inconsistent");
+    if (edge_distance < 0) return fail(GCRF_EINVAL, "edge_distance must be >= 0");
+    if (threshold != threshold) return fail(GCRF_EINVAL, "threshold is NaN");
+    if (G == 0) return GCRF_OK;
+    if (!contig_ptr || !prob || !annotated) return fail(GCRF_EINVAL, "NULL array");
+    if (capacity > 0 && (!seg_contig || !seg_begin || !seg_end || !seg_ordinal || !seg_avg_p || !seg_max_p))
+        return fail(GCRF_EINVAL, "NULL output array");
+    const bool device_ptrs = (flags & GCRF_FLAG_DEVICE_PTRS) != 0;
+    const bool f32 = (flags & GCRF_FLAG_PROB_F32) != 0;
+    DeviceGuard guard(m->device);
+
+    gcrf::SegmentsArgs a{};
+    a.C = C;
+    a.G = G;
+    a.prob_f32 = f32 ? 1 : 0;
+    a.threshold = threshold;
+    a.n_cds = n_cds;
+    a.edge_distance = edge_distance;
+    a.trim = trim ? 1 : 0;
+    a.reset_per_contig = (flags & GCRF_FLAG_RESET_PER_CONTIG) ? 1 : 0;
+    a.capacity = capacity;
+    const size_t cap = (size_t)capacity;
+    // outputs (host mode) and the count live in one block: [count | contig | begin | end | ordinal | avg | max]
+    const size_t out_bytes = device_ptrs ? 16 : 16 + cap * (4 * sizeof(int32_t) + 2 * sizeof(double)) + 64;
+    GCRF_CUDA(m->b_seg.reserve(out_bytes));
+    char *ob = static_cast<char *>(m->b_seg.ptr);
+    a.count = reinterpret_cast<int64_t *>(ob);
+    if (device_ptrs) {
+        a.contig_ptr = contig_ptr;
+        a.prob = prob;
+        a.annotated = annotated;
+        a.seg_contig = seg_contig;
+        a.seg_begin = seg_begin;
+        a.seg_end = seg_end;
+        a.seg_ordinal = seg_ordinal;
+        a.seg_avg_p = seg_avg_p;
+        a.seg_max_p = seg_max_p;
+    } else {
+        if (contig_ptr[0] != 0 || contig_ptr[C] != G) return fail(GCRF_EINVAL, "contig_ptr must start at 0 and end at G");
+        for (int64_t c = 0; c < C; ++c)
+            if (contig_ptr[c + 1] <= contig_ptr[c]) return fail(GCRF_EINVAL, "contig_ptr must be strictly increasing (contig %lld is empty)", (long long)c);
+        const size_t pbytes = (size_t)G * (f32 ? 4 : 8);
+        GCRF_CUDA(m->b_contig.reserve((size_t)(C + 1) * 4));
+        GCRF_CUDA(m->b_out.reserve(pbytes));
+        GCRF_CUDA(m->b_ann.reserve((size_t)G));
+        GCRF_CUDA(cudaMemcpyAsync(m->b_contig.ptr, contig_ptr, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+        GCRF_CUDA(cudaMemcpyAsync(m->b_out.ptr, prob, pbytes, cudaMemcpyHostToDevice, m->stream));
+        GCRF_CUDA(cudaMemcpyAsync(m->b_ann.ptr, annotated, (size_t)G, cudaMemcpyHostToDevice, m->stream));
+        a.contig_ptr = static_cast<const int32_t *>(m->b_contig.ptr);
+        a.prob = m->b_out.ptr;
+        a.annotated = static_cast<const uint8_t *>(m->b_ann.ptr);
+        char *q = ob + 16;
+        a.seg_avg_p = reinterpret_cast<double *>(q); q += cap * sizeof(double);
+        a.seg_max_p = reinterpret_cast<double *>(q); q += cap * sizeof(double);
+        a.seg_contig = reinterpret_cast<int32_t *>(q); q += cap * sizeof(int32_t);
+        a.seg_begin = reinterpret_cast<int32_t *>(q); q += cap * sizeof(int32_t);
+        a.seg_end = reinterpret_cast<int32_t *>(q); q += cap * sizeof(int32_t);
+        a.seg_ordinal = reinterpret_cast<int32_t *>(q);
+    }
+    GCRF_CUDA(m->b_scratch.reserve(gcrf::segments_scratch_bytes(G, m->num_sms)));
+    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    cudaError_t err = gcrf::launch_segments(a, m->b_scratch.ptr, m->num_sms, m->stream, &m->launches);
+    if (err != cudaSuccess) return fail_cuda(err, "launch_segments");
+    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
+    m->timed = m->timing;
+    int64_t count = 0;
+    GCRF_CUDA(cudaMemcpyAsync(&count, a.count, sizeof(count), cudaMemcpyDeviceToHost, m->stream));
+    GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    *n_segments = count;
+    if (!device_ptrs) {
+        const size_t n = (size_t)(count < capacity ? count : capacity);
+        if (n > 0) {
+            GCRF_CUDA(cudaMemcpyAsync(seg_avg_p, a.seg_avg_p, n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(seg_max_p, a.seg_max_p, n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(seg_contig, a.seg_contig, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(seg_begin, a.seg_begin, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(seg_end, a.seg_end, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(seg_ordinal, a.seg_ordinal, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+            GCRF_CUDA(cudaStreamSynchronize(m->stream));
+        }
     }
     return GCRF_OK;
 }

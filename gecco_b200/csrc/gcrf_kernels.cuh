@@ -84,4 +84,26 @@ cudaError_t launch_features(const int32_t *accession, const int32_t *gene_ptr32,
                             const int32_t *lut, int32_t lut_size, int32_t *attr_idx_out, int num_sms,
                             cudaStream_t stream, int64_t *launches);
 
+// Threshold + segment extraction (gcrf_segments.cu; gecco/refine.py:51-200, criterion "gecco").
+struct SegmentsArgs {
+    const int32_t *contig_ptr;  // [C+1]
+    const void *prob;           // double[G] or float[G]; NaN = the gene has no probability
+    int32_t prob_f32;
+    const uint8_t *annotated;   // [G] gene has >= 1 domain (gene.protein.domains is non-empty)
+    int64_t C, G;
+    double threshold;
+    int32_t n_cds, edge_distance, trim;
+    int32_t reset_per_contig;   // in-cluster state starts at False in every contig (one iter_clusters call per contig)
+    // outputs, `capacity` entries each, in the reference's order
+    int32_t *seg_contig, *seg_begin, *seg_end, *seg_ordinal;
+    double *seg_avg_p, *seg_max_p;
+    int64_t capacity;
+    int64_t *count;             // device: number of valid clusters found (may exceed capacity)
+    // scratch, carved by launch_segments
+    uint8_t *flag, *cmark;
+    int32_t *ann_prefix, *end_prefix, *ann_pos, *run_start;
+};
+size_t segments_scratch_bytes(int64_t G, int num_sms);
+cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaStream_t stream, int64_t *launches);
+
 }  // namespace gcrf

@@ -1,0 +1,381 @@
+// gcrf_segments.cu — threshold + contiguous-segment extraction on the marginal kernel's output (next row N1,
+// SURVEY.md §8(f)): the array form of gecco.refine.ClusterRefiner with criterion "gecco"
+// (gecco/refine.py:51-64 GeneGrouper, :183-200 _iter_clusters, :167-180 _trim_cluster, :139-165 _validate_cluster).
+//
+// The reference walks the genes in order with one piece of state (GeneGrouper.in_cluster, which survives contig
+// boundaries because the grouper object is created once, :190).  Here the walk is three chunked scans over the
+// gene axis, each two launches of a persistent grid (chunk summaries, then chunk replay with the carry-in folded
+// from the summaries):
+//
+//   round 1  in-cluster flag        max-scan of (position, p > threshold) over the genes that HAVE a probability
+//                                   (a gene without one — NaN — inherits the state of the last gene that has)
+//   round 2  annotated-gene count   sum-scan (exclusive prefix + compaction array of annotated positions),
+//            raw-run ordinal        sum-scan of run ends (the reference numbers clusters per contig BEFORE validation),
+//            run start              max-scan of "latest breaker": an out-of-cluster gene or a contig start
+//   round 3  valid-cluster count    sum-scan -> clusters are written in the reference's order, no atomics, no sort
+//
+// Every run end evaluates trim + validation in O(1) from those arrays (one binary search over contig_ptr per run).
+// HBM-bound integer/byte work: 9 B/gene read in round 1, <= 18 B/gene of scratch written and read once after that.
+#include "gcrf_kernels.cuh"
+
+namespace gcrf {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 8;
+constexpr int kTile = kThreads * kItems;
+
+struct SumMax {
+    int32_t ann, ends, brk;  // annotated genes, run ends, latest breaker position (max)
+};
+__device__ __forceinline__ SumMax combine(const SumMax &a, const SumMax &b) {
+    return SumMax{a.ann + b.ann, a.ends + b.ends, max(a.brk, b.brk)};
+}
+__device__ __forceinline__ uint32_t combine(uint32_t a, uint32_t b) { return max(a, b); }
+__device__ __forceinline__ int32_t combine(int32_t a, int32_t b) { return a + b; }
+
+__device__ __forceinline__ SumMax shfl_up(const SumMax &v, int d) {
+    return SumMax{__shfl_up_sync(0xffffffffu, v.ann, d), __shfl_up_sync(0xffffffffu, v.ends, d),
+                  __shfl_up_sync(0xffffffffu, v.brk, d)};
+}
+__device__ __forceinline__ uint32_t shfl_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ int32_t shfl_up(int32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+// Exclusive scan of one value per thread across the CTA; *total = combination of all of them.  `ident` is the
+// identity of combine() for T.  sWarp: kThreads/32 + 1 elements of shared scratch.
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T ident, T *sWarp, T *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T o = shfl_up(inc, d);
+        if (lane >= d) inc = combine(o, inc);
+    }
+    __syncthreads();  // sWarp may still be read from the previous call
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    T base = ident;
+    T all = ident;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        const T t = sWarp[w];
+        if (w < warp) base = combine(base, t);
+        all = combine(all, t);
+    }
+    *total = all;
+    T exc = shfl_up(inc, 1);
+    if (lane == 0) exc = ident;
+    return combine(base, exc);
+}
+
+// Combination of partial[0 .. n) (n <= a few thousand chunk summaries), by the whole CTA.
+template <typename T>
+__device__ __forceinline__ T block_fold(const T *partial, int n, T ident, T *sWarp) {
+    T acc = ident;
+    // order matters only for non-commutative operators; max and + commute
+    for (int i = threadIdx.x; i < n; i += kThreads) acc = combine(acc, partial[i]);
+    T total;
+    block_exclusive_scan(acc, ident, sWarp, &total);
+    return total;
+}
+
+struct Geometry {
+    int64_t G;
+    int64_t chunk;  // genes per CTA, a multiple of kTile
+};
+
+__device__ __forceinline__ double load_prob(const void *prob, int f32, int64_t g) {
+    return f32 ? (double)__ldg(static_cast<const float *>(prob) + g) : __ldg(static_cast<const double *>(prob) + g);
+}
+
+// ---- round 1: key of gene g = 2 (g + 1) + (p > threshold) if p is not NaN, else 0; flag[g] = low bit of the max
+//      over [0, g] (0 when no gene so far had a probability: GeneGrouper starts with in_cluster = False, :56)
+//      With reset_per_contig a gene without probability at a contig start counts as "out of cluster": one
+//      iter_clusters call — a fresh GeneGrouper — per contig, as the pipeline does (_common.py:616-618); the
+//      genes behind it inherit that.
+__device__ __forceinline__ uint32_t state_key(const SegmentsArgs &a, int64_t g) {
+    const double p = load_prob(a.prob, a.prob_f32, g);
+    if (p != p) {
+        if (!a.reset_per_contig) return 0u;
+        // nearest defined gene or contig start to the left decides; a start is a defined "False"
+        return a.cmark[g] ? (uint32_t)(2 * (g + 1)) : 0u;
+    }
+    return (uint32_t)(2 * (g + 1)) + (p > a.threshold ? 1u : 0u);
+}
+
+template <bool kReplay>
+__global__ void __launch_bounds__(kThreads)
+state_kernel(const SegmentsArgs a, const Geometry geo, uint32_t *partial) {
+    __shared__ uint32_t sWarp[kThreads / 32 + 1];
+    const int64_t c0 = (int64_t)blockIdx.x * geo.chunk, c1 = min(geo.G, c0 + geo.chunk);
+    uint32_t carry = 0;
+    if (kReplay) carry = block_fold(partial, (int)blockIdx.x, 0u, sWarp);
+    for (int64_t t0 = c0; t0 < c1; t0 += kTile) {
+        const int64_t g0 = t0 + (int64_t)threadIdx.x * kItems;
+        uint32_t key[kItems];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            key[i] = g0 + i < c1 ? state_key(a, g0 + i) : 0u;
+            mine = max(mine, key[i]);
+        }
+        if (!kReplay) {
+            carry = max(carry, mine);  // thread-local; folded once after the loop
+        } else {
+            uint32_t total;
+            uint32_t run = max(carry, block_exclusive_scan(mine, 0u, sWarp, &total));
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                run = max(run, key[i]);
+                if (g0 + i < c1) a.flag[g0 + i] = (uint8_t)(run & 1u);
+            }
+            carry = max(carry, total);
+        }
+    }
+    if (!kReplay) {
+        uint32_t total;
+        block_exclusive_scan(carry, 0u, sWarp, &total);
+        if (threadIdx.x == 0) partial[blockIdx.x] = total;
+    }
+}
+
+// contig starts -> byte marks (cmark is zeroed beforehand; cmark[G] = 1 closes the last contig)
+__global__ void __launch_bounds__(kThreads) mark_kernel(const int32_t *__restrict__ contig_ptr, int64_t C, uint8_t *cmark) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i <= C) cmark[__ldg(contig_ptr + i)] = 1;
+}
+
+// ---- round 2
+__device__ __forceinline__ bool is_run_end(const SegmentsArgs &a, int64_t g, int64_t G) {
+    return a.flag[g] && (g + 1 == G || !a.flag[g + 1] || a.cmark[g + 1]);
+}
+
+template <bool kReplay>
+__global__ void __launch_bounds__(kThreads)
+runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
+    __shared__ SumMax sWarp[kThreads / 32 + 1];
+    const SumMax ident{0, 0, 0};
+    const int64_t c0 = (int64_t)blockIdx.x * geo.chunk, c1 = min(geo.G, c0 + geo.chunk);
+    SumMax carry = ident;
+    if (kReplay) carry = block_fold(partial, (int)blockIdx.x, ident, sWarp);
+    for (int64_t t0 = c0; t0 < c1; t0 += kTile) {
+        const int64_t g0 = t0 + (int64_t)threadIdx.x * kItems;
+        SumMax item[kItems];
+        SumMax mine = ident;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int64_t g = g0 + i;
+            item[i] = ident;
+            if (g < c1) {
+                const bool fl = a.flag[g] != 0;
+                item[i].ann = a.annotated[g] ? 1 : 0;
+                item[i].ends = is_run_end(a, g, geo.G) ? 1 : 0;
+                // latest place a run can have started: right after an out-of-cluster gene, or at a contig start
+                item[i].brk = !fl ? (int32_t)(g + 1) : (a.cmark[g] ? (int32_t)g : 0);
+            }
+            mine = combine(mine, item[i]);
+        }
+        if (!kReplay) {
+            carry = combine(carry, mine);
+        } else {
+            SumMax total;
+            SumMax run = combine(carry, block_exclusive_scan(mine, ident, sWarp, &total));
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                const int64_t g = g0 + i;
+                if (g < c1) {
+                    a.ann_prefix[g] = run.ann;    // annotated genes in [0, g)
+                    a.end_prefix[g] = run.ends;   // run ends in [0, g)
+                    if (item[i].ann) a.ann_pos[run.ann] = (int32_t)g;
+                }
+                run = combine(run, item[i]);
+                if (g < c1) a.run_start[g] = run.brk;  // meaningful where flag[g] is set
+            }
+            carry = combine(carry, total);
+            if (t0 + kTile >= c1 && c1 == geo.G && threadIdx.x == 0) {
+                a.ann_prefix[geo.G] = carry.ann;
+                a.end_prefix[geo.G] = carry.ends;
+            }
+        }
+    }
+    if (!kReplay) {
+        SumMax total;
+        block_exclusive_scan(carry, ident, sWarp, &total);
+        if (threadIdx.x == 0) partial[blockIdx.x] = total;
+    }
+}
+
+// ---- round 3: trim + validate the run that ends at gene g (refine.py:139-180)
+struct Segment {
+    int32_t contig, begin, end, ordinal;
+    bool valid;
+};
+
+__device__ __forceinline__ int32_t overlap(int32_t a0, int32_t a1, int32_t b0, int32_t b1) {
+    return max(0, min(a1, b1) - max(a0, b0));
+}
+
+__device__ Segment evaluate_run(const SegmentsArgs &a, int64_t g) {
+    Segment s;
+    const int32_t rs = a.run_start[g], re = (int32_t)g + 1;
+    int32_t b = rs, t = re;
+    int32_t k0 = a.ann_prefix[b], k1 = a.ann_prefix[t];
+    if (a.trim) {  // _trim_cluster: genes without domains are dropped from both ends
+        if (k1 > k0) {
+            b = a.ann_pos[k0];
+            t = a.ann_pos[k1 - 1] + 1;
+        } else {
+            t = b;  // nothing annotated: the cluster is emptied
+        }
+    }
+    // contig of the run: largest c with contig_ptr[c] <= rs
+    int64_t lo = 0, hi = a.C;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a.contig_ptr + mid) <= rs) lo = mid; else hi = mid;
+    }
+    const int32_t cs = __ldg(a.contig_ptr + lo), ce = __ldg(a.contig_ptr + lo + 1);
+    // _validate_cluster, criterion "gecco": annotated genes of the cluster >= n_cds, and genes of the cluster that
+    // are not among the contig's first / last `edge_distance` ANNOTATED genes >= n_cds
+    const int32_t n_annot = k1 - k0;
+    int32_t n_edge = 0;
+    if (a.edge_distance > 0) {
+        const int32_t A0 = a.ann_prefix[cs], nA = a.ann_prefix[ce] - A0;
+        const int32_t r0 = k0 - A0, r1 = k1 - A0;  // ranks (within the contig) of the cluster's annotated genes
+        const int32_t low1 = min(a.edge_distance, nA), high0 = max(0, nA - a.edge_distance);
+        n_edge = overlap(r0, r1, 0, low1) + overlap(r0, r1, high0, nA) - overlap(r0, r1, high0, low1);
+    }
+    s.contig = (int32_t)lo;
+    s.begin = b;
+    s.end = t;
+    s.ordinal = a.end_prefix[g] - a.end_prefix[cs] + 1;  // enumerate(clusters) per contig, :199-200
+    s.valid = n_annot >= a.n_cds && (t - b) - n_edge >= a.n_cds;
+    return s;
+}
+
+template <bool kReplay>
+__global__ void __launch_bounds__(kThreads)
+emit_kernel(const SegmentsArgs a, const Geometry geo, int32_t *partial) {
+    __shared__ int32_t sWarp[kThreads / 32 + 1];
+    const int64_t c0 = (int64_t)blockIdx.x * geo.chunk, c1 = min(geo.G, c0 + geo.chunk);
+    int32_t carry = 0;
+    if (kReplay) carry = block_fold(partial, (int)blockIdx.x, 0, sWarp);
+    for (int64_t t0 = c0; t0 < c1; t0 += kTile) {
+        const int64_t g0 = t0 + (int64_t)threadIdx.x * kItems;
+        Segment seg[kItems];
+        int32_t mine = 0;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int64_t g = g0 + i;
+            seg[i].valid = false;
+            if (g < c1 && is_run_end(a, g, geo.G)) seg[i] = evaluate_run(a, g);
+            mine += seg[i].valid ? 1 : 0;
+        }
+        if (!kReplay) {
+            carry += mine;
+        } else {
+            int32_t total;
+            int32_t slot = carry + block_exclusive_scan(mine, 0, sWarp, &total);
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                if (seg[i].valid) {
+                    if (slot < a.capacity) {
+                        a.seg_contig[slot] = seg[i].contig;
+                        a.seg_begin[slot] = seg[i].begin;
+                        a.seg_end[slot] = seg[i].end;
+                        a.seg_ordinal[slot] = seg[i].ordinal;
+                    }
+                    ++slot;
+                }
+            }
+            carry += total;
+        }
+    }
+    if (!kReplay) {
+        int32_t total;
+        block_exclusive_scan(carry, 0, sWarp, &total);
+        if (threadIdx.x == 0) partial[blockIdx.x] = total;
+    } else if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        *a.count = (int64_t)carry;
+    }
+}
+
+// per-cluster mean / max of the gene probabilities (gecco/model.py:443-454: genes without one are left out);
+// one warp per cluster, NaN when no gene of the cluster has a probability
+__global__ void __launch_bounds__(kThreads) stats_kernel(const SegmentsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = min(*a.count, a.capacity);
+    for (int64_t s = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5; s < n; s += ((int64_t)gridDim.x * kThreads) >> 5) {
+        const int32_t b = a.seg_begin[s], e = a.seg_end[s];
+        double sum = 0.0, mx = -1.0;
+        int32_t cnt = 0;
+        for (int32_t g = b + lane; g < e; g += 32) {
+            const double p = load_prob(a.prob, a.prob_f32, g);
+            if (p == p) {
+                sum += p;
+                mx = fmax(mx, p);
+                ++cnt;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        }
+        if (lane == 0) {
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            a.seg_avg_p[s] = cnt ? sum / cnt : nan;
+            a.seg_max_p[s] = cnt ? mx : nan;
+        }
+    }
+}
+
+}  // namespace
+
+size_t segments_scratch_bytes(int64_t G, int num_sms) {
+    // flag[G] cmark[G+1] (bytes, padded) + ann_prefix[G+1] end_prefix[G+1] ann_pos[G] run_start[G] + chunk summaries
+    const size_t bytes8 = (((size_t)G + 16) & ~(size_t)15) * 2 + 32;
+    return bytes8 + 4 * ((size_t)G + 4) * 4 + (size_t)num_sms * 8 * sizeof(SumMax) + 64;
+}
+
+cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaStream_t stream, int64_t *launches) {
+    const int64_t G = args.G;
+    cudaError_t err = cudaMemsetAsync(args.count, 0, sizeof(int64_t), stream);
+    if (err != cudaSuccess || G <= 0) return err;
+    // carve the scratch block
+    char *p = static_cast<char *>(scratch);
+    const size_t bytes8 = ((size_t)G + 16) & ~(size_t)15;
+    args.flag = reinterpret_cast<uint8_t *>(p); p += bytes8;
+    args.cmark = reinterpret_cast<uint8_t *>(p); p += bytes8 + 32;
+    args.ann_prefix = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.end_prefix = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.ann_pos = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.run_start = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    void *partial = p;
+
+    const int64_t tiles = (G + kTile - 1) / kTile;
+    int64_t grid = (int64_t)num_sms * 8;
+    if (grid > tiles) grid = tiles;
+    Geometry geo;
+    geo.G = G;
+    geo.chunk = ((tiles + grid - 1) / grid) * kTile;
+    grid = (G + geo.chunk - 1) / geo.chunk;
+    const int n = (int)grid;
+
+    if ((err = cudaMemsetAsync(args.cmark, 0, (size_t)G + 1, stream)) != cudaSuccess) return err;
+    mark_kernel<<<(int)((args.C + 1 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(args.contig_ptr, args.C, args.cmark);
+    state_kernel<false><<<n, kThreads, 0, stream>>>(args, geo, static_cast<uint32_t *>(partial));
+    state_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<uint32_t *>(partial));
+    runs_kernel<false><<<n, kThreads, 0, stream>>>(args, geo, static_cast<SumMax *>(partial));
+    runs_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<SumMax *>(partial));
+    emit_kernel<false><<<n, kThreads, 0, stream>>>(args, geo, static_cast<int32_t *>(partial));
+    emit_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<int32_t *>(partial));
+    stats_kernel<<<num_sms * 2, kThreads, 0, stream>>>(args);
+    if (launches) *launches += 8;
+    return cudaGetLastError();
+}
+
+}  // namespace gcrf

@@ -58,6 +58,12 @@ typedef enum gcrf_status {
                                       stream (gcrf_model_set_stream) and does not synchronise */
 #define GCRF_FLAG_OUT_F32     0x2u /* out is float[G] instead of double[G] */
 #define GCRF_FLAG_PTR64       0x4u /* gene_ptr is int64_t[G+1] (nnz >= 2^31); contig_ptr stays int32 */
+#define GCRF_FLAG_PROB_F32    0x8u /* gcrf_segments: prob is float[G] instead of double[G] */
+#define GCRF_FLAG_RESET_PER_CONTIG 0x10u /* gcrf_segments: the in-cluster state starts at "out" in every
+                                      contig, i.e. one ClusterRefiner.iter_clusters call per contig as
+                                      `gecco run` does (gecco/cli/commands/_common.py:616-618); default: one
+                                      call over all contigs, where the state of GeneGrouper leaks across
+                                      contig boundaries (gecco/refine.py:190) */
 
 typedef struct gcrf_model gcrf_model;
 
@@ -145,6 +151,36 @@ int gcrf_marginals_chain(gcrf_model *model, const int32_t *contig_ptr, const voi
 int gcrf_model_set_vocabulary(gcrf_model *model, const int32_t *accession_of_attr, int32_t A);
 int gcrf_features_from_accessions(gcrf_model *model, const int32_t *accession, const void *gene_ptr,
                                   int64_t G, int64_t nnz, int32_t *attr_idx_out, uint32_t flags);
+
+/*
+ * Threshold + contiguous-segment extraction on the per-gene probabilities — the array form of
+ * gecco.refine.ClusterRefiner(criterion="gecco").iter_clusters (gecco/refine.py:120-200), the immediate
+ * consumer of gcrf_marginals_windowed's output in `gecco run` (gecco/cli/commands/_common.py:594-618).
+ *
+ *   prob[G]       per-gene probability in the same gene order as gcrf_marginals_*; NaN = the gene has no
+ *                 probability (Gene.average_probability is None): it inherits the in-cluster state of the
+ *                 previous gene — also across a contig boundary, like the reference's single GeneGrouper
+ *                 (refine.py:51-64, :190)
+ *   annotated[G]  1 if the gene has at least one domain (gene.protein.domains is non-empty)
+ *   threshold     a gene is in a cluster when prob > threshold                          (refine.py:62)
+ *   trim          drop un-annotated genes from both ends of every run                   (refine.py:167-180)
+ *   n_cds, edge_distance   validation, criterion "gecco"                                (refine.py:139-156)
+ *
+ * Outputs, in the reference's order (contigs as given, runs left to right), `capacity` entries each:
+ *   seg_contig / seg_begin / seg_end   cluster = genes [seg_begin, seg_end) (global gene indices) of that contig
+ *   seg_ordinal   1-based index of the RAW run inside its contig: the reference names clusters
+ *                 "{contig}_cluster_{ordinal}" before validation filters them           (refine.py:199-200)
+ *   seg_avg_p / seg_max_p   mean / max of the probabilities of the cluster's genes that have one
+ *                 (Cluster.average_probability / maximum_probability, gecco/model.py:443-454), else NaN
+ * *n_segments (always a HOST pointer) receives the number of valid clusters; if it exceeds `capacity` only
+ * the first `capacity` were written — call again with larger arrays.  The call synchronises the handle's
+ * stream in both pointer modes (it has to read the count).  Honours GCRF_FLAG_DEVICE_PTRS, GCRF_FLAG_PROB_F32,
+ * GCRF_FLAG_RESET_PER_CONTIG.
+ */
+int gcrf_segments(gcrf_model *model, const int32_t *contig_ptr, const void *prob, const uint8_t *annotated,
+                  int64_t C, int64_t G, double threshold, int32_t n_cds, int32_t edge_distance, int32_t trim,
+                  int32_t *seg_contig, int32_t *seg_begin, int32_t *seg_end, int32_t *seg_ordinal,
+                  double *seg_avg_p, double *seg_max_p, int64_t capacity, int64_t *n_segments, uint32_t flags);
 
 /*
  * Pinned host memory helpers so that host-pointer calls can run their copies at PCIe speed

@@ -25,6 +25,7 @@ Outputs (all small, all derived — no reference source is copied):
 from __future__ import annotations
 
 import csv
+import itertools
 import json
 import pathlib
 import pickle
@@ -291,8 +292,19 @@ def make_refine_golden(ref_dir: str = "/root/reference") -> None:
         rng.shuffle(shuffled)
         refiner = gecco.refine.ClusterRefiner(criterion="gecco", **kw)
         clusters = list(refiner.iter_clusters(shuffled))
-        cases.append({"settings": kw, "contigs": contigs,
-                      "clusters": [{"id": cl.id, "genes": [g.id for g in cl.genes]} for cl in clusters]})
+
+        def dump(cl):
+            return {"id": cl.id, "genes": [g.id for g in cl.genes], "average_p": cl.average_probability,
+                    "max_p": cl.maximum_probability}
+
+        # the pipeline calls iter_clusters once per contig (gecco/cli/commands/_common.py:616-618): a fresh
+        # GeneGrouper each time, so the in-cluster state does not leak from one contig into the next
+        ordered = sorted(genes, key=lambda g: (g.source.id, g.start))
+        per_contig = []
+        for _, group in itertools.groupby(ordered, key=lambda g: g.source.id):
+            per_contig.extend(refiner.iter_clusters(list(group)))
+        cases.append({"settings": kw, "contigs": contigs, "clusters": [dump(cl) for cl in clusters],
+                      "clusters_per_contig_call": [dump(cl) for cl in per_contig]})
     out = ROOT / "tests" / "golden" / "refine_cases.json"
     out.write_text(json.dumps({"cases": cases}, indent=0) + "\n")
     print(f"refine_cases: {len(cases)} cases, {sum(len(c['clusters']) for c in cases)} clusters")
