@@ -73,7 +73,8 @@ def random_table(seed, contigs, mean_len, nan_rate=0.02):
     ptr = numpy.concatenate([[0], numpy.cumsum(lens)]).astype(numpy.int32)
     G = int(ptr[-1])
     walk = numpy.cumsum(rng.normal(0, 0.35, size=G))
-    prob = 1 / (1 + numpy.exp(-(walk - numpy.convolve(walk, numpy.ones(200) / 200, mode="same")) * 2.5))
+    k = min(200, G)  # mode="same" returns max(len) samples: keep the kernel no longer than the walk
+    prob = 1 / (1 + numpy.exp(-(walk - numpy.convolve(walk, numpy.ones(k) / k, mode="same")) * 2.5))
     prob[rng.random(G) < nan_rate] = numpy.nan
     if contigs > 9:
         prob[ptr[7]:ptr[9]] = numpy.nan  # whole contigs without a probability
