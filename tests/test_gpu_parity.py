@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+@pytest.fixture(autouse=True, params=["pipeline", "fused"])
+def device_path(request, monkeypatch):
+    """Every parity test runs through both W=20 device paths: the two-kernel pipeline (default) and the fused
+    kernel (the library reads GCRF_PATH at call time; other window sizes take the generic kernel either way)."""
+    monkeypatch.setenv("GCRF_PATH", request.param)
+    return request.param
+
+
 def oracle(weights, batch, window=20, step=1, pad=True, nthreads=8):
     from oracle import crf_oracle
 
