@@ -42,6 +42,23 @@ EXPORTED_SYMBOLS = (
     "gcrf_model_launch_count",
     "gcrf_model_set_timing",
     "gcrf_model_last_kernel_ms",
+    "gcrf_table_last_error",
+    "gcrf_table_load",
+    "gcrf_table_parse",
+    "gcrf_table_destroy",
+    "gcrf_table_contigs",
+    "gcrf_table_genes",
+    "gcrf_table_domains",
+    "gcrf_table_contig_id",
+    "gcrf_table_gene_id",
+    "gcrf_table_contig_ptr",
+    "gcrf_table_annotated",
+    "gcrf_table_gene_coordinates",
+    "gcrf_table_pack",
+    "gcrf_table_row_gene",
+    "gcrf_table_gene_probabilities",
+    "gcrf_table_write_genes",
+    "gcrf_table_write_features",
 )
 
 _STATUS = {0: "GCRF_OK", -1: "GCRF_EINVAL", -2: "GCRF_ENODEVICE", -3: "GCRF_ECUDA", -4: "GCRF_ENOMEM",
@@ -111,6 +128,40 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_model_set_timing.argtypes = [vp, i32]
     lib.gcrf_model_last_kernel_ms.restype = ctypes.c_double
     lib.gcrf_model_last_kernel_ms.argtypes = [vp]
+    # tables (host code)
+    cp, dbl = ctypes.c_char_p, ctypes.c_double
+    lib.gcrf_table_last_error.restype = cp
+    lib.gcrf_table_last_error.argtypes = []
+    lib.gcrf_table_load.restype = ctypes.c_int
+    lib.gcrf_table_load.argtypes = [cp, ctypes.POINTER(cp), i32, dbl, dbl, ctypes.POINTER(vp)]
+    lib.gcrf_table_parse.restype = ctypes.c_int
+    lib.gcrf_table_parse.argtypes = [cp, u64, ctypes.POINTER(cp), ctypes.POINTER(u64), i32, dbl, dbl, ctypes.POINTER(vp)]
+    lib.gcrf_table_destroy.restype = None
+    lib.gcrf_table_destroy.argtypes = [vp]
+    for name in ("gcrf_table_contigs", "gcrf_table_genes", "gcrf_table_domains"):
+        getattr(lib, name).restype = i64
+        getattr(lib, name).argtypes = [vp]
+    lib.gcrf_table_contig_id.restype = cp
+    lib.gcrf_table_contig_id.argtypes = [vp, i64]
+    lib.gcrf_table_gene_id.restype = cp
+    lib.gcrf_table_gene_id.argtypes = [vp, i64]
+    lib.gcrf_table_contig_ptr.restype = vp
+    lib.gcrf_table_contig_ptr.argtypes = [vp]
+    lib.gcrf_table_annotated.restype = vp
+    lib.gcrf_table_annotated.argtypes = [vp]
+    lib.gcrf_table_gene_coordinates.restype = ctypes.c_int
+    lib.gcrf_table_gene_coordinates.argtypes = [vp, vp, vp]
+    lib.gcrf_table_pack.restype = ctypes.c_int
+    lib.gcrf_table_pack.argtypes = [vp, ctypes.POINTER(cp), i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                    ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.gcrf_table_row_gene.restype = vp
+    lib.gcrf_table_row_gene.argtypes = [vp]
+    lib.gcrf_table_gene_probabilities.restype = ctypes.c_int
+    lib.gcrf_table_gene_probabilities.argtypes = [vp, vp, vp, vp]
+    lib.gcrf_table_write_genes.restype = ctypes.c_int
+    lib.gcrf_table_write_genes.argtypes = [vp, vp, cp]
+    lib.gcrf_table_write_features.restype = ctypes.c_int
+    lib.gcrf_table_write_features.argtypes = [vp, vp, cp]
     _lib = lib
     return lib
 

@@ -80,8 +80,6 @@ struct gcrf_model {
     int64_t launches = 0;
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
-    DeviceBuffer b_pipe;        // two-kernel windowed path: progress flags, run halos, unary odds
-    uint32_t epoch = 0;         // launch counter of that path (flags carry it)
 };
 
 namespace {
@@ -299,7 +297,6 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_scratch.release();
     m->b_ann.release();
     m->b_seg.release();
-    m->b_pipe.release();
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
     if (m->d_table_fx) cudaFree(m->d_table_fx);
@@ -357,30 +354,9 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         args.prof = static_cast<unsigned long long *>(m->b_scratch.ptr);
     }
     gcrf::WindowedPlan plan{};
-    // Device paths for W = 20: "pipeline" (default: gather and window kernels co-resident), "fused" (one kernel,
-    // gcrf_stream.cu) and "generic" (any window size).  GCRF_PATH / GCRF_FORCE_GENERIC=1 select one for A/B tests.
+    // GCRF_FORCE_GENERIC=1 routes W=20 through the generic kernel too (A/B testing of the two device paths)
     const char *force = getenv("GCRF_FORCE_GENERIC");
-    const char *path = getenv("GCRF_PATH");
-    const bool want_generic = (force && force[0] == '1') || (path && !strcmp(path, "generic"));
-    const bool want_fused = path && !strcmp(path, "fused");
-    if (!want_generic && !want_fused && !prof && gcrf::pipeline_supported(args)) {
-        const size_t need = gcrf::pipeline_scratch_bytes(G, m->num_sms);
-        if (need > m->b_pipe.cap) {
-            GCRF_CUDA(cudaStreamSynchronize(m->stream));  // kernels of an earlier call may still use the old block
-            GCRF_CUDA(m->b_pipe.reserve(need));
-            GCRF_CUDA(cudaMemsetAsync(m->b_pipe.ptr, 0, m->b_pipe.cap, m->stream));
-        }
-        if (++m->epoch == 0) {  // wrapped: stale flags would look current
-            GCRF_CUDA(cudaMemsetAsync(m->b_pipe.ptr, 0, m->b_pipe.cap, m->stream));
-            m->epoch = 1;
-        }
-        if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
-        cudaError_t perr = gcrf::launch_pipeline(args, m->b_pipe.ptr, m->epoch, m->num_sms, m->stream, &m->launches);
-        if (perr != cudaSuccess) return fail_cuda(perr, "launch_pipeline");
-        if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-        m->timed = m->timing;
-        return finish_batch(m, b, out);
-    }
+    const bool want_generic = force && force[0] == '1';
     const bool fast = gcrf::stream_supported(args) && !want_generic;
     cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {

@@ -1,4 +1,4 @@
-// gcrf_device.cuh — device helpers shared by the windowed kernels (gcrf_stream.cu, gcrf_pipeline.cu):
+// gcrf_device.cuh — device helpers shared by the windowed kernels (gcrf_stream.cu):
 // fast reciprocal / exponential, the fixed-point table look-up, mbarrier + bulk-async copy (TMA) wrappers,
 // contig searches and the rare slow paths (direct row sums, padded short contigs).  sm_100a only.
 #pragma once

@@ -66,15 +66,6 @@ bool stream_supported(const WindowedArgs &args);
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan);
 cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches);
 
-// The same path as two co-resident kernels (gather | window DP) chained by programmatic dependent launch and
-// progress flags (gcrf_pipeline.cu).  `scratch` holds pipeline_scratch_bytes() bytes that were zeroed when
-// allocated; `epoch` must grow with every launch that shares the scratch.
-bool pipeline_supported(const WindowedArgs &args);
-size_t pipeline_scratch_bytes(int64_t G, int num_sms);
-void pipeline_geometry(int64_t G, int num_sms, int *grid, int *tiles_per_cta, int64_t *num_tiles);
-cudaError_t launch_pipeline(const WindowedArgs &args, void *scratch, uint32_t epoch, int num_sms, cudaStream_t stream,
-                            int64_t *launches);
-
 struct ChainArgs {
     ModelDev model;
     CsrDev csr;

@@ -177,7 +177,10 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         }
     }
     int ga = max(0, min(G, Gs0 + T::keep)), gb = max(0, min(G, Gs0 + T::ng));
-    int64_t pa = (int64_t)__ldg(gene_ptr + ga), pb = (int64_t)__ldg(gene_ptr + gb);
+    // Range ends and row pointers stay in registers exactly as loaded: widening or rebasing them right after the
+    // load would stall every warp for a full global-memory latency at the top of each tile (ncu: 8 % of all stall
+    // samples); the conversions happen one tile later, where the values are consumed.
+    PtrT pa_raw = __ldg(gene_ptr + ga), pb_raw = __ldg(gene_ptr + gb);
     PtrT rowreg[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -185,7 +188,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         rowreg[r] = t <= gb - ga ? __ldg(gene_ptr + ga + t) : 0;
     }
     __syncthreads();  // mbarrier initialised, delta table staged, cursor and halo written
-    if (tid == 0) stage_ids<kCap>(sIdx, csr.attr_idx, pa, pb, &sBar);
+    if (tid == 0) stage_ids<kCap>(sIdx, csr.attr_idx, (int64_t)pa_raw, (int64_t)pb_raw, &sBar);
     uint32_t bar_parity = 0;
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -195,6 +198,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         const int jn0 = ga - Gs;    // local index of the first new gene (= keep, except at the batch edges)
         const int jlo = max(0, -Gs);           // first existing local gene
         const int jhi = min(T::ng, G - Gs);    // one past the last existing local gene
+        const int64_t pa = (int64_t)pa_raw, pb = (int64_t)pb_raw;
         const int64_t a0 = pa & ~(int64_t)3;
         const int64_t total64 = pb - a0;       // staged-range length (ids) from the aligned start
         const bool staged = total64 <= kCap;   // CTA-uniform: the usual case
@@ -215,16 +219,17 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         }
         // ---- B. loads consumed later in the tile: contig slice, next tile's ranges and row pointers
         const int64_t c_first = sCursor;
-        int cp0 = INT_MAX;
-        if (c_first + tid <= csr.C && !GCRF_SKIP(64)) cp0 = __ldg(csr.contig_ptr + c_first + tid) - Gs;
+        const bool cp_ok = c_first + tid <= csr.C && !GCRF_SKIP(64);
+        int cp_raw = 0;  // rebased to local gene coordinates only after the walk
+        if (cp_ok) cp_raw = __ldg(csr.contig_ptr + c_first + tid);
         int nga = 0, ngb = 0;
-        int64_t npa = 0, npb = 0;
+        PtrT npa = 0, npb = 0;
         PtrT nrow[2] = {0, 0};
         if (has_next && !GCRF_SKIP(128)) {
             nga = max(0, min(G, Gs + T::tile_out + T::keep));
             ngb = max(0, min(G, Gs + T::tile_out + T::ng));
-            npa = (int64_t)__ldg(gene_ptr + nga);
-            npb = (int64_t)__ldg(gene_ptr + ngb);
+            npa = __ldg(gene_ptr + nga);
+            npb = __ldg(gene_ptr + ngb);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int t = tid + r * NT;
@@ -252,19 +257,12 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             const int x0 = tid * kWalk;
             int4 *v = reinterpret_cast<int4 *>(sIdx + x0);
             int run = 0;
-            if (x0 + kWalk <= total) {
+            // A thread whose range is only partly staged walks all of it as well: the words beyond `total` are
+            // leftovers of earlier tiles (any bit pattern resolves to a valid table slot) and no row ends there.
+            // A separate rolled loop for that one thread was the slowest path into the barrier below.
+            if (x0 < total) {
 #pragma unroll
                 for (int i = 0; i < kWalk / 4; ++i) {
-                    int4 id = v[i];
-                    run += lookup(sTab, id.x, A); id.x = run;
-                    run += lookup(sTab, id.y, A); id.y = run;
-                    run += lookup(sTab, id.z, A); id.z = run;
-                    run += lookup(sTab, id.w, A); id.w = run;
-                    v[i] = id;
-                }
-            } else {
-#pragma unroll 1
-                for (int i = 0; x0 + 4 * i < total; ++i) {
                     int4 id = v[i];
                     run += lookup(sTab, id.x, A); id.x = run;
                     run += lookup(sTab, id.y, A); id.y = run;
@@ -275,6 +273,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             }
         }
         // contig slice -> shared (its load was issued at the top of the tile; visible after the barrier)
+        const int cp0 = cp_ok ? cp_raw - Gs : INT_MAX;
         sCp[tid] = cp0;
         if (tid == NT - 1) sCp[NT] = INT_MAX;  // sentinel unless the rest of the slice gets loaded below
         // a tile that holds more contigs than one slice entry per thread covers (contigs of 1-2 genes): load the rest
@@ -341,7 +340,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         if (kt >= NT - 1) kt = T::ng;
         const bool has_short = sShort != 0;
         // ---- stage the next tile's ids while this tile's dynamic programme runs
-        if (has_next && tid == 0 && !GCRF_SKIP(32)) stage_ids<kCap>(sIdx, csr.attr_idx, npa, npb, &sBar);
+        if (has_next && tid == 0 && !GCRF_SKIP(32)) stage_ids<kCap>(sIdx, csr.attr_idx, (int64_t)npa, (int64_t)npb, &sBar);
         GCRF_MARK(4);
         if (has_short) {
             // per staged gene: status (1 = padded short contig, 2 = skipped short contig) and the padded windows
@@ -480,7 +479,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         GCRF_MARK(7);
 
         // rotate the prefetched ranges
-        ga = nga; gb = ngb; pa = npa; pb = npb;
+        ga = nga; gb = ngb; pa_raw = npa; pb_raw = npb;
         rowreg[0] = nrow[0];
         rowreg[1] = nrow[1];
     }

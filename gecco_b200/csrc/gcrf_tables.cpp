@@ -1,0 +1,740 @@
+// gcrf_tables.cpp — the table side of `gecco predict`, native and without per-row Python objects
+// (SURVEY.md §8(f) rows N2 and N3).  Host code only; it feeds the CSR arrays of gcrf_marginals_windowed and
+// writes the result tables straight from the probability array.
+//
+// What it restates, in the reference's order of operations (gecco/cli/commands/predict.py:62-100):
+//   * GeneTable.load / FeatureTable.load: tab-separated, a header line naming the columns, any column order,
+//     extra columns ignored, "\n" or "\r\n" line ends (gecco/_base.py:119-131, gecco/model.py:621-637, 773-789);
+//   * annotate_genes: domain rows are attached to genes by protein_id, in row order, across all feature files;
+//     duplicate gene names, unknown protein ids and rows that disagree with their gene are errors
+//     (gecco/cli/commands/_common.py:211-262);
+//   * genes sorted by (sequence_id, start, end), each gene's domains by (domain_start, domain_end), both stable
+//     (predict.py:81-83); ClusterCRF's own sort by (sequence_id, start) and by domain start (crf/__init__.py:199-201)
+//     leaves that order untouched;
+//   * filter_domains: keep i_evalue < e_filter, then pvalue < p_filter; NaN compares false and is dropped
+//     (_common.py:419-448);
+//   * features: the SET of domain names of a gene, first occurrence first, names unknown to the model dropped
+//     (crf/features.py:13-35); domain mode: one row per domain, one empty row per domain-less gene (:38-48);
+//   * GeneTable.from_genes(...).dump / FeatureTable.from_genes(...).dump: columns in schema order, NaN written as
+//     an empty field, a probability column that holds nothing but NaN is left out, "\n" line ends
+//     (gecco/model.py:644-670, 791-813, gecco/_base.py:133-151).  Floats are written in their shortest
+//     round-trip form with Python's repr() layout (1e-05, not 1e-5): that is what the reference's committed
+//     result tables (tests/test_cli/data/BGC0001866.*.tsv, diffed by the Galaxy tool test) contain.
+#include "../../include/gecco_crf_b200.h"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <numeric>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+using sv = std::string_view;
+
+struct GeneRow {
+    sv seq, prot, strand;
+    int64_t start = 0, end = 0;
+};
+
+struct DomainRow {
+    sv seq, prot, strand, name, hmm;
+    int64_t start = 0, end = 0, dstart = 0, dend = 0;
+    double i_evalue = 0, pvalue = 0;
+    int32_t gene = -1;  // index into the sorted genes
+};
+
+struct ParseError {
+    std::string message;
+};
+
+// ---- field-level helpers ---------------------------------------------------------------------------------
+sv unquote(sv f) {
+    if (f.size() >= 2 && f.front() == '"' && f.back() == '"') return f.substr(1, f.size() - 2);
+    return f;
+}
+
+bool parse_int(sv f, int64_t *out) {
+    f = unquote(f);
+    if (f.empty()) return false;
+    const char *b = f.data(), *e = f.data() + f.size();
+    if (*b == '+') ++b;
+    auto r = std::from_chars(b, e, *out);
+    return r.ec == std::errc() && r.ptr == e;
+}
+
+// polars reads an empty float field as null -> NaN (gecco/_base.py:127-130)
+bool parse_float(sv f, double *out) {
+    f = unquote(f);
+    if (f.empty()) {
+        *out = std::numeric_limits<double>::quiet_NaN();
+        return true;
+    }
+    const char *b = f.data(), *e = f.data() + f.size();
+    if (*b == '+') ++b;
+    auto r = std::from_chars(b, e, *out);
+    if (r.ec == std::errc::result_out_of_range) {  // 1e-400 and friends: what strtod would give
+        *out = std::strtod(std::string(f).c_str(), nullptr);
+        return true;
+    }
+    return r.ec == std::errc() && r.ptr == e;
+}
+
+struct Header {
+    std::vector<sv> names;
+    int find(const char *name) const {
+        for (size_t i = 0; i < names.size(); ++i)
+            if (names[i] == name) return (int)i;
+        return -1;
+    }
+};
+
+sv strip_cr(sv line) {
+    if (!line.empty() && line.back() == '\r') line.remove_suffix(1);
+    return line;
+}
+
+void split_tabs(sv line, std::vector<sv> &out) {
+    out.clear();
+    size_t b = 0;
+    for (;;) {
+        const size_t t = line.find('\t', b);
+        if (t == sv::npos) {
+            out.push_back(line.substr(b));
+            return;
+        }
+        out.push_back(line.substr(b, t - b));
+        b = t + 1;
+    }
+}
+
+// Header line -> names; returns the offset of the first data line.
+size_t read_header(sv buf, Header *h) {
+    size_t nl = buf.find('\n');
+    sv line = strip_cr(nl == sv::npos ? buf : buf.substr(0, nl));
+    std::vector<sv> f;
+    split_tabs(line, f);
+    for (sv x : f) h->names.push_back(unquote(x));
+    return nl == sv::npos ? buf.size() : nl + 1;
+}
+
+// Calls row(fields, line_number) for every non-empty data line of buf[begin, end), on `threads` threads over
+// newline-aligned chunks; results keep the file order because every chunk fills its own vector.
+template <typename Row, typename Fn>
+void parse_lines(sv buf, size_t begin, int threads, std::vector<Row> *rows, Fn &&make_row) {
+    const size_t n = buf.size();
+    if (begin >= n) return;
+    if (threads < 1) threads = 1;
+    const size_t min_chunk = 1u << 20;
+    size_t want = (n - begin + min_chunk - 1) / min_chunk;
+    if ((size_t)threads > want) threads = (int)want;
+    std::vector<size_t> cut(threads + 1, n);
+    cut[0] = begin;
+    for (int t = 1; t < threads; ++t) {
+        size_t p = begin + (n - begin) / threads * t;
+        const size_t nl = buf.find('\n', p);
+        cut[t] = nl == sv::npos ? n : nl + 1;
+        if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    }
+    std::vector<std::vector<Row>> parts(threads);
+    std::vector<std::string> errors(threads);
+    auto work = [&](int t) {
+        std::vector<sv> f;
+        size_t p = cut[t];
+        const size_t stop = cut[t + 1];
+        try {
+            while (p < stop) {
+                size_t nl = buf.find('\n', p);
+                if (nl == sv::npos || nl > stop) nl = stop;
+                sv line = strip_cr(buf.substr(p, nl - p));
+                if (!line.empty()) {
+                    split_tabs(line, f);
+                    parts[t].push_back(make_row(f, p));
+                }
+                p = nl + 1;
+            }
+        } catch (const ParseError &e) {
+            errors[t] = e.message;
+        }
+    };
+    if (threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    for (const auto &e : errors)
+        if (!e.empty()) throw ParseError{e};
+    size_t total = rows->size();
+    for (const auto &p : parts) total += p.size();
+    rows->reserve(total);
+    for (auto &p : parts) rows->insert(rows->end(), p.begin(), p.end());
+}
+
+size_t line_number(sv buf, size_t offset) { return 1 + (size_t)std::count(buf.begin(), buf.begin() + offset, '\n'); }
+
+// ---- Python repr() of a double -----------------------------------------------------------------------------
+// Shortest digits that round-trip (std::to_chars), laid out as float.__repr__ does: fixed notation for
+// 1e-4 <= |x| < 1e16 (always with a fractional part), otherwise d[.ddd]e+XX with at least two exponent digits.
+void append_repr(std::string &out, double x) {
+    if (std::isnan(x)) {
+        out += "nan";
+        return;
+    }
+    if (std::isinf(x)) {
+        out += x < 0 ? "-inf" : "inf";
+        return;
+    }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
+    sv s(buf, (size_t)(r.ptr - buf));
+    if (s.front() == '-') {
+        out += '-';
+        s.remove_prefix(1);
+    }
+    const size_t epos = s.find('e');
+    sv mant = s.substr(0, epos);
+    int exp10 = 0;
+    {
+        sv e = s.substr(epos + 1);
+        const bool neg = e.front() == '-';
+        if (e.front() == '-' || e.front() == '+') e.remove_prefix(1);
+        std::from_chars(e.data(), e.data() + e.size(), exp10);
+        if (neg) exp10 = -exp10;
+    }
+    std::string digits;
+    for (char c : mant)
+        if (c != '.') digits += c;
+    if (x == 0.0) {
+        out += "0.0";
+        return;
+    }
+    if (exp10 >= -4 && exp10 < 16) {
+        if (exp10 < 0) {
+            out += "0.";
+            out.append((size_t)(-exp10 - 1), '0');
+            out += digits;
+        } else {
+            const size_t ip = (size_t)exp10 + 1;  // digits in front of the point
+            if (digits.size() <= ip) {
+                out += digits;
+                out.append(ip - digits.size(), '0');
+                out += ".0";
+            } else {
+                out.append(digits, 0, ip);
+                out += '.';
+                out.append(digits, ip, std::string::npos);
+            }
+        }
+    } else {
+        out += digits[0];
+        if (digits.size() > 1) {
+            out += '.';
+            out.append(digits, 1, std::string::npos);
+        }
+        out += 'e';
+        out += exp10 < 0 ? '-' : '+';
+        const int a = exp10 < 0 ? -exp10 : exp10;
+        if (a < 10) out += '0';
+        out += std::to_string(a);
+    }
+}
+
+void append_int(std::string &out, int64_t v) {
+    char buf[24];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    out.append(buf, (size_t)(r.ptr - buf));
+}
+
+}  // namespace
+
+struct gcrf_table {
+    std::vector<std::string> buffers;  // the files; every string_view below points into one of them
+    // genes, in the reference's order (sequence_id, start, end)
+    std::vector<GeneRow> genes;
+    std::vector<int32_t> contig_ptr;           // [C+1] into genes
+    std::vector<std::string> contig_ids;       // [C]
+    std::vector<std::string> gene_ids;         // [G] NUL-terminated copies, built lazily for the accessor
+    // domain rows kept by the filters, grouped by gene, ordered by (domain_start, domain_end)
+    std::vector<DomainRow> domains;
+    std::vector<int64_t> dom_ptr;              // [G+1] into domains
+    std::vector<uint8_t> annotated;            // [G] gene has >= 1 domain left
+    // gcrf_table_pack results
+    int32_t packed_mode = -1;
+    std::vector<int32_t> row_contig_ptr, row_ptr, attr_idx, row_gene;
+};
+
+namespace {
+
+thread_local char t_error[512] = "";
+
+int tfail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int read_file(const char *path, std::string *out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return tfail(GCRF_EINVAL, "cannot open %s", path);
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out->resize(n > 0 ? (size_t)n : 0);
+    const size_t got = n > 0 ? fread(out->data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    if (got != out->size()) return tfail(GCRF_EINVAL, "short read on %s", path);
+    return GCRF_OK;
+}
+
+int column(const Header &h, const char *name, const char *what) {
+    const int i = h.find(name);
+    if (i < 0) throw ParseError{std::string(what) + " table has no column '" + name + "'"};
+    return i;
+}
+
+void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, double e_filter, double p_filter, int threads) {
+    // ---- genes table
+    std::vector<GeneRow> rows;
+    {
+        Header h;
+        const size_t body = read_header(genes_buf, &h);
+        const int c_seq = column(h, "sequence_id", "genes"), c_prot = column(h, "protein_id", "genes"),
+                  c_start = column(h, "start", "genes"), c_end = column(h, "end", "genes"),
+                  c_strand = column(h, "strand", "genes");
+        const size_t need = (size_t)std::max({c_seq, c_prot, c_start, c_end, c_strand}) + 1;
+        parse_lines(genes_buf, body, threads, &rows, [&](const std::vector<sv> &f, size_t off) {
+            if (f.size() < need) throw ParseError{"genes table: line " + std::to_string(line_number(genes_buf, off)) + " has too few fields"};
+            GeneRow g;
+            g.seq = unquote(f[c_seq]);
+            g.prot = unquote(f[c_prot]);
+            // GeneTable.to_genes: Strand.Coding if strand == "+" else Strand.Reverse (gecco/model.py:826)
+            g.strand = unquote(f[c_strand]) == "+" ? sv("+") : sv("-");
+            if (!parse_int(f[c_start], &g.start) || !parse_int(f[c_end], &g.end))
+                throw ParseError{"genes table: bad coordinate on line " + std::to_string(line_number(genes_buf, off))};
+            return g;
+        });
+    }
+    if (rows.size() > 0x7fffff00u) throw ParseError{"too many genes for int32 row pointers; shard the table"};
+    // annotate_genes: gene names are unique (_common.py:217-219)
+    std::unordered_map<sv, int32_t> by_name;
+    by_name.reserve(rows.size() * 2);
+    for (size_t i = 0; i < rows.size(); ++i)
+        if (!by_name.emplace(rows[i].prot, (int32_t)i).second) throw ParseError{"Duplicate gene names in input genes"};
+    // sort by (sequence_id, start, end), stable (predict.py:81)
+    std::vector<int32_t> order(rows.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        const GeneRow &x = rows[a], &y = rows[b];
+        const int c = x.seq.compare(y.seq);
+        if (c != 0) return c < 0;
+        if (x.start != y.start) return x.start < y.start;
+        return x.end < y.end;
+    });
+    std::vector<int32_t> rank(rows.size());
+    t->genes.resize(rows.size());
+    for (size_t k = 0; k < order.size(); ++k) {
+        t->genes[k] = rows[order[k]];
+        rank[order[k]] = (int32_t)k;
+    }
+    const size_t G = t->genes.size();
+    t->contig_ptr.assign(1, 0);
+    for (size_t k = 0; k < G; ++k) {
+        if (k == 0 || t->genes[k].seq != t->genes[k - 1].seq) {
+            if (k) t->contig_ptr.push_back((int32_t)k);
+            t->contig_ids.emplace_back(t->genes[k].seq);
+        }
+    }
+    if (G) t->contig_ptr.push_back((int32_t)G);
+
+    // ---- feature tables, concatenated in the order given (load_features, _common.py:193-208)
+    std::vector<DomainRow> drows;
+    for (sv fb : feature_bufs) {
+        Header h;
+        const size_t body = read_header(fb, &h);
+        if (h.names.empty() || (h.names.size() == 1 && h.names[0].empty())) continue;  // an empty file
+        const int c_seq = column(h, "sequence_id", "features"), c_prot = column(h, "protein_id", "features"),
+                  c_start = column(h, "start", "features"), c_end = column(h, "end", "features"),
+                  c_strand = column(h, "strand", "features"), c_dom = column(h, "domain", "features"),
+                  c_hmm = column(h, "hmm", "features"), c_ev = column(h, "i_evalue", "features"),
+                  c_pv = column(h, "pvalue", "features"), c_ds = column(h, "domain_start", "features"),
+                  c_de = column(h, "domain_end", "features");
+        const size_t need = (size_t)std::max({c_seq, c_prot, c_start, c_end, c_strand, c_dom, c_hmm, c_ev, c_pv, c_ds, c_de}) + 1;
+        parse_lines(fb, body, threads, &drows, [&](const std::vector<sv> &f, size_t off) {
+            auto where = [&] { return " on line " + std::to_string(line_number(fb, off)) + " of a features table"; };
+            if (f.size() < need) throw ParseError{"too few fields" + where()};
+            DomainRow d;
+            d.seq = unquote(f[c_seq]);
+            d.prot = unquote(f[c_prot]);
+            d.strand = unquote(f[c_strand]);
+            d.name = unquote(f[c_dom]);
+            d.hmm = unquote(f[c_hmm]);
+            if (!parse_int(f[c_start], &d.start) || !parse_int(f[c_end], &d.end) || !parse_int(f[c_ds], &d.dstart) ||
+                !parse_int(f[c_de], &d.dend))
+                throw ParseError{"bad integer" + where()};
+            if (!parse_float(f[c_ev], &d.i_evalue) || !parse_float(f[c_pv], &d.pvalue)) throw ParseError{"bad number" + where()};
+            return d;
+        });
+    }
+    // annotate_genes: attach by protein_id, check the row against its gene (_common.py:226-249)
+    std::vector<int64_t> count(G + 1, 0);
+    for (DomainRow &d : drows) {
+        auto it = by_name.find(d.prot);
+        if (it == by_name.end()) throw ParseError{"Unknown protein " + std::string(d.prot) + " in features table"};
+        const GeneRow &g = rows[it->second];
+        const std::string id(d.prot);
+        if (g.seq != d.seq) throw ParseError{"Mismatched source sequence for '" + id + "': '" + std::string(g.seq) + "' != '" + std::string(d.seq) + "'"};
+        if (g.end - g.start != d.end - d.start)
+            throw ParseError{"Mismatched gene length for '" + id + "': " + std::to_string(g.end - g.start) + " != " + std::to_string(d.end - d.start)};
+        if (g.start != d.start) throw ParseError{"Mismatched gene start for '" + id + "': " + std::to_string(g.start) + " != " + std::to_string(d.start)};
+        if (g.end != d.end) throw ParseError{"Mismatched gene end for '" + id + "': " + std::to_string(g.end) + " != " + std::to_string(d.end)};
+        if (g.strand != d.strand) throw ParseError{"Mismatched gene strand for '" + id + "': '" + std::string(g.strand) + "' != '" + std::string(d.strand) + "'"};
+        d.gene = rank[it->second];
+        // filter_domains (_common.py:419-448): NaN < x is false, so NaN rows go as well
+        const bool keep = (std::isnan(e_filter) || d.i_evalue < e_filter) && (std::isnan(p_filter) || d.pvalue < p_filter);
+        if (!keep) d.gene = -1;
+        else ++count[(size_t)d.gene + 1];
+    }
+    // group by gene keeping the row order (counting sort), then order every gene's rows by (start, end), stable
+    t->dom_ptr.assign(G + 1, 0);
+    for (size_t g = 0; g < G; ++g) t->dom_ptr[g + 1] = t->dom_ptr[g] + count[g + 1];
+    t->domains.resize((size_t)t->dom_ptr[G]);
+    {
+        std::vector<int64_t> cursor(t->dom_ptr.begin(), t->dom_ptr.end() - 1);
+        for (const DomainRow &d : drows)
+            if (d.gene >= 0) t->domains[(size_t)cursor[d.gene]++] = d;
+    }
+    t->annotated.assign(G, 0);
+    for (size_t g = 0; g < G; ++g) {
+        auto b = t->domains.begin() + t->dom_ptr[g], e = t->domains.begin() + t->dom_ptr[g + 1];
+        t->annotated[g] = b != e;
+        if (e - b > 1)
+            std::stable_sort(b, e, [](const DomainRow &x, const DomainRow &y) {
+                if (x.dstart != y.dstart) return x.dstart < y.dstart;
+                return x.dend < y.dend;
+            });
+    }
+}
+
+int default_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 1;
+    if (n > 32) n = 32;
+    return (int)n;
+}
+
+int load_buffers(std::vector<std::string> &&bufs, double e_filter, double p_filter, gcrf_table **out) {
+    gcrf_table *t = new (std::nothrow) gcrf_table();
+    if (!t) return tfail(GCRF_ENOMEM, "out of host memory");
+    t->buffers = std::move(bufs);
+    std::vector<sv> feats;
+    for (size_t i = 1; i < t->buffers.size(); ++i) feats.emplace_back(t->buffers[i]);
+    try {
+        build(t, sv(t->buffers[0]), feats, e_filter, p_filter, default_threads());
+    } catch (const ParseError &e) {
+        delete t;
+        return tfail(GCRF_EINVAL, "%s", e.message.c_str());
+    } catch (const std::bad_alloc &) {
+        delete t;
+        return tfail(GCRF_ENOMEM, "out of host memory");
+    }
+    *out = t;
+    return GCRF_OK;
+}
+
+// per-gene (average_p, max_p) from per-row probabilities; NaN = none (Gene.average_probability /
+// maximum_probability, gecco/model.py:274-290)
+void gene_probabilities(const gcrf_table *t, const double *row_prob, size_t g, double *avg, double *mx, int64_t *row_cursor) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    if (!row_prob) {
+        *avg = *mx = nan;
+        return;
+    }
+    const int64_t nd = t->dom_ptr[g + 1] - t->dom_ptr[g];
+    if (t->packed_mode == 0 || nd == 0) {
+        const double p = row_prob[(*row_cursor)++];  // with_probability: the gene's own value
+        *avg = *mx = p;
+        return;
+    }
+    long double sum = 0;
+    double best = nan;
+    int64_t n = 0;
+    for (int64_t k = 0; k < nd; ++k) {
+        const double p = row_prob[(*row_cursor)++];
+        if (std::isnan(p)) continue;
+        sum += p;
+        best = n == 0 ? p : std::max(best, p);
+        ++n;
+    }
+    *avg = n ? (double)(sum / n) : nan;
+    *mx = best;
+}
+
+int write_all(const char *path, const std::string &text) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return tfail(GCRF_EINVAL, "cannot open %s for writing", path);
+    const size_t put = fwrite(text.data(), 1, text.size(), f);
+    const int rc = fclose(f);
+    if (put != text.size() || rc != 0) return tfail(GCRF_EINVAL, "short write on %s", path);
+    return GCRF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gcrf_table_last_error(void) { return t_error; }
+
+int gcrf_table_load(const char *genes_tsv, const char *const *features_tsv, int32_t n_features, double e_filter,
+                    double p_filter, gcrf_table **out) {
+    if (!out) return tfail(GCRF_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!genes_tsv || n_features < 0 || (n_features > 0 && !features_tsv)) return tfail(GCRF_EINVAL, "bad arguments");
+    std::vector<std::string> bufs((size_t)n_features + 1);
+    int rc = read_file(genes_tsv, &bufs[0]);
+    if (rc != GCRF_OK) return rc;
+    for (int32_t i = 0; i < n_features; ++i) {
+        if (!features_tsv[i]) return tfail(GCRF_EINVAL, "features path %d is NULL", i);
+        rc = read_file(features_tsv[i], &bufs[(size_t)i + 1]);
+        if (rc != GCRF_OK) return rc;
+    }
+    return load_buffers(std::move(bufs), e_filter, p_filter, out);
+}
+
+int gcrf_table_parse(const char *genes, uint64_t genes_len, const char *const *features, const uint64_t *features_len,
+                     int32_t n_features, double e_filter, double p_filter, gcrf_table **out) {
+    if (!out) return tfail(GCRF_EINVAL, "out is NULL");
+    *out = nullptr;
+    if ((!genes && genes_len) || n_features < 0 || (n_features > 0 && (!features || !features_len)))
+        return tfail(GCRF_EINVAL, "bad arguments");
+    std::vector<std::string> bufs((size_t)n_features + 1);
+    bufs[0].assign(genes ? genes : "", (size_t)genes_len);
+    for (int32_t i = 0; i < n_features; ++i) bufs[(size_t)i + 1].assign(features[i] ? features[i] : "", (size_t)features_len[i]);
+    return load_buffers(std::move(bufs), e_filter, p_filter, out);
+}
+
+void gcrf_table_destroy(gcrf_table *t) { delete t; }
+
+int64_t gcrf_table_contigs(const gcrf_table *t) { return t ? (int64_t)t->contig_ids.size() : 0; }
+int64_t gcrf_table_genes(const gcrf_table *t) { return t ? (int64_t)t->genes.size() : 0; }
+int64_t gcrf_table_domains(const gcrf_table *t) { return t ? (int64_t)t->domains.size() : 0; }
+
+const char *gcrf_table_contig_id(const gcrf_table *t, int64_t c) {
+    if (!t || c < 0 || c >= (int64_t)t->contig_ids.size()) return nullptr;
+    return t->contig_ids[(size_t)c].c_str();
+}
+
+const char *gcrf_table_gene_id(gcrf_table *t, int64_t g) {
+    if (!t || g < 0 || g >= (int64_t)t->genes.size()) return nullptr;
+    if (t->gene_ids.empty()) {
+        t->gene_ids.reserve(t->genes.size());
+        for (const GeneRow &r : t->genes) t->gene_ids.emplace_back(r.prot);
+    }
+    return t->gene_ids[(size_t)g].c_str();
+}
+
+const int32_t *gcrf_table_contig_ptr(const gcrf_table *t) { return t && !t->contig_ptr.empty() ? t->contig_ptr.data() : nullptr; }
+const uint8_t *gcrf_table_annotated(const gcrf_table *t) { return t && !t->annotated.empty() ? t->annotated.data() : nullptr; }
+
+int gcrf_table_gene_coordinates(const gcrf_table *t, int64_t *start, int64_t *end) {
+    if (!t) return tfail(GCRF_EINVAL, "table is NULL");
+    for (size_t g = 0; g < t->genes.size(); ++g) {
+        if (start) start[g] = t->genes[g].start;
+        if (end) end[g] = t->genes[g].end;
+    }
+    return GCRF_OK;
+}
+
+int gcrf_table_pack(gcrf_table *t, const char *const *attr_names, int32_t A, int32_t feature_type,
+                    const int32_t **contig_ptr, const int32_t **row_ptr, const int32_t **attr_idx, int64_t *rows,
+                    int64_t *nnz) {
+    if (!t) return tfail(GCRF_EINVAL, "table is NULL");
+    if (A < 0 || (A > 0 && !attr_names)) return tfail(GCRF_EINVAL, "bad vocabulary");
+    if (feature_type != 0 && feature_type != 1) return tfail(GCRF_EINVAL, "invalid feature type: %d", feature_type);
+    try {
+        std::unordered_map<sv, int32_t> vocab;
+        vocab.reserve((size_t)A * 2);
+        for (int32_t a = 0; a < A; ++a) {
+            if (!attr_names[a]) return tfail(GCRF_EINVAL, "attribute name %d is NULL", a);
+            if (!vocab.emplace(sv(attr_names[a]), a).second) return tfail(GCRF_EINVAL, "attribute %s appears twice", attr_names[a]);
+        }
+        const size_t G = t->genes.size(), C = t->contig_ids.size();
+        t->row_ptr.assign(1, 0);
+        t->attr_idx.clear();
+        t->row_gene.clear();
+        t->row_contig_ptr.assign(1, 0);
+        std::vector<int32_t> seen((size_t)A, -1);  // last gene that used the attribute: the per-gene set
+        size_t c = 0;
+        for (size_t g = 0; g < G; ++g) {
+            while (c + 1 < C && (int64_t)g >= t->contig_ptr[c + 1]) {
+                t->row_contig_ptr.push_back((int32_t)(t->row_ptr.size() - 1));
+                ++c;
+            }
+            const int64_t b = t->dom_ptr[g], e = t->dom_ptr[g + 1];
+            if (feature_type == 0) {
+                for (int64_t k = b; k < e; ++k) {
+                    auto it = vocab.find(t->domains[(size_t)k].name);
+                    if (it == vocab.end() || seen[(size_t)it->second] == (int32_t)g) continue;
+                    seen[(size_t)it->second] = (int32_t)g;
+                    t->attr_idx.push_back(it->second);
+                }
+                t->row_ptr.push_back((int32_t)t->attr_idx.size());
+                t->row_gene.push_back((int32_t)g);
+            } else {
+                for (int64_t k = b; k < e; ++k) {
+                    auto it = vocab.find(t->domains[(size_t)k].name);
+                    if (it != vocab.end()) t->attr_idx.push_back(it->second);
+                    t->row_ptr.push_back((int32_t)t->attr_idx.size());
+                    t->row_gene.push_back((int32_t)g);
+                }
+                if (b == e) {  // a gene without domains is one empty position (features.py:44-46)
+                    t->row_ptr.push_back((int32_t)t->attr_idx.size());
+                    t->row_gene.push_back((int32_t)g);
+                }
+            }
+            if (t->attr_idx.size() > 0x7fffff00u || t->row_ptr.size() > 0x7fffff00u)
+                return tfail(GCRF_EINVAL, "table too large for int32 row pointers; shard it");
+        }
+        if (G) t->row_contig_ptr.push_back((int32_t)(t->row_ptr.size() - 1));
+        t->packed_mode = feature_type;
+    } catch (const std::bad_alloc &) {
+        return tfail(GCRF_ENOMEM, "out of host memory");
+    }
+    if (contig_ptr) *contig_ptr = t->row_contig_ptr.data();
+    if (row_ptr) *row_ptr = t->row_ptr.data();
+    if (attr_idx) *attr_idx = t->attr_idx.data();
+    if (rows) *rows = (int64_t)t->row_ptr.size() - 1;
+    if (nnz) *nnz = (int64_t)t->attr_idx.size();
+    return GCRF_OK;
+}
+
+const int32_t *gcrf_table_row_gene(const gcrf_table *t) { return t && !t->row_gene.empty() ? t->row_gene.data() : nullptr; }
+
+int gcrf_table_gene_probabilities(const gcrf_table *t, const double *row_prob, double *average_p, double *max_p) {
+    if (!t) return tfail(GCRF_EINVAL, "table is NULL");
+    if (t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");
+    int64_t cursor = 0;
+    for (size_t g = 0; g < t->genes.size(); ++g) {
+        double a, m;
+        gene_probabilities(t, row_prob, g, &a, &m, &cursor);
+        if (average_p) average_p[g] = a;
+        if (max_p) max_p[g] = m;
+    }
+    return GCRF_OK;
+}
+
+int gcrf_table_write_genes(const gcrf_table *t, const double *row_prob, const char *path) {
+    if (!t || !path) return tfail(GCRF_EINVAL, "bad arguments");
+    if (row_prob && t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");
+    const size_t G = t->genes.size();
+    std::vector<double> avg(G), mx(G);
+    bool any_avg = false, any_max = false;
+    int64_t cursor = 0;
+    for (size_t g = 0; g < G; ++g) {
+        gene_probabilities(t, row_prob, g, &avg[g], &mx[g], &cursor);
+        any_avg |= !std::isnan(avg[g]);
+        any_max |= !std::isnan(mx[g]);
+    }
+    std::string out;
+    out.reserve(G * 96 + 128);
+    out += "sequence_id\tprotein_id\tstart\tend\tstrand";
+    if (any_avg) out += "\taverage_p";  // a column of nothing but its default is left out (gecco/_base.py:136-144)
+    if (any_max) out += "\tmax_p";
+    out += '\n';
+    for (size_t g = 0; g < G; ++g) {
+        const GeneRow &r = t->genes[g];
+        out.append(r.seq);
+        out += '\t';
+        out.append(r.prot);
+        out += '\t';
+        append_int(out, r.start);
+        out += '\t';
+        append_int(out, r.end);
+        out += '\t';
+        out.append(r.strand);
+        if (any_avg) {
+            out += '\t';
+            if (!std::isnan(avg[g])) append_repr(out, avg[g]);
+        }
+        if (any_max) {
+            out += '\t';
+            if (!std::isnan(mx[g])) append_repr(out, mx[g]);
+        }
+        out += '\n';
+    }
+    return write_all(path, out);
+}
+
+int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const char *path) {
+    if (!t || !path) return tfail(GCRF_EINVAL, "bad arguments");
+    if (row_prob && t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");
+    const size_t G = t->genes.size();
+    // per-domain probability: the gene's value in protein mode, the row's own in domain mode
+    std::vector<double> dp(t->domains.size(), std::numeric_limits<double>::quiet_NaN());
+    bool any = false;
+    if (row_prob) {
+        int64_t cursor = 0;
+        for (size_t g = 0; g < G; ++g) {
+            const int64_t b = t->dom_ptr[g], e = t->dom_ptr[g + 1];
+            if (t->packed_mode == 0 || b == e) {
+                const double p = row_prob[cursor++];
+                for (int64_t k = b; k < e; ++k) dp[(size_t)k] = p;
+            } else {
+                for (int64_t k = b; k < e; ++k) dp[(size_t)k] = row_prob[cursor++];
+            }
+        }
+        for (double p : dp) any |= !std::isnan(p);
+    }
+    std::string out;
+    out.reserve(t->domains.size() * 160 + 160);
+    out += "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end";
+    if (any) out += "\tcluster_probability";
+    out += '\n';
+    for (size_t g = 0; g < G; ++g) {
+        const GeneRow &r = t->genes[g];
+        for (int64_t k = t->dom_ptr[g]; k < t->dom_ptr[g + 1]; ++k) {
+            const DomainRow &d = t->domains[(size_t)k];
+            out.append(r.seq);
+            out += '\t';
+            out.append(r.prot);
+            out += '\t';
+            append_int(out, r.start);
+            out += '\t';
+            append_int(out, r.end);
+            out += '\t';
+            out.append(r.strand);
+            out += '\t';
+            out.append(d.name);
+            out += '\t';
+            out.append(d.hmm);
+            out += '\t';
+            if (!std::isnan(d.i_evalue)) append_repr(out, d.i_evalue);
+            out += '\t';
+            if (!std::isnan(d.pvalue)) append_repr(out, d.pvalue);
+            out += '\t';
+            append_int(out, d.dstart);
+            out += '\t';
+            append_int(out, d.dend);
+            if (any) {
+                out += '\t';
+                if (!std::isnan(dp[(size_t)k])) append_repr(out, dp[(size_t)k]);
+            }
+            out += '\n';
+        }
+    }
+    return write_all(path, out);
+}
+
+}  // extern "C"

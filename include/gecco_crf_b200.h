@@ -201,6 +201,65 @@ int64_t gcrf_model_launch_count(const gcrf_model *model);
 int gcrf_model_set_timing(gcrf_model *model, int32_t enable);
 double gcrf_model_last_kernel_ms(gcrf_model *model);
 
+/*
+ * Tables (host code; no device needed) — the input and output side of `gecco predict` without per-row
+ * Python objects.  Replaces, in the reference's own order of operations (gecco/cli/commands/predict.py:62-100):
+ *   GeneTable.load / FeatureTable.load           gecco/_base.py:119-131, gecco/model.py:621-637, 773-789
+ *   annotate_genes                               gecco/cli/commands/_common.py:211-262
+ *   the coordinate sorts                         gecco/cli/commands/predict.py:81-83
+ *   filter_domains                               gecco/cli/commands/_common.py:419-448
+ *   extract_features_protein / _domain           gecco/crf/features.py:13-48
+ *   GeneTable.from_genes(...).dump               gecco/model.py:791-813, gecco/_base.py:133-151
+ *   FeatureTable.from_genes(...).dump            gecco/model.py:644-670
+ * The reference reads the tables with polars (Rust) and rebuilds Gene/Protein/Domain objects row by row.
+ *
+ * gcrf_table_load reads one genes table and n_features feature tables (tab-separated, header line, "\n" or
+ * "\r\n"; decompress first if they are gzipped — gcrf_table_parse takes memory buffers).  Genes end up ordered by
+ * (sequence_id, start, end), every gene's domain rows by (domain_start, domain_end), both stable; rows with
+ * i_evalue >= e_filter or pvalue >= p_filter are dropped (pass NaN for "no filter"; `gecco predict` defaults to
+ * p_filter = 1e-9 and no e_filter).  Errors mirror the reference's ValueErrors (duplicate gene names, a feature row
+ * that disagrees with its gene) and are reported through gcrf_table_last_error().
+ */
+typedef struct gcrf_table gcrf_table;
+
+const char *gcrf_table_last_error(void);
+int gcrf_table_load(const char *genes_tsv, const char *const *features_tsv, int32_t n_features, double e_filter,
+                    double p_filter, gcrf_table **out);
+int gcrf_table_parse(const char *genes, uint64_t genes_len, const char *const *features, const uint64_t *features_len,
+                     int32_t n_features, double e_filter, double p_filter, gcrf_table **out);
+void gcrf_table_destroy(gcrf_table *table);
+
+int64_t gcrf_table_contigs(const gcrf_table *table); /* C */
+int64_t gcrf_table_genes(const gcrf_table *table);   /* G */
+int64_t gcrf_table_domains(const gcrf_table *table); /* domain rows left after the filters */
+const char *gcrf_table_contig_id(const gcrf_table *table, int64_t contig);
+const char *gcrf_table_gene_id(gcrf_table *table, int64_t gene);
+const int32_t *gcrf_table_contig_ptr(const gcrf_table *table); /* [C+1] into genes */
+const uint8_t *gcrf_table_annotated(const gcrf_table *table);  /* [G] gene kept >= 1 domain: gcrf_segments' input */
+int gcrf_table_gene_coordinates(const gcrf_table *table, int64_t *start /* [G] or NULL */, int64_t *end /* [G] or NULL */);
+
+/*
+ * The CSR batch of gcrf_marginals_windowed.  attr_names[a] is the model's name of attribute a.  feature_type 0
+ * ("protein"): one row per gene holding the set of its known domain names, first occurrence first; 1 ("domain"):
+ * one row per domain, one empty row per domain-less gene.  The returned arrays belong to the table and stay
+ * valid until the next gcrf_table_pack / gcrf_table_destroy; contig_ptr indexes rows.
+ */
+int gcrf_table_pack(gcrf_table *table, const char *const *attr_names, int32_t A, int32_t feature_type,
+                    const int32_t **contig_ptr, const int32_t **row_ptr, const int32_t **attr_idx, int64_t *rows,
+                    int64_t *nnz);
+const int32_t *gcrf_table_row_gene(const gcrf_table *table); /* [rows] gene of every packed row */
+
+/*
+ * Results.  row_prob[rows] is what gcrf_marginals_windowed returned for the packed batch (NaN = no probability;
+ * NULL = none at all).  Per gene: average_p / max_p as Gene.average_probability / maximum_probability compute them
+ * (gecco/model.py:274-290).  The writers produce the reference's genes / features tables: schema column order, NaN
+ * as an empty field, an all-NaN probability column left out, floats in shortest round-trip form laid out like
+ * Python's repr() — byte-identical to the reference's committed result tables when given the same numbers.
+ */
+int gcrf_table_gene_probabilities(const gcrf_table *table, const double *row_prob, double *average_p, double *max_p);
+int gcrf_table_write_genes(const gcrf_table *table, const double *row_prob, const char *path);
+int gcrf_table_write_features(const gcrf_table *table, const double *row_prob, const char *path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,11 +13,11 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(autouse=True, params=["pipeline", "fused"])
+@pytest.fixture(autouse=True, params=["fused", "generic"])
 def device_path(request, monkeypatch):
-    """Every parity test runs through both W=20 device paths: the two-kernel pipeline (default) and the fused
-    kernel (the library reads GCRF_PATH at call time; other window sizes take the generic kernel either way)."""
-    monkeypatch.setenv("GCRF_PATH", request.param)
+    """Every parity test runs through both device paths for W=20: the fused streaming kernel (default) and the
+    generic kernel that serves every other window size (the library reads GCRF_FORCE_GENERIC at call time)."""
+    monkeypatch.setenv("GCRF_FORCE_GENERIC", "1" if request.param == "generic" else "0")
     return request.param
 
 

@@ -1,0 +1,240 @@
+"""The native table path (csrc/gcrf_tables.cpp): loading, annotating, sorting and
+filtering the genes / features tables, packing them for the kernels and writing the result tables — against the
+row-by-row Python restatement (oracle/tables_oracle.py) and the reference's own committed result tables."""
+import gzip
+import hashlib
+import math
+import pathlib
+import random
+
+import numpy
+import pytest
+
+from oracle import tables_oracle
+
+REFERENCE = pathlib.Path("/root/reference/tests/test_cli/data")
+
+
+def bgc_tables(bgc, *, with_probabilities=False, shuffle=None, crlf=False, reorder=False):
+    """The fixture's two tables as text, from tests/golden/bgc0001866.json."""
+    genes = {g["protein_id"]: g for g in bgc["genes"]}
+    gcols = ["sequence_id", "protein_id", "start", "end", "strand"] + (["average_p", "max_p"] if with_probabilities else [])
+    fcols = ["sequence_id", "protein_id", "start", "end", "strand", "domain", "hmm", "i_evalue", "pvalue", "domain_start",
+             "domain_end"] + (["cluster_probability"] if with_probabilities else [])
+    grows = [{c: g[c] for c in gcols} for g in bgc["genes"]]
+    frows = []
+    for d in bgc["domains"]:
+        g = genes[d["protein_id"]]
+        row = {c: g[c] for c in ("sequence_id", "protein_id", "start", "end", "strand")}
+        row.update({c: d[c] for c in fcols if c in d})
+        frows.append(row)
+    if shuffle is not None:
+        rng = random.Random(shuffle)
+        rng.shuffle(grows)
+        rng.shuffle(frows)
+    if reorder:
+        gcols = gcols[::-1]
+        fcols = fcols[3:] + fcols[:3]
+    nl = "\r\n" if crlf else "\n"
+
+    def fmt(x):
+        return repr(x) if isinstance(x, float) else str(x)
+
+    gtext = nl.join(["\t".join(gcols)] + ["\t".join(fmt(r[c]) for c in gcols) for r in grows]) + nl
+    ftext = nl.join(["\t".join(fcols)] + ["\t".join(fmt(r[c]) for c in fcols) for r in frows]) + nl
+    return gtext, ftext
+
+
+def native(gtext, ftexts, **kw):
+    from gecco_b200.tables import FeatureTables
+
+    return FeatureTables.parse(gtext.encode(), [f.encode() for f in ftexts], **kw)
+
+
+def assert_same_pack(tables, genes, weights, feature_type):
+    packed = tables.pack(weights.attrs, feature_type)
+    cp, rp, ai, rg = tables_oracle.pack(genes, weights.attr_index, feature_type)
+    assert packed.contig_ptr.tolist() == cp
+    assert packed.gene_ptr.tolist() == rp
+    assert packed.attr_idx.tolist() == ai
+    assert tables.row_gene.tolist() == rg
+    return packed
+
+
+def test_result_tables_are_byte_identical_to_the_reference(bgc, weights, tmp_path):
+    """Golden probabilities in -> the reference's committed genes.tsv / features.tsv out (SHA-256 with "\\n" ends)."""
+    gtext, ftext = bgc_tables(bgc)
+    with native(gtext, [ftext]) as tables:
+        assert (tables.contigs, tables.genes, tables.domains) == (1, 23, 37)
+        assert tables.gene_ids == [g["protein_id"] for g in bgc["genes"]]
+        packed = tables.pack(weights.attrs)
+        assert packed.nnz == 35  # 37 rows, PF00550 three times in gene _23
+        prob = numpy.array([g["average_p"] for g in bgc["genes"]])
+        tables.write_genes(tmp_path / "genes.tsv", prob)
+        tables.write_features(tmp_path / "features.tsv", prob)
+        for name, key in (("genes.tsv", "genes_tsv"), ("features.tsv", "features_tsv")):
+            data = (tmp_path / name).read_bytes()
+            assert hashlib.sha256(data).hexdigest() == bgc["sha256_lf"][key], name
+            if (REFERENCE / f"BGC0001866.{name}").exists():
+                assert data == (REFERENCE / f"BGC0001866.{name}").read_bytes().replace(b"\r\n", b"\n")
+        avg, mx = tables.gene_probabilities(prob)
+        assert numpy.array_equal(avg, prob) and numpy.array_equal(mx, prob)
+
+
+@pytest.mark.parametrize("feature_type", ["protein", "domain"])
+@pytest.mark.parametrize("variant", [dict(), dict(shuffle=1, crlf=True), dict(shuffle=2, reorder=True, with_probabilities=True)])
+def test_load_matches_the_row_by_row_restatement(bgc, weights, feature_type, variant, tmp_path):
+    gtext, ftext = bgc_tables(bgc, **variant)
+    for filters in (dict(), dict(p_filter=1e-20), dict(p_filter=None, e_filter=1e-15), dict(p_filter=1e-12, e_filter=1e-10)):
+        genes = tables_oracle.load(gtext.replace("\r\n", "\n"), [ftext.replace("\r\n", "\n")], **filters)
+        with native(gtext, [ftext], **filters) as tables:
+            assert tables.gene_ids == [g["protein_id"] for g in genes]
+            assert tables.domains == sum(len(g["domains"]) for g in genes)
+            assert tables.annotated.tolist() == [int(bool(g["domains"])) for g in genes]
+            packed = assert_same_pack(tables, genes, weights, feature_type)
+            rng = numpy.random.default_rng(7)
+            prob = rng.random(packed.G)
+            prob[rng.random(packed.G) < 0.2] = numpy.nan
+            tables.write_genes(tmp_path / "g.tsv", prob)
+            tables.write_features(tmp_path / "f.tsv", prob)
+            assert (tmp_path / "g.tsv").read_text() == tables_oracle.dump_genes(genes, prob.tolist(), feature_type)
+            assert (tmp_path / "f.tsv").read_text() == tables_oracle.dump_features(genes, prob.tolist(), feature_type)
+            # no probabilities at all: the columns are left out
+            tables.write_genes(tmp_path / "g0.tsv")
+            tables.write_features(tmp_path / "f0.tsv")
+            assert (tmp_path / "g0.tsv").read_text() == tables_oracle.dump_genes(genes)
+            assert (tmp_path / "f0.tsv").read_text() == tables_oracle.dump_features(genes)
+
+
+def synthetic_tables(seed, contigs, genes_per_contig, names):
+    rng = random.Random(seed)
+    grows, frows = [], []
+    for c in range(contigs):
+        cid = f"ctg{rng.randrange(10**6):06d}.{c}"
+        pos = 1
+        for k in range(rng.randrange(1, genes_per_contig * 2)):
+            start = pos + rng.randrange(0, 300)
+            end = start + 3 * rng.randrange(30, 900)
+            pos = start + rng.randrange(0, 50) if rng.random() < 0.1 else end  # a few overlapping / equal starts
+            gid, strand = f"{cid}_{k + 1}", rng.choice("+-")
+            grows.append((cid, gid, start, end, strand))
+            for _ in range(rng.choice([0, 0, 1, 1, 2, 3, 8])):
+                ds = rng.randrange(1, 400)
+                pv = 10 ** rng.uniform(-30, -5)
+                frows.append((cid, gid, start, end, strand, rng.choice(names), "Pfam", pv * 2766, pv, ds,
+                              ds + rng.randrange(5, 200)))
+    rng.shuffle(grows)
+    rng.shuffle(frows)
+    gtext = "sequence_id\tprotein_id\tstart\tend\tstrand\n" + "".join("\t".join(map(str, r)) + "\n" for r in grows)
+    head = "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end\n"
+    half = len(frows) // 2
+    ftexts = [head + "".join("\t".join(repr(x) if isinstance(x, float) else str(x) for x in r) + "\n" for r in part)
+              for part in (frows[:half], frows[half:])]
+    return gtext, ftexts
+
+
+def test_larger_shuffled_tables_in_two_feature_files(weights, tmp_path):
+    """~6k genes / ~12k domain rows, unknown and repeated domain names, rows shuffled, two feature files, gzip."""
+    names = list(weights.attrs[:300]) + ["PF99999", "TIGR00001"]
+    gtext, ftexts = synthetic_tables(11, 60, 100, names)
+    genes = tables_oracle.load(gtext, ftexts)
+    with native(gtext, ftexts) as tables:
+        assert tables.gene_ids == [g["protein_id"] for g in genes]
+        assert tables.contig_ids == list(dict.fromkeys(g["sequence_id"] for g in genes))
+        for feature_type in ("protein", "domain"):
+            assert_same_pack(tables, genes, weights, feature_type)
+        start, end = tables.gene_coordinates()
+        assert start.tolist() == [g["start"] for g in genes] and end.tolist() == [g["end"] for g in genes]
+    # the same through files, one of them gzipped (gecco._meta.zopen sniffs the magic bytes)
+    from gecco_b200.tables import FeatureTables
+
+    (tmp_path / "x.genes.tsv").write_text(gtext)
+    (tmp_path / "a.features.tsv").write_text(ftexts[0])
+    with gzip.open(tmp_path / "b.features.tsv.gz", "wt") as f:
+        f.write(ftexts[1])
+    for paths in ([tmp_path / "a.features.tsv", tmp_path / "b.features.tsv.gz"],):
+        with FeatureTables.load(tmp_path / "x.genes.tsv", paths) as tables:
+            assert tables.gene_ids == [g["protein_id"] for g in genes]
+            assert_same_pack(tables, genes, weights, "protein")
+    with FeatureTables.load(tmp_path / "x.genes.tsv", tmp_path / "a.features.tsv", p_filter=None) as tables:
+        assert tables.domains == ftexts[0].count("\n") - 1
+
+
+def test_table_errors_are_the_reference_s_value_errors(bgc):
+    gtext, ftext = bgc_tables(bgc)
+    lines = gtext.splitlines()
+    with pytest.raises(ValueError, match="Duplicate gene names"):
+        native("\n".join(lines + [lines[1]]) + "\n", [ftext])
+    with pytest.raises(ValueError, match="no column 'strand'"):
+        native(gtext.replace("strand", "direction"), [ftext])
+    flines = ftext.splitlines()
+    bad = flines[1].split("\t")
+    bad[2] = str(int(bad[2]) + 3)
+    with pytest.raises(ValueError, match="Mismatched gene"):
+        native(gtext, ["\n".join([flines[0], "\t".join(bad)]) + "\n"])
+    bad = flines[1].split("\t")
+    bad[1] = "nobody_1"
+    with pytest.raises(ValueError, match="nobody_1"):
+        native(gtext, ["\n".join([flines[0], "\t".join(bad)]) + "\n"])
+    with pytest.raises(FileNotFoundError):
+        from gecco_b200.tables import FeatureTables
+
+        FeatureTables.load("/nonexistent/genes.tsv", [])
+    # empty tables are fine
+    with native("sequence_id\tprotein_id\tstart\tend\tstrand\n", []) as tables:
+        assert (tables.contigs, tables.genes, tables.domains) == (0, 0, 0)
+        assert tables.pack(["PF00001"]).G == 0
+
+
+def test_float_layout_is_python_repr(tmp_path):
+    """Shortest round-trip digits, repr() layout: 1e-05 not 1e-5, 1e+16, 123456789012345.0, 0.0001."""
+    values = [0.0, 1.0, 0.5, 1e-4, 9.999e-5, 1e-5, 1e15, 1e16, 123456789012345.0, 1.7976931348623157e308, 5e-324,
+              0.1 + 0.2, 2.262067179461254e-08, 1 / 3, 100.0, 1234.5, 0.9998703656415205]
+    rng = random.Random(3)
+    values += [rng.random() * 10 ** rng.randrange(-30, 30) for _ in range(2000)]
+    gtext = "sequence_id\tprotein_id\tstart\tend\tstrand\n" + "".join(f"c\tg{i}\t{1 + 10 * i}\t{9 + 10 * i}\t+\n" for i in range(len(values)))
+    with native(gtext, []) as tables:
+        tables.pack([])
+        tables.write_genes(tmp_path / "g.tsv", numpy.array(values))
+        got = [line.split("\t")[5] for line in (tmp_path / "g.tsv").read_text().splitlines()[1:]]
+    assert got == [repr(v) for v in values]
+
+
+@pytest.mark.skipif(not (REFERENCE / "mibig-2.0.proG2.features.tsv").exists(), reason="reference checkout not mounted")
+def test_reference_mibig_tables(weights, mibig):
+    """The reference's own 15,158-gene / 123,031-row training tables: same CSR as the golden arrays."""
+    from gecco_b200.packer import pack_arrays
+    from gecco_b200.tables import FeatureTables
+
+    with FeatureTables.load(REFERENCE / "mibig-2.0.proG2.genes.tsv", REFERENCE / "mibig-2.0.proG2.features.tsv") as tables:
+        assert (tables.contigs, tables.genes, tables.domains) == (18, 15158, 25446)
+        packed = tables.pack(weights.attrs)
+        want = pack_arrays(mibig["gene_contig"], mibig["dom_ptr"], mibig["dom_pfam"], weights)
+        assert numpy.array_equal(packed.contig_ptr, want.contig_ptr)
+        assert numpy.array_equal(packed.gene_ptr, want.gene_ptr)
+        assert numpy.array_equal(packed.attr_idx, want.attr_idx)
+
+
+@pytest.mark.gpu
+def test_predict_tables_on_device(bgc, tmp_path):
+    """Tables in, tables out through the B200: the reference's golden numbers within the north-star tolerance."""
+    from gecco_b200.crf import ClusterCRF
+    from gecco_b200.tables import predict_tables
+
+    gtext, ftext = bgc_tables(bgc, shuffle=5)
+    (tmp_path / "BGC0001866.genes.tsv").write_text(gtext)
+    (tmp_path / "BGC0001866.features.tsv").write_text(ftext)
+    crf = ClusterCRF.trained()
+    tables, prob = predict_tables(tmp_path / "BGC0001866.genes.tsv", tmp_path / "BGC0001866.features.tsv", tmp_path / "out", model=crf)
+    golden = numpy.array([g["average_p"] for g in bgc["genes"]])
+    assert numpy.abs(prob - golden).max() <= 1e-5
+    rows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.genes.tsv").read_text())
+    assert [r["protein_id"] for r in rows] == [g["protein_id"] for g in bgc["genes"]]
+    assert max(abs(float(r["average_p"]) - g["average_p"]) for r, g in zip(rows, bgc["genes"])) <= 1e-5
+    frows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.features.tsv").read_text())
+    assert len(frows) == 37 and all(abs(float(r["cluster_probability"]) - d["cluster_probability"]) <= 1e-5
+                                    for r, d in zip(frows, bgc["domains"]))
+    # the reference finds exactly one cluster on this genome (tests/test_cli/test_run.py:68-70)
+    clusters = tables.segments(crf, prob, threshold=0.8, n_cds=3)
+    assert len(clusters) == 1 and clusters[0][0] == "BGC0001866.1"
+    tables.close()

@@ -118,6 +118,40 @@ def reference_predict(crfmod, modelmod, SeqRecord, weights, contigs, pad=True, w
 # ------------------------------------------------------------------------------------------------
 
 
+def make_bgc_golden(ref_dir: str = "/root/reference") -> None:
+    """tests/golden/bgc0001866.json: the reference's CLI fixture (inputs + python-crfsuite golden probabilities) and the
+    SHA-256 of its two result tables with "\n" line ends, for the byte-exactness test of the native table writers."""
+    import hashlib
+
+    data = pathlib.Path(ref_dir) / "tests" / "test_cli" / "data"
+    golden = ROOT / "tests" / "golden"
+    genes = read_tsv(data / "BGC0001866.genes.tsv")
+    feats = read_tsv(data / "BGC0001866.features.tsv")
+
+    def sha_lf(path):
+        return hashlib.sha256(path.read_bytes().replace(b"\r\n", b"\n")).hexdigest()
+
+    doc = {
+        "source": "zellerlab/GECCO v0.11.0 tests/test_cli/data/BGC0001866.{genes,features}.tsv",
+        "note": "average_p was produced by real python-crfsuite (reference golden); p-values kept for the default p<1e-9 filter",
+        "sha256_lf": {"genes_tsv": sha_lf(data / "BGC0001866.genes.tsv"), "features_tsv": sha_lf(data / "BGC0001866.features.tsv")},
+        "genes": [
+            {"sequence_id": g["sequence_id"], "protein_id": g["protein_id"], "start": int(g["start"]),
+             "end": int(g["end"]), "strand": g["strand"], "average_p": float(g["average_p"]),
+             "max_p": float(g["max_p"])}
+            for g in genes
+        ],
+        "domains": [
+            {"protein_id": f["protein_id"], "domain": f["domain"], "hmm": f["hmm"], "domain_start": int(f["domain_start"]),
+             "domain_end": int(f["domain_end"]), "i_evalue": float(f["i_evalue"]), "pvalue": float(f["pvalue"]),
+             "cluster_probability": float(f["cluster_probability"])}
+            for f in feats
+        ],
+    }
+    (golden / "bgc0001866.json").write_text(json.dumps(doc, indent=1) + "\n")
+    print(f"bgc0001866: {len(doc['genes'])} genes, {len(doc['domains'])} domain rows")
+
+
 def main(ref_dir: str = "/root/reference") -> None:
     ref = pathlib.Path(ref_dir)
     golden = ROOT / "tests" / "golden"
@@ -133,28 +167,8 @@ def main(ref_dir: str = "/root/reference") -> None:
     print(f"model: {len(weights.attrs)} attrs, {int(weights.state_mask.sum())} state features")
 
     data = ref / "tests" / "test_cli" / "data"
-
     # (2) BGC0001866 golden
-    genes = read_tsv(data / "BGC0001866.genes.tsv")
-    feats = read_tsv(data / "BGC0001866.features.tsv")
-    doc = {
-        "source": "zellerlab/GECCO v0.11.0 tests/test_cli/data/BGC0001866.{genes,features}.tsv",
-        "note": "average_p was produced by real python-crfsuite (reference golden); p-values kept for the default p<1e-9 filter",
-        "genes": [
-            {"sequence_id": g["sequence_id"], "protein_id": g["protein_id"], "start": int(g["start"]),
-             "end": int(g["end"]), "strand": g["strand"], "average_p": float(g["average_p"]),
-             "max_p": float(g["max_p"])}
-            for g in genes
-        ],
-        "domains": [
-            {"protein_id": f["protein_id"], "domain": f["domain"], "domain_start": int(f["domain_start"]),
-             "domain_end": int(f["domain_end"]), "i_evalue": float(f["i_evalue"]), "pvalue": float(f["pvalue"]),
-             "cluster_probability": float(f["cluster_probability"])}
-            for f in feats
-        ],
-    }
-    (golden / "bgc0001866.json").write_text(json.dumps(doc, indent=1) + "\n")
-    print(f"bgc0001866: {len(doc['genes'])} genes, {len(doc['domains'])} domain rows")
+    make_bgc_golden(ref_dir)
 
     # (3) mibig through the reference's own loop
     crfmod, modelmod, SeqRecord = import_reference_crf(ref)

@@ -1,10 +1,9 @@
-"""Kernel-only timing of the W=20 device paths on synthetic batches (tuning aid, B200 only).
+"""Kernel-only timing of the windowed device path on the synthetic shapes (tuning aid, B200 only).
 
-    python tools/pipe_time.py [config2|sparse|config4|config5 ...]
+    python tools/path_time.py [config2|sparse|config4|config5 ...]
 
-For every requested shape: the fused kernel, then the two-kernel pipeline over a grid of GCRF_PIPE_CTAS x
-GCRF_PIPE_STAGES (+ GCRF_PIPE_SERIAL=1 for the overlap A/B).  Prints per-call time (events inside the ABI) and
-back-to-back time (20 calls between two stream events), and the max |dp| between the paths.
+Per shape: per-call time (events inside the ABI around the kernel) and back-to-back time (20 calls between two
+stream events), for the fused streaming kernel and the generic kernel.
 """
 import os
 import pathlib
@@ -31,10 +30,8 @@ torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
 
 
-def measure(b, env):
-    for k in ("GCRF_PATH", "GCRF_PIPE_CTAS", "GCRF_PIPE_STAGES", "GCRF_PIPE_SERIAL"):
-        os.environ.pop(k, None)
-    os.environ.update(env)
+def measure(b, generic):
+    os.environ["GCRF_FORCE_GENERIC"] = "1" if generic else "0"
     cp = torch.from_numpy(b.contig_ptr).to(dev); gp = torch.from_numpy(b.gene_ptr).to(dev); ai = torch.from_numpy(b.attr_idx).to(dev)
     out = torch.full((b.G,), -1.0, dtype=torch.float64, device=dev)
 
@@ -62,13 +59,11 @@ def measure(b, env):
 for name in (sys.argv[1:] or ["config2"]):
     b = shapes[name]()
     print(f"== {name}: C={b.C} G={b.G} nnz={b.nnz}", flush=True)
-    lo, med, b2b, ref = measure(b, {"GCRF_PATH": "fused"})
-    print(f"fused                      per-call min {lo*1e3:7.1f} us  median {med*1e3:7.1f} us  back-to-back {b2b*1e3:7.1f} us", flush=True)
-    grid = [(c, s, 0) for c in (1, 2, 3, 4) for s in (1, 2)] + [(2, 2, 1), (3, 1, 1)]
-    for ctas, stages, serial in grid:
-        env = {"GCRF_PATH": "pipeline", "GCRF_PIPE_CTAS": str(ctas), "GCRF_PIPE_STAGES": str(stages), "GCRF_PIPE_SERIAL": str(serial)}
-        lo, med, b2b, got = measure(b, env)
-        ok = numpy.array_equal(numpy.isnan(got), numpy.isnan(ref))
-        err = float(numpy.nanmax(numpy.abs(got - ref))) if ok else float("inf")
-        print(f"pipeline ctas={ctas} stages={stages} serial={serial}  per-call min {lo*1e3:7.1f} us  median {med*1e3:7.1f} us  "
-              f"back-to-back {b2b*1e3:7.1f} us  max|dp vs fused| {err:.1e}", flush=True)
+    ref = None
+    for label, generic in (("fused", False), ("generic", True)):
+        lo, med, b2b, got = measure(b, generic)
+        if ref is None:
+            ref = got
+        err = float(numpy.nanmax(numpy.abs(got - ref)))
+        print(f"{label:8s} per-call min {lo*1e3:7.1f} us  median {med*1e3:7.1f} us  back-to-back {b2b*1e3:7.1f} us  "
+              f"max|dp vs fused| {err:.1e}", flush=True)

@@ -1,4 +1,7 @@
-"""A few calls of the W=20 device path on one synthetic shape (for ncu captures; env selects the path)."""
+"""A few calls of the windowed device path on one synthetic shape (for ncu captures).
+
+    python tools/run_once.py [config2|sparse|config4|config5] [calls]
+"""
 import pathlib
 import sys
 
