@@ -22,6 +22,7 @@ GCRF_FLAG_OUT_F32 = 0x2
 GCRF_FLAG_PTR64 = 0x4
 GCRF_FLAG_PROB_F32 = 0x8
 GCRF_FLAG_RESET_PER_CONTIG = 0x10
+GCRF_FLAG_IDX_U16 = 0x20
 
 # every symbol include/gecco_crf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTED_SYMBOLS = (
@@ -278,7 +279,12 @@ class CRFEngine:
         else:
             gene_ptr = numpy.ascontiguousarray(gene_ptr, dtype=numpy.int32)
             flags = 0
-        attr_idx = numpy.ascontiguousarray(attr_idx, dtype=numpy.int32)
+        if isinstance(attr_idx, numpy.ndarray) and attr_idx.dtype == numpy.uint16:
+            # compact ids (0xFFFF = unknown attribute): half the bytes over PCIe, widened on the device
+            attr_idx = numpy.ascontiguousarray(attr_idx)
+            flags |= GCRF_FLAG_IDX_U16
+        else:
+            attr_idx = numpy.ascontiguousarray(attr_idx, dtype=numpy.int32)
         return contig_ptr, gene_ptr, attr_idx, flags
 
     # ------------------------------------------------------------------ host-pointer calls
@@ -376,9 +382,9 @@ class CRFEngine:
 
     def marginals_windowed_device(self, contig_ptr: int, gene_ptr: int, attr_idx: int, C: int, G: int, nnz: int,
                                   out: int, *, window: Optional[int] = None, step: Optional[int] = None,
-                                  pad: bool = True, f32: bool = False, ptr64: bool = False) -> None:
+                                  pad: bool = True, f32: bool = False, ptr64: bool = False, flags: int = 0) -> None:
         """Enqueue on device-resident arrays given as raw device addresses; returns without syncing."""
-        flags = GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_OUT_F32 if f32 else 0) | (GCRF_FLAG_PTR64 if ptr64 else 0)
+        flags |= GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_OUT_F32 if f32 else 0) | (GCRF_FLAG_PTR64 if ptr64 else 0)
         window = self.weights.window_size if window is None else window
         step = self.weights.window_step if step is None else step
         _check(self._lib, self._lib.gcrf_marginals_windowed(

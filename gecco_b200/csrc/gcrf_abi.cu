@@ -75,11 +75,17 @@ struct gcrf_model {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // overlapped host path of gcrf_marginals_windowed: results of slice k travel back on copy_stream while the
+    // inputs of slice k+1 arrive on `stream` (PCIe is full duplex; the two directions have their own copy engines)
+    static constexpr int kMaxSlices = 8;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_slice[kMaxSlices] = {};
     bool timed = false;
     bool timing = false;  // record events around the kernels (gcrf_model_set_timing)
     int64_t launches = 0;
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
+    DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
 };
 
 namespace {
@@ -115,8 +121,11 @@ struct Batch {
 };
 
 // Validates the common arguments and, in host-pointer mode, stages the inputs on the device.
-int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx,
-                int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags, Batch *b) {
+int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const void *attr_idx_any,
+                int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags, Batch *b, bool defer_copies = false) {
+    const int32_t *attr_idx = static_cast<const int32_t *>(attr_idx_any);
+    const bool idx16 = (flags & GCRF_FLAG_IDX_U16) != 0;
+    if (idx16 && m && m->A >= 0xFFFF) return fail(GCRF_EINVAL, "GCRF_FLAG_IDX_U16 needs a model with fewer than 65535 attributes");
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
     if (C < 0 || G < 0 || nnz < 0) return fail(GCRF_EINVAL, "negative size");
     if (G > 0x7fffffff - 1024) return fail(GCRF_EINVAL, "G must fit in int32 (shard the batch)");
@@ -136,6 +145,13 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
     if (b->device_ptrs) {
         if ((reinterpret_cast<uintptr_t>(attr_idx) & 15u) != 0)
             return fail(GCRF_EINVAL, "device attr_idx must be 16-byte aligned");
+        if (idx16) {  // widen into the library's own buffer
+            GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
+            cudaError_t werr = gcrf::launch_widen_u16(static_cast<const uint16_t *>(attr_idx_any), static_cast<int32_t *>(m->b_attr.ptr),
+                                                      nnz, m->num_sms, m->stream, &m->launches);
+            if (werr != cudaSuccess) return fail_cuda(werr, "launch_widen_u16");
+            attr_idx = static_cast<const int32_t *>(m->b_attr.ptr);
+        }
         b->csr.contig_ptr = contig_ptr;
         b->csr.gene_ptr32 = ptr64 ? nullptr : static_cast<const int32_t *>(gene_ptr);
         b->csr.gene_ptr64 = ptr64 ? static_cast<const int64_t *>(gene_ptr) : nullptr;
@@ -149,12 +165,22 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
     const size_t gene_bytes = (size_t)(G + 1) * (ptr64 ? 8 : 4);
     GCRF_CUDA(m->b_contig.reserve((size_t)(C + 1) * 4));
     GCRF_CUDA(m->b_gene.reserve(gene_bytes));
-    GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 16));
+    GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
     GCRF_CUDA(m->b_out.reserve(b->out_bytes));
-    GCRF_CUDA(cudaMemcpyAsync(m->b_contig.ptr, contig_ptr, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, m->stream));
-    GCRF_CUDA(cudaMemcpyAsync(m->b_gene.ptr, gene_ptr, gene_bytes, cudaMemcpyHostToDevice, m->stream));
-    if (nnz > 0)
-        GCRF_CUDA(cudaMemcpyAsync(m->b_attr.ptr, attr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
+    if (!defer_copies) {
+        GCRF_CUDA(cudaMemcpyAsync(m->b_contig.ptr, contig_ptr, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+        GCRF_CUDA(cudaMemcpyAsync(m->b_gene.ptr, gene_ptr, gene_bytes, cudaMemcpyHostToDevice, m->stream));
+        if (nnz > 0 && idx16) {
+            // half the PCIe bytes: the ids cross as uint16 and are widened on the device
+            GCRF_CUDA(m->b_idx16.reserve((size_t)nnz * 2 + 16));
+            GCRF_CUDA(cudaMemcpyAsync(m->b_idx16.ptr, attr_idx_any, (size_t)nnz * 2, cudaMemcpyHostToDevice, m->stream));
+            cudaError_t werr = gcrf::launch_widen_u16(static_cast<const uint16_t *>(m->b_idx16.ptr), static_cast<int32_t *>(m->b_attr.ptr),
+                                                      nnz, m->num_sms, m->stream, &m->launches);
+            if (werr != cudaSuccess) return fail_cuda(werr, "launch_widen_u16");
+        } else if (nnz > 0) {
+            GCRF_CUDA(cudaMemcpyAsync(m->b_attr.ptr, attr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
+        }
+    }
     b->csr.contig_ptr = static_cast<const int32_t *>(m->b_contig.ptr);
     b->csr.gene_ptr32 = ptr64 ? nullptr : static_cast<const int32_t *>(m->b_gene.ptr);
     b->csr.gene_ptr64 = ptr64 ? static_cast<const int64_t *>(m->b_gene.ptr) : nullptr;
@@ -271,6 +297,11 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
     if ((err = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return cleanup(fail_cuda(err, "cudaStreamCreate"));
     m->stream = m->own_stream;
+    if ((err = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaStreamCreate"));
+    for (int k = 0; k < gcrf_model::kMaxSlices; ++k)
+        if ((err = cudaEventCreateWithFlags(&m->ev_slice[k], cudaEventDisableTiming)) != cudaSuccess)
+            return cleanup(fail_cuda(err, "cudaEventCreate"));
     if ((err = cudaEventCreate(&m->ev_start)) != cudaSuccess) return cleanup(fail_cuda(err, "cudaEventCreate"));
     if ((err = cudaEventCreate(&m->ev_stop)) != cudaSuccess) return cleanup(fail_cuda(err, "cudaEventCreate"));
     m->dev.table = m->d_table;
@@ -297,12 +328,19 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_scratch.release();
     m->b_ann.release();
     m->b_seg.release();
+    m->b_idx16.release();
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
     if (m->d_table_fx) cudaFree(m->d_table_fx);
     if (m->d_lut) cudaFree(m->d_lut);
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
+    for (int k = 0; k < gcrf_model::kMaxSlices; ++k)
+        if (m->ev_slice[k]) cudaEventDestroy(m->ev_slice[k]);
+    if (m->copy_stream) {
+        cudaStreamSynchronize(m->copy_stream);
+        cudaStreamDestroy(m->copy_stream);
+    }
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
 }
@@ -320,39 +358,12 @@ int gcrf_model_synchronize(gcrf_model *m) {
     return GCRF_OK;
 }
 
-int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx,
-                            int64_t C, int64_t G, int64_t nnz, int32_t window, int32_t step, int32_t pad, void *out,
-                            uint32_t flags) {
-    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
-    // gecco/_meta.py:127-130
-    if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
-    if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
-    DeviceGuard guard(m->device);
-    Batch b;
-    int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b);
-    if (rc != GCRF_OK || G == 0) return rc;
+}  // extern "C"
 
-    gcrf::WindowedArgs args{};
-    args.model = m->dev;
-    args.csr = b.csr;
-    args.out = b.d_out;
-    args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
-    args.window = window;
-    args.step = step;
-    args.pad = pad ? 1 : 0;
-    args.prof = nullptr;
-    {
-        const char *skip = getenv("GCRF_DEBUG_SKIP");  // results are WRONG when set: timing experiments only
-        args.debug_skip = skip ? atoi(skip) : 0;
-    }
-    // GCRF_PHASE_PROFILE=1: per-phase cycle counters of the streaming kernel, printed to stderr (tuning aid)
-    const char *prof_env = getenv("GCRF_PHASE_PROFILE");
-    const bool prof = prof_env && prof_env[0] == '1';
-    if (prof) {
-        GCRF_CUDA(m->b_scratch.reserve(16 * sizeof(unsigned long long)));
-        GCRF_CUDA(cudaMemsetAsync(m->b_scratch.ptr, 0, 16 * sizeof(unsigned long long), m->stream));
-        args.prof = static_cast<unsigned long long *>(m->b_scratch.ptr);
-    }
+namespace {
+
+// Plans and enqueues the windowed kernel for one (sub-)batch on the handle's stream.
+int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
     gcrf::WindowedPlan plan{};
     // GCRF_FORCE_GENERIC=1 routes W=20 through the generic kernel too (A/B testing of the two device paths)
     const char *force = getenv("GCRF_FORCE_GENERIC");
@@ -361,7 +372,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {
         cudaGetLastError();
-        return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", window, m->A);
+        return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", args.window, m->A);
     }
     if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
     if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
@@ -381,10 +392,132 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%.1f%%", names[k], tot ? 100.0 * h[k] / tot : 0.0);
         fprintf(stderr, " | cycles/cta=%.0f\n", h[15] ? (double)tot / h[15] : 0.0);
     }
+    return GCRF_OK;
+}
+
+// Host-buffer batches large enough to be PCIe-bound are cut into contig-aligned slices: while slice k's marginals
+// travel back to the host (copy_stream), slice k+1's CSR arrays are already on their way in (stream).  Contigs are
+// independent, so every slice is a plain kernel launch over its own contigs (CsrDev::gene_base).
+int windowed_sliced(gcrf_model *m, gcrf::WindowedArgs args, const int32_t *contig_ptr, const void *gene_ptr,
+                    const int32_t *attr_idx, void *out, int slices) {
+    const gcrf::CsrDev whole = args.csr;
+    const bool ptr64 = whole.gene_ptr64 != nullptr;
+    const size_t psz = ptr64 ? 8 : 4, osz = args.out_f32 ? 4 : 8;
+    auto row = [&](int64_t g) -> int64_t {
+        return ptr64 ? static_cast<const int64_t *>(gene_ptr)[g] : static_cast<const int32_t *>(gene_ptr)[g];
+    };
+    // slice boundaries: contigs, balanced by bytes moved (4 per id, 4 + 8 per gene)
+    auto cost_at = [&](int64_t c) -> double { return 4.0 * (double)row(contig_ptr[c]) + 12.0 * (double)contig_ptr[c]; };
+    const double total = cost_at(whole.C);
+    int64_t cut[gcrf_model::kMaxSlices + 1];
+    cut[0] = 0;
+    for (int k = 1; k < slices; ++k) {
+        const double want = total * k / slices;
+        int64_t lo = cut[k - 1], hi = whole.C;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            if (cost_at(mid) < want) lo = mid + 1; else hi = mid;
+        }
+        cut[k] = lo;
+    }
+    cut[slices] = whole.C;
+    char *d_contig = static_cast<char *>(m->b_contig.ptr), *d_gene = static_cast<char *>(m->b_gene.ptr);
+    char *d_attr = static_cast<char *>(m->b_attr.ptr), *d_out = static_cast<char *>(m->b_out.ptr);
+    int used = 0;
+    for (int k = 0; k < slices; ++k) {
+        const int64_t c0 = cut[k], c1 = cut[k + 1];
+        if (c1 <= c0) continue;
+        const int64_t g0 = contig_ptr[c0], g1 = contig_ptr[c1];
+        const int64_t p0 = row(g0), p1 = row(g1);
+        // every array lands where the whole batch would have put it, so all indices stay valid as they are
+        GCRF_CUDA(cudaMemcpyAsync(d_contig + (size_t)c0 * 4, contig_ptr + c0, (size_t)(c1 - c0 + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+        GCRF_CUDA(cudaMemcpyAsync(d_gene + (size_t)g0 * psz, static_cast<const char *>(gene_ptr) + (size_t)g0 * psz,
+                                  (size_t)(g1 - g0 + 1) * psz, cudaMemcpyHostToDevice, m->stream));
+        if (p1 > p0)
+            GCRF_CUDA(cudaMemcpyAsync(d_attr + (size_t)p0 * 4, attr_idx + p0, (size_t)(p1 - p0) * 4, cudaMemcpyHostToDevice, m->stream));
+        args.csr = whole;
+        args.csr.contig_ptr = reinterpret_cast<const int32_t *>(d_contig) + c0;
+        args.csr.gene_ptr32 = ptr64 ? nullptr : reinterpret_cast<const int32_t *>(d_gene) + g0;
+        args.csr.gene_ptr64 = ptr64 ? reinterpret_cast<const int64_t *>(d_gene) + g0 : nullptr;
+        args.csr.C = c1 - c0;
+        args.csr.G = g1 - g0;
+        args.csr.gene_base = g0;
+        args.out = d_out + (size_t)g0 * osz;
+        const int rc = launch_windowed_path(m, args, false);
+        if (rc != GCRF_OK) return rc;
+        GCRF_CUDA(cudaEventRecord(m->ev_slice[used], m->stream));
+        GCRF_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_slice[used], 0));
+        GCRF_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + (size_t)g0 * osz, d_out + (size_t)g0 * osz, (size_t)(g1 - g0) * osz,
+                                  cudaMemcpyDeviceToHost, m->copy_stream));
+        ++used;
+    }
+    GCRF_CUDA(cudaStreamSynchronize(m->copy_stream));
+    GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    return GCRF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const void *attr_idx,
+                            int64_t C, int64_t G, int64_t nnz, int32_t window, int32_t step, int32_t pad, void *out,
+                            uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    // gecco/_meta.py:127-130
+    if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
+    if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
+    DeviceGuard guard(m->device);
+    // GCRF_PHASE_PROFILE=1: per-phase cycle counters of the streaming kernel, printed to stderr (tuning aid)
+    const char *prof_env = getenv("GCRF_PHASE_PROFILE");
+    const bool prof = prof_env && prof_env[0] == '1';
+    // host buffers, PCIe-bound size: overlap the two copy directions over contig-aligned slices
+    int slices = 1;
+    if (!(flags & (GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_IDX_U16)) && !m->timing && !prof && C >= 2) {
+        const double bytes = 4.0 * (double)nnz + 12.0 * (double)G;
+        const char *env = getenv("GCRF_HOST_SLICES");  // tuning / A-B: 1 turns the overlap off
+        // Off unless asked for: on the PCIe Gen5 hosts measured (config 2, 207 MB in / 16 MB out) the D2H overlap
+        // bought < 1 % and every slice costs ~25 us of launch/copy latency (profiles/r1_e2e_slices.txt).
+        (void)bytes;
+        slices = env ? atoi(env) : 1;
+        if (slices > gcrf_model::kMaxSlices) slices = gcrf_model::kMaxSlices;
+        if (slices > C) slices = (int)C;
+        if (slices < 1) slices = 1;
+    }
+    Batch b;
+    int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b, slices > 1);
+    if (rc != GCRF_OK || G == 0) return rc;
+
+    gcrf::WindowedArgs args{};
+    args.model = m->dev;
+    args.csr = b.csr;
+    args.csr.gene_base = 0;
+    args.out = b.d_out;
+    args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
+    args.window = window;
+    args.step = step;
+    args.pad = pad ? 1 : 0;
+    args.prof = nullptr;
+    {
+        const char *skip = getenv("GCRF_DEBUG_SKIP");  // results are WRONG when set: timing experiments only
+        args.debug_skip = skip ? atoi(skip) : 0;
+    }
+    if (prof) {
+        GCRF_CUDA(m->b_scratch.reserve(16 * sizeof(unsigned long long)));
+        GCRF_CUDA(cudaMemsetAsync(m->b_scratch.ptr, 0, 16 * sizeof(unsigned long long), m->stream));
+        args.prof = static_cast<unsigned long long *>(m->b_scratch.ptr);
+    }
+    if (slices > 1) return windowed_sliced(m, args, contig_ptr, gene_ptr, static_cast<const int32_t *>(attr_idx), out, slices);
+    rc = launch_windowed_path(m, args, prof);
+    if (rc != GCRF_OK) return rc;
     return finish_batch(m, b, out);
 }
 
-int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx,
+}  // extern "C"
+
+extern "C" {
+
+int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const void *attr_idx,
                          int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
     DeviceGuard guard(m->device);

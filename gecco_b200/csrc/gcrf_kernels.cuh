@@ -30,6 +30,10 @@ struct CsrDev {
     const int64_t *gene_ptr64;  // [G+1] or nullptr
     const int32_t *attr_idx;    // [nnz]
     int64_t C, G, nnz;
+    // Sub-batch launches (the overlapped host path): contig_ptr, gene_ptr and out point at the slice's first
+    // contig / gene, but the VALUES of contig_ptr still count genes from the start of the whole batch:
+    // gene_base is subtracted from them.  gene_ptr values keep indexing the whole attr_idx array.
+    int64_t gene_base;
 };
 
 struct WindowedArgs {
@@ -83,6 +87,9 @@ cudaError_t launch_chain(const ChainArgs &args, int num_sms, cudaStream_t stream
 cudaError_t launch_features(const int32_t *accession, const int32_t *gene_ptr32, const int64_t *gene_ptr64, int64_t G,
                             const int32_t *lut, int32_t lut_size, int32_t *attr_idx_out, int num_sms,
                             cudaStream_t stream, int64_t *launches);
+
+// uint16 attribute ids -> int32 (0xFFFF -> -1); out holds at least round_up(n, 8) entries
+cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int num_sms, cudaStream_t stream, int64_t *launches);
 
 // Threshold + segment extraction (gcrf_segments.cu; gecco/refine.py:51-200, criterion "gecco").
 struct SegmentsArgs {

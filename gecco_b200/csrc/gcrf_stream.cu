@@ -137,7 +137,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads the batch
     if (tid < 32) {
         const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
-        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0, tid);
+        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0 + csr.gene_base, tid);
         if (tid == 0) sCursor = c;
     }
     // New genes of a tile = local genes [keep, ng).  The run's first halo [0, keep) is gathered right here into the
@@ -273,14 +273,15 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             }
         }
         // contig slice -> shared (its load was issued at the top of the tile; visible after the barrier)
-        const int cp0 = cp_ok ? cp_raw - Gs : INT_MAX;
+        const int GsA = Gs + (int)csr.gene_base;  // local gene 0 in the units of contig_ptr's values
+        const int cp0 = cp_ok ? cp_raw - GsA : INT_MAX;
         sCp[tid] = cp0;
         if (tid == NT - 1) sCp[NT] = INT_MAX;  // sentinel unless the rest of the slice gets loaded below
         // a tile that holds more contigs than one slice entry per thread covers (contigs of 1-2 genes): load the rest
         const bool wide_slice = __syncthreads_or(tid == NT - 1 && cp0 < T::ng) != 0;
         if (wide_slice) {
             for (int k = NT + tid; k <= T::ng + 1; k += NT)
-                sCp[k] = c_first + k <= csr.C ? __ldg(csr.contig_ptr + c_first + k) - Gs : INT_MAX;
+                sCp[k] = c_first + k <= csr.C ? __ldg(csr.contig_ptr + c_first + k) - GsA : INT_MAX;
             __syncthreads();
         }
         GCRF_MARK(2);

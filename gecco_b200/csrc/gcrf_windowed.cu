@@ -189,7 +189,7 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
         // ---- B. contig slice: sCp[k] = contig_ptr[c_first + k] - Gs, k = 0 .. ngt+1
         if (tile == tile_begin) {
             if (warp == 0) {
-                const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, Gs, lane);
+                const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, Gs + csr.gene_base, lane);
                 if (lane == 0) sCursor = c;
             }
             __syncthreads();
@@ -197,7 +197,7 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
         c_first = sCursor;
         for (int k = tid; k <= ngt + 1; k += kThreads) {
             const int64_t c = c_first + k;
-            sCp[k] = c <= csr.C ? __ldg(csr.contig_ptr + c) - Gs : INT_MAX;
+            sCp[k] = c <= csr.C ? __ldg(csr.contig_ptr + c) - (Gs + (int)csr.gene_base) : INT_MAX;
         }
         __syncthreads();  // sTab, sPtr, sCp visible
 

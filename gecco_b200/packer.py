@@ -18,7 +18,7 @@ from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy
 
-__all__ = ["PackedGenes", "pack_genes", "pack_records", "pack_arrays", "pfam_lut"]
+__all__ = ["PackedGenes", "pack_genes", "pack_records", "pack_arrays", "pfam_lut", "compact_ids"]
 
 
 @dataclass
@@ -125,6 +125,17 @@ def pack_genes(genes: Iterable[Any], attr_index: Dict[str, int], feature_type: s
             contig_lens[-1] += 1
             gene_lens.append(0)
     return _finish(contig_lens, gene_lens, attrs, contig_ids=contig_ids), genes, slices
+
+
+def compact_ids(attr_idx: numpy.ndarray, num_attrs: int) -> numpy.ndarray:
+    """``int32`` attribute ids -> ``uint16`` with ``0xFFFF`` for every id outside ``[0, num_attrs)`` — the layout of
+    ``GCRF_FLAG_IDX_U16``: the ids are what a host-buffer call moves over PCIe, this halves them."""
+    if num_attrs >= 0xFFFF:
+        raise ValueError("compact ids need a model with fewer than 65535 attributes")
+    attr_idx = numpy.asarray(attr_idx)
+    out = attr_idx.astype(numpy.uint16)
+    out[(attr_idx < 0) | (attr_idx >= num_attrs)] = 0xFFFF
+    return out
 
 
 def pfam_lut(attrs: Sequence[str]) -> numpy.ndarray:

@@ -58,6 +58,8 @@ typedef enum gcrf_status {
                                       stream (gcrf_model_set_stream) and does not synchronise */
 #define GCRF_FLAG_OUT_F32     0x2u /* out is float[G] instead of double[G] */
 #define GCRF_FLAG_PTR64       0x4u /* gene_ptr is int64_t[G+1] (nnz >= 2^31); contig_ptr stays int32 */
+#define GCRF_FLAG_IDX_U16     0x20u /* attr_idx is uint16_t[nnz] (0xFFFF = unknown attribute; models with fewer than
+                                      65535 attributes): half the bytes over PCIe, widened on the device */
 #define GCRF_FLAG_PROB_F32    0x8u /* gcrf_segments: prob is float[G] instead of double[G] */
 #define GCRF_FLAG_RESET_PER_CONTIG 0x10u /* gcrf_segments: the in-cluster state starts at "out" in every
                                       contig, i.e. one ClusterRefiner.iter_clusters call per contig as
@@ -122,7 +124,7 @@ int gcrf_model_synchronize(gcrf_model *model);
  * measured <= 2e-6, tests/test_gpu_parity.py).
  */
 int gcrf_marginals_windowed(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
-                            const int32_t *attr_idx, int64_t C, int64_t G, int64_t nnz,
+                            const void *attr_idx, int64_t C, int64_t G, int64_t nnz,
                             int32_t window, int32_t step, int32_t pad, void *out, uint32_t flags);
 
 /*
@@ -132,7 +134,7 @@ int gcrf_marginals_windowed(gcrf_model *model, const int32_t *contig_ptr, const 
  * for callers that want the un-windowed marginal, and is the deep-chain path (BASELINE config 5).
  */
 int gcrf_marginals_chain(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
-                         const int32_t *attr_idx, int64_t C, int64_t G, int64_t nnz, void *out,
+                         const void *attr_idx, int64_t C, int64_t G, int64_t nnz, void *out,
                          uint32_t flags);
 
 /*

@@ -266,6 +266,55 @@ def test_device_pointer_mode_matches_host_mode(engine, weights):
     assert engine.launch_count > 0
 
 
+def test_compact_uint16_ids_are_bit_identical(engine, weights):
+    """GCRF_FLAG_IDX_U16: uint16 ids (0xFFFF = unknown) widened on the device give the same bits, host and device mode."""
+    import torch
+    from gecco_b200 import synth
+    from gecco_b200._lib import GCRF_FLAG_IDX_U16
+    from gecco_b200.packer import compact_ids
+
+    for batch in (synth.config2(len(weights.attrs), contigs=120), synth.ragged_edge_cases(len(weights.attrs)),
+                  synth.config2(len(weights.attrs), contigs=3, mean_genes=2.0, mean_domains=1.0)):
+        want = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+        small = compact_ids(batch.attr_idx, len(weights.attrs))
+        assert small.dtype == numpy.uint16 and small.nbytes * 2 == batch.attr_idx.nbytes
+        assert numpy.array_equal(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, small), want, equal_nan=True)
+        assert numpy.array_equal(engine.marginals_chain(batch.contig_ptr, batch.gene_ptr, small),
+                                 engine.marginals_chain(batch.contig_ptr, batch.gene_ptr, batch.attr_idx), equal_nan=True)
+        dev = torch.device("cuda:0")
+        cp, gp = torch.from_numpy(batch.contig_ptr).to(dev), torch.from_numpy(batch.gene_ptr).to(dev)
+        ai = torch.from_numpy(small.view(numpy.int16)).to(dev)
+        out = torch.empty(batch.G, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), batch.C, batch.G, batch.nnz, out.data_ptr(),
+                                         flags=GCRF_FLAG_IDX_U16)
+        engine.synchronize()
+        assert numpy.array_equal(out.cpu().numpy(), want, equal_nan=True)
+
+
+def test_overlapped_host_slices_are_bit_identical(engine, weights, monkeypatch):
+    """The host-buffer path cuts PCIe-bound batches into contig-aligned slices (copies of both directions overlap);
+    forced here on small batches: same bits as the one-launch path, for every output type and the skip path."""
+    from gecco_b200 import synth
+
+    rng = numpy.random.default_rng(4)
+    lens = rng.integers(1, 60, size=700)
+    batches = [synth.config2(len(weights.attrs), contigs=300), synth.make_batch(rng, lens, 4.0, len(weights.attrs), 0.05),
+               synth.make_batch(rng, numpy.array([5000, 3, 1, 900]), 12.0, len(weights.attrs), 0.0)]
+    for batch in batches:
+        for kw in (dict(), dict(pad=False), dict(f32=True), dict(window=7, step=2)):
+            monkeypatch.setenv("GCRF_HOST_SLICES", "1")
+            whole = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, **kw)
+            for slices in ("2", "5", "8"):
+                monkeypatch.setenv("GCRF_HOST_SLICES", slices)
+                cut = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, **kw)
+                assert numpy.array_equal(whole, cut, equal_nan=True), (slices, kw)
+        monkeypatch.setenv("GCRF_HOST_SLICES", "3")
+        p64 = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr.astype(numpy.int64), batch.attr_idx)
+        monkeypatch.setenv("GCRF_HOST_SLICES", "1")
+        assert numpy.array_equal(p64, engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx), equal_nan=True)
+
+
 def test_feature_extraction_on_device(engine, mibig, weights):
     """Accession -> attribute id on device with the reference's set semantics: running the marginals on its output
     (unknown / repeated rows marked -1, row pointers untouched) equals the host packer + oracle on the real fixture."""
