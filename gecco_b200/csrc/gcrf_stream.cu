@@ -109,6 +109,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
     unsigned char *sStat = reinterpret_cast<unsigned char *>(smem + tl.off_stat);
     __shared__ __align__(8) uint64_t sBar, sBarTab;
     __shared__ int64_t sCursor;
+    __shared__ int64_t sNextPb;  // end of the next tile's id range, published by the thread that holds that row pointer
     __shared__ int sShort;
 
     const int tile_begin = blockIdx.x * tiles_per_cta;
@@ -177,10 +178,12 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         }
     }
     int ga = max(0, min(G, Gs0 + T::keep)), gb = max(0, min(G, Gs0 + T::ng));
-    // Range ends and row pointers stay in registers exactly as loaded: widening or rebasing them right after the
-    // load would stall every warp for a full global-memory latency at the top of each tile (ncu: 8 % of all stall
-    // samples); the conversions happen one tile later, where the values are consumed.
-    PtrT pa_raw = __ldg(gene_ptr + ga), pb_raw = __ldg(gene_ptr + gb);
+    // Only the first tile loads its id range [pa, pb) directly.  Later tiles start where the previous one ended
+    // (pa' = pb) and take pb' from the row pointers that are prefetched a tile ahead anyway: the thread holding the
+    // last one publishes it through shared memory after the walk barrier.  A direct warp-uniform load of pb' gets
+    // moved to a uniform register by the compiler right away, which stalled every warp for a full global-memory
+    // latency at the top of each tile (ncu: 7-8 % of all stall samples).
+    int64_t pa = (int64_t)__ldg(gene_ptr + ga), pb = (int64_t)__ldg(gene_ptr + gb);
     PtrT rowreg[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -188,7 +191,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         rowreg[r] = t <= gb - ga ? __ldg(gene_ptr + ga + t) : 0;
     }
     __syncthreads();  // mbarrier initialised, delta table staged, cursor and halo written
-    if (tid == 0) stage_ids<kCap>(sIdx, csr.attr_idx, (int64_t)pa_raw, (int64_t)pb_raw, &sBar);
+    if (tid == 0) stage_ids<kCap>(sIdx, csr.attr_idx, pa, pb, &sBar);
     uint32_t bar_parity = 0;
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -198,7 +201,10 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         const int jn0 = ga - Gs;    // local index of the first new gene (= keep, except at the batch edges)
         const int jlo = max(0, -Gs);           // first existing local gene
         const int jhi = min(T::ng, G - Gs);    // one past the last existing local gene
-        const int64_t pa = (int64_t)pa_raw, pb = (int64_t)pb_raw;
+        if (tile > tile_begin) {
+            pa = pb;
+            pb = sNextPb;  // written before the previous tile's unary barrier
+        }
         const int64_t a0 = pa & ~(int64_t)3;
         const int64_t total64 = pb - a0;       // staged-range length (ids) from the aligned start
         const bool staged = total64 <= kCap;   // CTA-uniform: the usual case
@@ -223,13 +229,10 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         int cp_raw = 0;  // rebased to local gene coordinates only after the walk
         if (cp_ok) cp_raw = __ldg(csr.contig_ptr + c_first + tid);
         int nga = 0, ngb = 0;
-        PtrT npa = 0, npb = 0;
         PtrT nrow[2] = {0, 0};
         if (has_next && !GCRF_SKIP(128)) {
             nga = max(0, min(G, Gs + T::tile_out + T::keep));
             ngb = max(0, min(G, Gs + T::tile_out + T::ng));
-            npa = __ldg(gene_ptr + nga);
-            npb = __ldg(gene_ptr + ngb);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int t = tid + r * NT;
@@ -260,6 +263,9 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             // A thread whose range is only partly staged walks all of it as well: the words beyond `total` are
             // leftovers of earlier tiles (any bit pattern resolves to a valid table slot) and no row ends there.
             // A separate rolled loop for that one thread was the slowest path into the barrier below.
+            // (Splitting this into three register passes — 13 id loads, 52 look-ups, prefix — so that all shared-memory
+            // requests are in flight at once moved the time into the other phases: 79.9 vs 78.1 us on config 2.  The
+            // shared-memory pipe, not this thread's latency, is what the walk runs against.)
             if (x0 < total) {
 #pragma unroll
                 for (int i = 0; i < kWalk / 4; ++i) {
@@ -279,6 +285,12 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         if (tid == NT - 1) sCp[NT] = INT_MAX;  // sentinel unless the rest of the slice gets loaded below
         // a tile that holds more contigs than one slice entry per thread covers (contigs of 1-2 genes): load the rest
         const bool wide_slice = __syncthreads_or(tid == NT - 1 && cp0 < T::ng) != 0;
+        // the next tile's last row pointer (loaded at the top of this tile, long since arrived) -> shared; read by
+        // thread 0 after the unary barrier below and by everyone at the top of the next tile
+        if (has_next) {
+            const int last = ngb - nga;
+            if (tid == last % NT) sNextPb = (int64_t)(last >= NT ? nrow[1] : nrow[0]);
+        }
         if (wide_slice) {
             for (int k = NT + tid; k <= T::ng + 1; k += NT)
                 sCp[k] = c_first + k <= csr.C ? __ldg(csr.contig_ptr + c_first + k) - GsA : INT_MAX;
@@ -341,7 +353,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         if (kt >= NT - 1) kt = T::ng;
         const bool has_short = sShort != 0;
         // ---- stage the next tile's ids while this tile's dynamic programme runs
-        if (has_next && tid == 0 && !GCRF_SKIP(32)) stage_ids<kCap>(sIdx, csr.attr_idx, (int64_t)npa, (int64_t)npb, &sBar);
+        if (has_next && tid == 0 && !GCRF_SKIP(32)) stage_ids<kCap>(sIdx, csr.attr_idx, pb, sNextPb, &sBar);
         GCRF_MARK(4);
         if (has_short) {
             // per staged gene: status (1 = padded short contig, 2 = skipped short contig) and the padded windows
@@ -480,7 +492,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         GCRF_MARK(7);
 
         // rotate the prefetched ranges
-        ga = nga; gb = ngb; pa_raw = npa; pb_raw = npb;
+        ga = nga; gb = ngb;
         rowreg[0] = nrow[0];
         rowreg[1] = nrow[1];
     }
