@@ -50,13 +50,12 @@ struct StreamTiling {
     static constexpr int keep = ng - tile_out;     // genes carried over from the previous tile
     static_assert(tile_out + 1 <= 2 * NT, "two row pointers per thread must cover a tile's new genes");
     static_assert(keep <= NT, "the ring carry is one gene per thread");
-    int off_idx, off_pool, off_u0, off_u1, off_q, off_sp, off_cp, off_stat, words;
+    int off_idx, off_pool, off_u0, off_q, off_sp, off_cp, off_stat, words;
     __host__ __device__ explicit StreamTiling(int A) {
         int o = round_up4s(A + 1);
         off_idx = o; o += kCap + 4;
         off_pool = o; o += round_up4s((W + 1) * kPitch);
         off_u0 = o; o += round_up4s(ng + 2);
-        off_u1 = o; o += round_up4s(ng + 2);
         off_q = o; o += round_up4s(ng + 2);
         off_sp = o; o += round_up4s(tile_out + 3);
         off_cp = o; o += round_up4s(ng + 4);
@@ -102,7 +101,6 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
     int32_t *sIdx = reinterpret_cast<int32_t *>(smem + tl.off_idx);
     float *sPool = smem + tl.off_pool;
     float *sU0 = smem + tl.off_u0;  // sU0[j] = u of local gene j
-    float *sU1 = smem + tl.off_u1;  // sU1[j] = u of local gene j + 1 (so odd pairs are 8-byte aligned too)
     float *sQ = smem + tl.off_q;    // odds of genes of padded short contigs
     int *sP = reinterpret_cast<int *>(smem + tl.off_sp);   // staged-range coordinates of the new genes' rows
     int *sCp = reinterpret_cast<int *>(smem + tl.off_cp);  // contig_ptr slice in local gene coordinates
@@ -174,7 +172,6 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                         : direct_unary(gene_ptr, csr.attr_idx, args.model.table, A, g, clampv);
             }
             sU0[T::tile_out + tid] = u;
-            if (tid >= 1) sU1[T::tile_out + tid - 1] = u;
         }
     }
     int ga = max(0, min(G, Gs0 + T::keep)), gb = max(0, min(G, Gs0 + T::ng));
@@ -244,7 +241,6 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         if (tid < T::keep) {
             const float c0 = sU0[tid + T::tile_out];
             sU0[tid] = c0;
-            if (tid >= 1) sU1[tid - 1] = c0;
         }
         GCRF_MARK(0);
 
@@ -325,7 +321,6 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 }
                 const int j = jn0 + t;
                 sU0[j] = u;
-                if (j >= 1) sU1[j - 1] = u;
             }
         }
         if (jlo > 0 || jhi < T::ng) {
@@ -333,7 +328,6 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             for (int j = tid; j < T::ng + 1; j += NT) {
                 if (j < jlo || j >= jhi) {
                     sU0[j] = 1.0f;
-                    if (j >= 1) sU1[j - 1] = 1.0f;
                 }
             }
         }
@@ -348,7 +342,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         }
         // contig starts are a prefix of the slice: counting them among the first NT entries is exact unless all
         // of those are starts, in which case the searches below stay unbounded.  The barrier also publishes
-        // sU0/sU1 and retires the last readers of sIdx.
+        // sU0 and retires the last readers of sIdx.
         int kt = __syncthreads_count(tid >= 1 && sCp[tid] < T::ng);
         if (kt >= NT - 1) kt = T::ng;
         const bool has_short = sShort != 0;
@@ -402,10 +396,18 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             }
             if (GCRF_SKIP(2)) va = vb = 0.f;
             if (va + vb > 0.f) {
-                auto upair = [&](int k) -> float2 {
-                    return (k & 1) ? *reinterpret_cast<const float2 *>(&sU1[b0 + k - 1])
-                                   : *reinterpret_cast<const float2 *>(&sU0[b0 + k]);
-                };
+                // The 21 unary odds the two windows touch, loaded ONCE (ten 8-byte loads and one 4-byte load) and kept
+                // in registers for both chains: per-step operand loads were 320 of a tile's ~1,740 shared-memory
+                // wavefronts.  Odd steps pair registers of two different loads — two scalar multiplies, no load.
+                float uu[W + 1];
+#pragma unroll
+                for (int i = 0; i < W / 2; ++i) {
+                    const float2 p = *reinterpret_cast<const float2 *>(&sU0[b0 + 2 * i]);
+                    uu[2 * i] = p.x;
+                    uu[2 * i + 1] = p.y;
+                }
+                uu[W] = sU0[b0 + W];
+                auto upair = [&](int k) -> float2 { return make_float2(uu[k], uu[k + 1]); };
                 const float2 M01 = make_float2(m01 * va, m01 * vb);  // masked: an invalid slot keeps odds == 0
                 const float2 M10 = make_float2(m10, m10), M11 = make_float2(m11, m11), ONE = make_float2(1.f, 1.f);
                 const float2 B01 = make_float2(m01, m01);
