@@ -50,6 +50,7 @@ struct StreamTiling {
     static constexpr int keep = ng - tile_out;     // genes carried over from the previous tile
     static_assert(tile_out + 1 <= 2 * NT, "two row pointers per thread must cover a tile's new genes");
     static_assert(keep <= NT, "the ring carry is one gene per thread");
+    static_assert(keep + 1 <= NT - 32, "the last warp holds no halo row pointer (it runs the contig search instead)");
     int off_idx, off_pool, off_u0, off_q, off_sp, off_cp, off_stat, words;
     __host__ __device__ explicit StreamTiling(int A) {
         int o = round_up4s(A + 1);
@@ -134,10 +135,12 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         tma_load_1d(sTab, args.model.table_fx, tab_bytes, &sBarTab);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads the batch
-    if (tid < 32) {
+    if (tid >= NT - 32) {
+        // the last warp: it holds none of the halo's row pointers, so its three dependent global round trips run
+        // beside the other warps' loads instead of in front of them
         const int64_t g0 = max(0, tile_begin * T::tile_out - T::lo);
-        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0 + csr.gene_base, tid);
-        if (tid == 0) sCursor = c;
+        const int64_t c = warp_find_contig(csr.contig_ptr, csr.C, g0 + csr.gene_base, tid & 31);
+        if (tid == NT - 32) sCursor = c;
     }
     // New genes of a tile = local genes [keep, ng).  The run's first halo [0, keep) is gathered right here into the
     // slots the first tile's ring carry will read: its ids are one contiguous range, every thread resolves a
