@@ -75,6 +75,7 @@ class GcrfError(RuntimeError):
 def library_path() -> pathlib.Path:
     # GCRF_TUNING_LIB=1 selects the build with phase timers / ablation switches (tools/quick_kernel_time.py)
     name = "libgecco_crf_b200_tuning.so" if os.environ.get("GCRF_TUNING_LIB") == "1" else "libgecco_crf_b200.so"
+    name = os.environ.get("GCRF_LIB_NAME", name)  # A/B builds of single kernels (tools/ab_libs.sh)
     return pathlib.Path(__file__).resolve().parent / name
 
 

@@ -13,6 +13,8 @@
 // not the HBM-bound headline path.
 #include "gcrf_kernels.cuh"
 
+#include <cstdlib>
+
 namespace gcrf {
 
 namespace {
@@ -135,6 +137,84 @@ chain_kernel(const CsrDev csr, const double *__restrict__ u, double *__restrict_
     }
 }
 
+// One CTA per contig (grid-stride), for batches of long contigs: 256 lanes share a chain instead of 32, so a
+// 5,000-gene contig is ~20 sequential steps per lane, and 100 such contigs fill the machine (one warp per contig
+// leaves all but 100 warps idle).  Same mathematics as chain_kernel: per-lane segment products, an inclusive scan
+// (shuffles inside a warp, the eight warp totals through shared memory), replay from the exact incoming message.
+__global__ void __launch_bounds__(kThreads)
+chain_block_kernel(const CsrDev csr, const double *__restrict__ u, double *__restrict__ r_buf, void *__restrict__ out,
+                   int out_f32, double m01, double m10, double m11) {
+    constexpr int kWarps = kThreads / 32;
+    __shared__ M2 sTot[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t c = blockIdx.x; c < csr.C; c += gridDim.x) {
+        const int64_t g0 = __ldg(csr.contig_ptr + c), g1 = __ldg(csr.contig_ptr + c + 1);
+        const int64_t n = g1 - g0;
+        if (n <= 0) continue;
+        const int64_t seg = (n + kThreads - 1) / kThreads;
+        int64_t b = g0 + (int64_t)tid * seg, e = b + seg;
+        if (b > g1) b = g1;
+        if (e > g1) e = g1;
+
+        // ---- forward
+        M2 S = identity();
+        for (int64_t g = b; g < e; ++g) {
+            const double ug = u[g];
+            const M2 F = (g == g0) ? M2{0.0, ug, 0.0, 1.0} : M2{ug * m11, ug * m01, m10, 1.0};
+            S = compose(F, S);
+        }
+        M2 P = S;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const M2 Y = shfl_up(P, d);
+            if (lane >= d) P = compose(P, Y);
+        }
+        if (lane == 31) sTot[warp] = P;
+        __syncthreads();
+        M2 X = shfl_up(P, 1);  // earlier lanes of this warp
+        if (lane == 0) X = identity();
+        for (int w = warp - 1; w >= 0; --w) X = compose(X, sTot[w]);  // then the earlier warps, nearest first
+        double r = 0.0;
+        if (tid > 0) r = X.b / X.d;  // first column of X is zero: every chain starts with F_0
+        for (int64_t g = b; g < e; ++g) {
+            const double ug = u[g];
+            r = (g == g0) ? ug : ((m01 + m11 * r) / (1.0 + m10 * r)) * ug;
+            r_buf[g] = r;
+        }
+        __syncthreads();  // sTot is reused below
+
+        // ---- backward
+        M2 R = identity();
+        for (int64_t g = b; g < e; ++g) {
+            if (g == g0) continue;
+            const double ug = u[g];
+            const M2 B = M2{m11 * ug, m10, m01 * ug, 1.0};
+            R = compose(R, B);
+        }
+        M2 Q = R;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const M2 Y = shfl_down(Q, d);
+            if (lane + d < 32) Q = compose(Q, Y);
+        }
+        if (lane == 0) sTot[warp] = Q;
+        __syncthreads();
+        M2 E = shfl_down(Q, 1);  // later lanes of this warp
+        if (lane == 31) E = identity();
+        for (int w = warp + 1; w < kWarps; ++w) E = compose(E, sTot[w]);  // then the later warps, nearest first
+        double s = (E.a + E.b) / (E.c + E.d);  // applied to s_{n-1} = 1
+        for (int64_t g = e - 1; g >= b; --g) {
+            const double q = r_buf[g] * s;
+            const double p = q / (1.0 + q);
+            if (out_f32) static_cast<float *>(out)[g] = (float)p;
+            else static_cast<double *>(out)[g] = p;
+            const double w = u[g] * s;
+            s = (m10 + m11 * w) / (1.0 + m01 * w);
+        }
+        __syncthreads();  // before the next contig overwrites sTot
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_chain(const ChainArgs &args, int num_sms, cudaStream_t stream, int64_t *launches) {
@@ -146,10 +226,20 @@ cudaError_t launch_chain(const ChainArgs &args, int num_sms, cudaStream_t stream
     unary64_kernel<<<(int)blocks_u, kThreads, 0, stream>>>(args.csr, args.table64, args.model.A, u);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    int64_t blocks_c = (args.csr.C * 32 + kThreads - 1) / kThreads;
-    if (blocks_c > (int64_t)num_sms * 8) blocks_c = (int64_t)num_sms * 8;
-    chain_kernel<<<(int)blocks_c, kThreads, 0, stream>>>(args.csr, u, r, args.out, args.out_f32, args.m01, args.m10,
-                                                         args.m11);
+    // a warp per contig, or a CTA per contig when the contigs are long on average (GCRF_CHAIN_TEAM=warp|block overrides)
+    const char *team = getenv("GCRF_CHAIN_TEAM");
+    const bool block_team = team ? team[0] == 'b' : args.csr.G / args.csr.C >= 256;
+    if (block_team) {
+        int64_t blocks_c = args.csr.C;
+        if (blocks_c > (int64_t)num_sms * 8) blocks_c = (int64_t)num_sms * 8;
+        chain_block_kernel<<<(int)blocks_c, kThreads, 0, stream>>>(args.csr, u, r, args.out, args.out_f32, args.m01, args.m10,
+                                                                   args.m11);
+    } else {
+        int64_t blocks_c = (args.csr.C * 32 + kThreads - 1) / kThreads;
+        if (blocks_c > (int64_t)num_sms * 8) blocks_c = (int64_t)num_sms * 8;
+        chain_kernel<<<(int)blocks_c, kThreads, 0, stream>>>(args.csr, u, r, args.out, args.out_f32, args.m01, args.m10,
+                                                             args.m11);
+    }
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

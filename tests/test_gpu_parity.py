@@ -169,6 +169,23 @@ def test_chain_ragged(engine, weights):
         assert_close(got[g0:g1], want, tol=1e-9, what=f"chain contig {c} (n={g1 - g0})")
 
 
+@pytest.mark.parametrize("team", ["warp", "block"])
+def test_chain_teams_agree(engine, weights, monkeypatch, team):
+    """The chain primitive runs one warp or one CTA per contig (chosen by mean contig length): both on both shapes."""
+    from gecco_b200 import synth
+    from oracle import crf_oracle
+
+    monkeypatch.setenv("GCRF_CHAIN_TEAM", team)
+    rng = numpy.random.default_rng(17)
+    lens = numpy.array([1, 2, 31, 32, 33, 255, 256, 257, 1000, 5003, 8, 700])
+    for batch in (synth.ragged_edge_cases(len(weights.attrs)), synth.make_batch(rng, lens, 6.0, len(weights.attrs), 0.05)):
+        got = engine.marginals_chain(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+        for c in range(batch.C):
+            g0, g1 = int(batch.contig_ptr[c]), int(batch.contig_ptr[c + 1])
+            want = crf_oracle.chain_marginals(weights.state_w, weights.trans_w, batch.gene_ptr, batch.attr_idx, g0, g1)[:, 1]
+            assert_close(got[g0:g1], want, tol=1e-9, what=f"{team} team, contig {c} (n={g1 - g0})")
+
+
 def test_window_equal_to_contig_is_the_chain(engine, weights):
     """Size-independent property: one window covering a whole contig == the chain primitive."""
     from gecco_b200 import synth
