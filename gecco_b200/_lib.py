@@ -60,6 +60,7 @@ EXPORTED_SYMBOLS = (
     "gcrf_table_gene_probabilities",
     "gcrf_table_write_genes",
     "gcrf_table_write_features",
+    "gcrf_table_write_clusters",
 )
 
 _STATUS = {0: "GCRF_OK", -1: "GCRF_EINVAL", -2: "GCRF_ENODEVICE", -3: "GCRF_ECUDA", -4: "GCRF_ENOMEM",
@@ -164,6 +165,8 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_table_write_genes.argtypes = [vp, vp, cp]
     lib.gcrf_table_write_features.restype = ctypes.c_int
     lib.gcrf_table_write_features.argtypes = [vp, vp, cp]
+    lib.gcrf_table_write_clusters.restype = ctypes.c_int
+    lib.gcrf_table_write_clusters.argtypes = [vp, vp, vp, vp, vp, vp, i64, cp]
     _lib = lib
     return lib
 

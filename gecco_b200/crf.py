@@ -262,8 +262,44 @@ class ClusterCRF(object):
         model_io.save_tsv_model(weights, model_path)
 
 
+def _predict_tables_main(argv: List[str]) -> int:
+    """``python -m gecco_b200 predict-tables``: the table-to-table part of ``gecco predict`` without GECCO's Python
+    object model (same option names and defaults as ``gecco/cli/commands/_parser.py:171-337``)."""
+    import argparse
+
+    from .tables import predict_tables
+
+    ap = argparse.ArgumentParser(prog="python -m gecco_b200 predict-tables",
+                                 description="genes + features tables -> CRF marginals on the B200 -> genes / features / clusters tables")
+    ap.add_argument("--genes", required=True, help="a genes table (*.genes.tsv, optionally compressed)")
+    ap.add_argument("--features", required=True, nargs="+", help="one or more features tables (*.features.tsv)")
+    ap.add_argument("-o", "--output-dir", default=".", help="where to write {base}.genes.tsv / .features.tsv / .clusters.tsv")
+    ap.add_argument("--base", default=None, help="output file prefix (default: derived from the genes table's name)")
+    ap.add_argument("--model", default=None, help="directory with model.pkl (+ .md5) or model.state.tsv / model.trans.tsv")
+    ap.add_argument("-e", "--e-filter", type=float, default=None, help="drop domains with an i-evalue over this")
+    ap.add_argument("-p", "--p-filter", type=float, default=1e-9, help="drop domains with a p-value over this")
+    ap.add_argument("--no-pad", dest="pad", action="store_false", help="skip contigs shorter than the window instead of padding")
+    ap.add_argument("-m", "--threshold", type=float, default=0.8, help="probability threshold of cluster membership")
+    ap.add_argument("-c", "--cds", type=int, default=3, help="minimum number of annotated genes in a cluster")
+    ap.add_argument("-E", "--edge-distance", type=int, default=0, help="annotated genes this close to a contig edge do not count")
+    ap.add_argument("--no-trim", dest="trim", action="store_false", help="keep un-annotated genes at cluster edges")
+    args = ap.parse_args(argv)
+    tables, prob = predict_tables(args.genes, args.features, args.output_dir, model=args.model, base=args.base,
+                                  e_filter=args.e_filter, p_filter=args.p_filter, pad=args.pad, threshold=args.threshold,
+                                  cds=args.cds, edge_distance=args.edge_distance, trim=args.trim)
+    print(f"{tables.genes} genes on {tables.contigs} contigs, {tables.domains} domains -> {args.output_dir}")
+    tables.close()
+    return 0
+
+
 def main(argv: Optional[List[str]] = None) -> int:
-    """``python -m gecco_b200 ...`` = ``gecco ...`` with the CRF swapped for this one."""
+    """``python -m gecco_b200 ...`` = ``gecco ...`` with the CRF swapped for this one; ``predict-tables`` is this
+    package's own table-to-table command."""
+    import sys
+
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if argv and argv[0] == "predict-tables":
+        return _predict_tables_main(argv[1:])
     try:
         from gecco.cli import main as gecco_main  # type: ignore
     except ImportError as err:  # pragma: no cover - GECCO is not installed in the build image

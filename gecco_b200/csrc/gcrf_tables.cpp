@@ -677,6 +677,72 @@ int gcrf_table_write_genes(const gcrf_table *t, const double *row_prob, const ch
     return write_all(path, out);
 }
 
+int gcrf_table_write_clusters(const gcrf_table *t, const double *row_prob, const int32_t *seg_contig, const int32_t *seg_begin,
+                              const int32_t *seg_end, const int32_t *seg_ordinal, int64_t n_segments, const char *path) {
+    if (!t || !path || n_segments < 0) return tfail(GCRF_EINVAL, "bad arguments");
+    if (n_segments > 0 && (!seg_contig || !seg_begin || !seg_end || !seg_ordinal)) return tfail(GCRF_EINVAL, "NULL segment array");
+    if (row_prob && t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");
+    const size_t G = t->genes.size();
+    std::vector<double> avg(G), mx(G);
+    int64_t cursor = 0;
+    for (size_t g = 0; g < G; ++g) gene_probabilities(t, row_prob, g, &avg[g], &mx[g], &cursor);
+    // ClusterTable.from_clusters on clusters without a predicted type (gecco/model.py:735-762): the data columns in
+    // insertion order, then the schema columns that are missing with their default (`type` = "Unknown").
+    std::string out = "sequence_id\tcluster_id\tstart\tend\taverage_p\tmax_p\tproteins\tdomains\ttype\n";
+    std::vector<sv> names;
+    for (int64_t k = 0; k < n_segments; ++k) {
+        const int64_t c = seg_contig[k], b = seg_begin[k], e = seg_end[k];
+        if (c < 0 || c >= (int64_t)t->contig_ids.size() || b < 0 || e > (int64_t)G || b >= e)
+            return tfail(GCRF_EINVAL, "segment %lld is out of range", (long long)k);
+        const std::string &seq = t->contig_ids[(size_t)c];
+        int64_t start = t->genes[(size_t)b].start, end = t->genes[(size_t)b].end;
+        long double sum = 0;
+        double best = std::numeric_limits<double>::quiet_NaN();
+        int64_t n = 0;
+        for (int64_t g = b; g < e; ++g) {
+            start = std::min(start, t->genes[(size_t)g].start);
+            end = std::max(end, t->genes[(size_t)g].end);
+            if (!std::isnan(avg[(size_t)g])) {  // Cluster.average_probability / maximum_probability (gecco/model.py:442-455)
+                sum += avg[(size_t)g];
+                ++n;
+            }
+            if (!std::isnan(mx[(size_t)g])) best = std::isnan(best) ? mx[(size_t)g] : std::max(best, mx[(size_t)g]);
+        }
+        out += seq;
+        out += '\t';
+        out += seq;
+        out += "_cluster_";
+        append_int(out, seg_ordinal[k]);
+        out += '\t';
+        append_int(out, start);
+        out += '\t';
+        append_int(out, end);
+        out += '\t';
+        if (n) append_repr(out, (double)(sum / n));
+        out += '\t';
+        if (!std::isnan(best)) append_repr(out, best);
+        out += '\t';
+        names.clear();
+        for (int64_t g = b; g < e; ++g) names.push_back(t->genes[(size_t)g].prot);
+        std::sort(names.begin(), names.end());  // ";".join(sorted(gene.protein.id ...))
+        for (size_t i = 0; i < names.size(); ++i) {
+            if (i) out += ';';
+            out.append(names[i]);
+        }
+        out += '\t';
+        names.clear();
+        for (int64_t g = b; g < e; ++g)
+            for (int64_t d = t->dom_ptr[(size_t)g]; d < t->dom_ptr[(size_t)g + 1]; ++d) names.push_back(t->domains[(size_t)d].name);
+        std::sort(names.begin(), names.end());
+        for (size_t i = 0; i < names.size(); ++i) {
+            if (i) out += ';';
+            out.append(names[i]);
+        }
+        out += "\tUnknown\n";
+    }
+    return write_all(path, out);
+}
+
 int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const char *path) {
     if (!t || !path) return tfail(GCRF_EINVAL, "bad arguments");
     if (row_prob && t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");

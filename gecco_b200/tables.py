@@ -222,14 +222,29 @@ class FeatureTables:
         if rc != 0:
             raise _table_error(self._lib, rc)
 
+    def find_segments(self, crf, row_prob: numpy.ndarray, *, threshold: float = 0.8, n_cds: int = 3, edge_distance: int = 0,
+                      trim: bool = True):
+        """``gcrf_segments`` on this table's genes: the raw ``Segments`` arrays (see :meth:`segments`)."""
+        avg, _ = self.gene_probabilities(row_prob)
+        return crf._get_engine().segments(self.contig_ptr, avg, self.annotated, threshold=threshold, n_cds=n_cds,
+                                          edge_distance=edge_distance, trim=trim, reset_per_contig=True)
+
+    def write_clusters(self, path: PathLike, row_prob: numpy.ndarray, seg) -> None:
+        """``ClusterTable.from_clusters(clusters).dump(path)`` for clusters without a predicted type
+        (``gecco/cli/commands/_common.py:79-92``, ``gecco/model.py:735-771``); ``seg`` comes from :meth:`find_segments`."""
+        keep, ptr = self._prob_ptr(row_prob)
+        arrays = [numpy.ascontiguousarray(a, dtype=numpy.int32) for a in (seg.contig, seg.begin, seg.end, seg.ordinal)]
+        rc = self._lib.gcrf_table_write_clusters(self._h, ptr, *[a.ctypes.data for a in arrays], len(arrays[0]),
+                                                 os.fspath(path).encode())
+        if rc != 0:
+            raise _table_error(self._lib, rc)
+
     def segments(self, crf, row_prob: numpy.ndarray, *, threshold: float = 0.8, n_cds: int = 3, edge_distance: int = 0,
                  trim: bool = True):
         """Cluster segments straight from the arrays (``ClusterRefiner.iter_clusters``, ``gecco/refine.py:118-134``;
         defaults of ``gecco predict``: ``--threshold 0.8 --cds 3``).  Returns rows
         ``(contig_id, first_gene_id, last_gene_id, first_gene, last_gene + 1, average_p, max_p)``."""
-        avg, _ = self.gene_probabilities(row_prob)
-        seg = crf._get_engine().segments(self.contig_ptr, avg, self.annotated, threshold=threshold, n_cds=n_cds,
-                                         edge_distance=edge_distance, trim=trim, reset_per_contig=True)
+        seg = self.find_segments(crf, row_prob, threshold=threshold, n_cds=n_cds, edge_distance=edge_distance, trim=trim)
         ids, contigs = self.gene_ids, self.contig_ids
         return [(contigs[int(c)], ids[int(b)], ids[int(e) - 1], int(b), int(e), float(a), float(m))
                 for c, b, e, a, m in zip(seg.contig, seg.begin, seg.end, seg.average_p, seg.max_p)]
@@ -243,9 +258,12 @@ def _table_error(lib, rc: int) -> Exception:
 
 def predict_tables(genes: PathLike, features: Union[PathLike, Iterable[PathLike]], output_dir: PathLike, *, model=None,
                    base: Optional[str] = None, e_filter: Optional[float] = None, p_filter: Optional[float] = 1e-9,
-                   pad: bool = True):
-    """The table-to-table part of ``gecco predict`` (``predict.py:62-100``): load, annotate, sort, filter, CRF
-    marginals on the B200, write ``{base}.genes.tsv`` and ``{base}.features.tsv``.  Returns ``(tables, row_prob)``."""
+                   pad: bool = True, threshold: float = 0.8, cds: int = 3, edge_distance: int = 0, trim: bool = True,
+                   clusters: bool = True):
+    """The table-to-table part of ``gecco predict`` (``predict.py:62-110``): load, annotate, sort, filter, CRF
+    marginals on the B200, write ``{base}.genes.tsv`` and ``{base}.features.tsv``; then threshold + segment
+    extraction on the device and ``{base}.clusters.tsv`` (untyped: the type classifier is not part of this package;
+    like the reference, no clusters table is written when nothing is found).  Returns ``(tables, row_prob)``."""
     from .crf import ClusterCRF
 
     crf = model if isinstance(model, ClusterCRF) else ClusterCRF.trained(model)
@@ -259,4 +277,8 @@ def predict_tables(genes: PathLike, features: Union[PathLike, Iterable[PathLike]
                 base = base[: -len(suffix)]
     tables.write_genes(os.path.join(output_dir, f"{base}.genes.tsv"), prob)
     tables.write_features(os.path.join(output_dir, f"{base}.features.tsv"), prob)
+    if clusters and tables.genes:
+        seg = tables.find_segments(crf, prob, threshold=threshold, n_cds=cds, edge_distance=edge_distance, trim=trim)
+        if len(seg.contig):
+            tables.write_clusters(os.path.join(output_dir, f"{base}.clusters.tsv"), prob, seg)
     return tables, prob

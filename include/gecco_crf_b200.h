@@ -261,6 +261,16 @@ const int32_t *gcrf_table_row_gene(const gcrf_table *table); /* [rows] gene of e
 int gcrf_table_gene_probabilities(const gcrf_table *table, const double *row_prob, double *average_p, double *max_p);
 int gcrf_table_write_genes(const gcrf_table *table, const double *row_prob, const char *path);
 int gcrf_table_write_features(const gcrf_table *table, const double *row_prob, const char *path);
+/*
+ * The clusters table for segments found by gcrf_segments on this table's genes (seg_* as that call returns them;
+ * n_segments entries): ClusterTable.from_clusters(...).dump for clusters without a predicted type
+ * (gecco/model.py:735-771): cluster_id = "<sequence_id>_cluster_<ordinal>" (gecco/refine.py:200), start / end = the
+ * extreme gene coordinates, average_p / max_p over the member genes (gecco/model.py:442-455), proteins and domains
+ * sorted and ";"-joined, type "Unknown".  The type classifier (gecco/types/) is outside this library.
+ */
+int gcrf_table_write_clusters(const gcrf_table *table, const double *row_prob, const int32_t *seg_contig,
+                              const int32_t *seg_begin, const int32_t *seg_end, const int32_t *seg_ordinal,
+                              int64_t n_segments, const char *path);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,37 @@ def test_result_tables_are_byte_identical_to_the_reference(bgc, weights, tmp_pat
         assert numpy.array_equal(avg, prob) and numpy.array_equal(mx, prob)
 
 
+def test_clusters_table_matches_the_reference_row(bgc, weights, tmp_path):
+    """Golden probabilities -> segments (CPU oracle of gcrf_segments here, the device in the gpu test) -> the
+    reference's committed clusters.tsv row, in every column that does not come from the type classifier."""
+    from gecco_b200._lib import Segments
+    from oracle import refine_oracle
+
+    gtext, ftext = bgc_tables(bgc, shuffle=9)
+    with native(gtext, [ftext]) as tables:
+        tables.pack(weights.attrs)
+        prob = numpy.array([g["average_p"] for g in bgc["genes"]])
+        rows = refine_oracle.extract_clusters(tables.contig_ptr, prob, tables.annotated, threshold=0.8, n_cds=3,
+                                              edge_distance=0, trim=True, reset_per_contig=True)
+        assert len(rows) == 1  # tests/test_cli/test_run.py:68-70
+        seg = Segments(len(rows)).truncated(len(rows))
+        for i, (c, b, e, o, avg, mx) in enumerate(rows):
+            seg.contig[i], seg.begin[i], seg.end[i], seg.ordinal[i] = c, b, e, o
+        tables.write_clusters(tmp_path / "clusters.tsv", prob, seg)
+    got = tables_oracle.read_table((tmp_path / "clusters.tsv").read_text())
+    assert len(got) == 1 and got[0]["type"] == "Unknown"
+    assert list(got[0]) == ["sequence_id", "cluster_id", "start", "end", "average_p", "max_p", "proteins", "domains", "type"]
+    want = bgc["clusters"][0]
+    for key in ("sequence_id", "cluster_id", "average_p", "max_p"):
+        assert got[0][key] == want[key], key  # strings: the floats are the reference's digits exactly
+    # v0.11.0 writes sorted(protein ids) and sorted(domain names, repeats included) (gecco/model.py:751-758); the
+    # committed fixture predates that: proteins in gene order, each domain name once
+    assert got[0]["proteins"] == ";".join(sorted(want["proteins"].split(";")))
+    assert got[0]["domains"] == ";".join(sorted(d["domain"] for d in bgc["domains"]))
+    assert sorted(set(got[0]["domains"].split(";"))) == want["domains"].split(";")
+    assert (int(got[0]["start"]), int(got[0]["end"])) == (want["start"], want["end"])
+
+
 @pytest.mark.parametrize("feature_type", ["protein", "domain"])
 @pytest.mark.parametrize("variant", [dict(), dict(shuffle=1, crlf=True), dict(shuffle=2, reorder=True, with_probabilities=True)])
 def test_load_matches_the_row_by_row_restatement(bgc, weights, feature_type, variant, tmp_path):
@@ -237,4 +268,11 @@ def test_predict_tables_on_device(bgc, tmp_path):
     # the reference finds exactly one cluster on this genome (tests/test_cli/test_run.py:68-70)
     clusters = tables.segments(crf, prob, threshold=0.8, n_cds=3)
     assert len(clusters) == 1 and clusters[0][0] == "BGC0001866.1"
+    crows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.clusters.tsv").read_text())
+    want = bgc["clusters"][0]
+    assert len(crows) == 1 and all(crows[0][k] == want[k] for k in ("sequence_id", "cluster_id"))
+    assert crows[0]["proteins"] == ";".join(sorted(want["proteins"].split(";")))
+    assert sorted(set(crows[0]["domains"].split(";"))) == want["domains"].split(";")
+    assert (int(crows[0]["start"]), int(crows[0]["end"])) == (want["start"], want["end"])
+    assert abs(float(crows[0]["average_p"]) - float(want["average_p"])) <= 1e-5
     tables.close()

@@ -135,6 +135,11 @@ def make_bgc_golden(ref_dir: str = "/root/reference") -> None:
         "source": "zellerlab/GECCO v0.11.0 tests/test_cli/data/BGC0001866.{genes,features}.tsv",
         "note": "average_p was produced by real python-crfsuite (reference golden); p-values kept for the default p<1e-9 filter",
         "sha256_lf": {"genes_tsv": sha_lf(data / "BGC0001866.genes.tsv"), "features_tsv": sha_lf(data / "BGC0001866.features.tsv")},
+        "clusters": [
+            {k: (int(c[k]) if k in ("start", "end") else c[k])
+             for k in ("sequence_id", "cluster_id", "start", "end", "average_p", "max_p", "proteins", "domains")}
+            for c in read_tsv(data / "BGC0001866.clusters.tsv")
+        ],
         "genes": [
             {"sequence_id": g["sequence_id"], "protein_id": g["protein_id"], "start": int(g["start"]),
              "end": int(g["end"]), "strand": g["strand"], "average_p": float(g["average_p"]),
