@@ -39,6 +39,8 @@ namespace gcrf {
 
 namespace {
 
+constexpr int kFewPerLane = 16;  // ids per lane of the one-warp walk used for tiles with <= 512 staged ids
+
 template <int W, int NT>
 struct StreamTiling {
     static constexpr int kSlots = 2 * NT;          // window slots per tile
@@ -210,6 +212,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
         const bool staged = total64 <= kCap;   // CTA-uniform: the usual case
         const int total = staged ? (int)total64 : 0;
         const bool has_next = tile + 1 < tile_end;
+        const bool few_ids = staged && total <= 32 * kFewPerLane;  // CTA-uniform
 
         GCRF_MARK(8);
         // Three CTA barriers per tile: after the walk, after the unary odds (a counting barrier) and after the
@@ -265,7 +268,46 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             // (Splitting this into three register passes — 13 id loads, 52 look-ups, prefix — so that all shared-memory
             // requests are in flight at once moved the time into the other phases: 79.9 vs 78.1 us on config 2.  The
             // shared-memory pipe, not this thread's latency, is what the walk runs against.)
-            if (x0 < total) {
+            if (few_ids) {
+                // Real annotation density (1-2 domains per gene): a few hundred ids per tile.  Thirteen dependent
+                // load -> look-up rounds in a handful of threads would be the tile's longest latency chain; instead
+                // the first warp takes 16 ids per lane, all loads and look-ups in flight together, and a shuffle scan
+                // turns the per-lane sums into ONE prefix over the whole staged range (no per-thread segments).
+                if (tid < 32 && tid * kFewPerLane < total) {
+                    int4 *w = reinterpret_cast<int4 *>(sIdx + tid * kFewPerLane);
+                    int4 id[kFewPerLane / 4];
+#pragma unroll
+                    for (int i = 0; i < kFewPerLane / 4; ++i) id[i] = w[i];
+#pragma unroll
+                    for (int i = 0; i < kFewPerLane / 4; ++i) {
+                        id[i].x = lookup(sTab, id[i].x, A);
+                        id[i].y = lookup(sTab, id[i].y, A);
+                        id[i].z = lookup(sTab, id[i].z, A);
+                        id[i].w = lookup(sTab, id[i].w, A);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kFewPerLane / 4; ++i) {
+                        id[i].x += run;
+                        id[i].y += id[i].x;
+                        id[i].z += id[i].y;
+                        id[i].w += id[i].z;
+                        run = id[i].w;
+                    }
+                    int inc = run;  // lanes without ids were filtered above: shuffle only among the active ones
+                    const unsigned active = __activemask();
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int y = __shfl_up_sync(active, inc, d);
+                        if (tid >= d) inc += y;
+                    }
+                    const int base = inc - run;
+#pragma unroll
+                    for (int i = 0; i < kFewPerLane / 4; ++i) {
+                        id[i].x += base; id[i].y += base; id[i].z += base; id[i].w += base;
+                        w[i] = id[i];
+                    }
+                }
+            } else if (x0 < total) {
 #pragma unroll
                 for (int i = 0; i < kWalk / 4; ++i) {
                     int4 id = v[i];
@@ -307,7 +349,9 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 if (staged && e - s < fx_nsafe) {
                     // prefix difference, plus the totals of the threads the row runs through
                     int v = 0;
-                    if (e > s) {
+                    if (few_ids) {
+                        if (e > s) v = sIdx[e - 1] - (s > 0 ? sIdx[s - 1] : 0);  // one prefix over the whole range
+                    } else if (e > s) {
                         const int q0 = walk_thread(s), q1 = walk_thread(e - 1);
                         v = sIdx[e - 1];
                         if (s != q0 * kWalk) v -= sIdx[s - 1];
