@@ -369,21 +369,15 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
     const char *force = getenv("GCRF_FORCE_GENERIC");
     const bool want_generic = force && force[0] == '1';
     const bool fast = gcrf::stream_supported(args) && !want_generic;
-    // GCRF_PATH=ws|fused picks between the two W=20 kernels (A/B runs; same results)
-    const char *path = getenv("GCRF_PATH");
-    const bool ws = fast && gcrf::ws_supported(args) && (path ? !strcmp(path, "ws") : false);
-    cudaError_t err = ws     ? gcrf::plan_ws(args, m->num_sms, &plan)
-                      : fast ? gcrf::plan_stream(args, m->num_sms, &plan)
-                             : gcrf::plan_windowed(args, m->num_sms, &plan);
+    cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", args.window, m->A);
     }
     if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
     if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
-    err = ws     ? gcrf::launch_ws(args, plan, m->stream, &m->launches)
-          : fast ? gcrf::launch_stream(args, plan, m->stream, &m->launches)
-                 : gcrf::launch_windowed(args, plan, m->stream, &m->launches);
+    err = fast ? gcrf::launch_stream(args, plan, m->stream, &m->launches)
+               : gcrf::launch_windowed(args, plan, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_windowed");
     if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
     m->timed = m->timing;
@@ -391,21 +385,6 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
         unsigned long long h[16];
         GCRF_CUDA(cudaMemcpyAsync(h, args.prof, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
         GCRF_CUDA(cudaStreamSynchronize(m->stream));
-        if (ws) {
-            // gather role: slots 0-4, window role: slots 8-11; h[15] counts both roles of every pair
-            static const char *gn[5] = {"top", "wait_ids", "walk", "wait_empty", "rowsums"};
-            static const char *wn[4] = {"contig", "wait_full", "dp", "pool_out"};
-            const double pairs = h[15] / 2.0;
-            unsigned long long gt = 0, wt = 0;
-            for (int k = 0; k < 5; ++k) gt += h[k];
-            for (int k = 0; k < 4; ++k) wt += h[8 + k];
-            fprintf(stderr, "[gcrf ws phases] pairs=%.0f grid=%d tiles/pair=%d | gather:", pairs, plan.grid, plan.tiles_per_cta);
-            for (int k = 0; k < 5; ++k) fprintf(stderr, " %s=%.1f%%", gn[k], gt ? 100.0 * h[k] / gt : 0.0);
-            fprintf(stderr, " cycles/pair=%.0f | window:", pairs ? gt / pairs : 0.0);
-            for (int k = 0; k < 4; ++k) fprintf(stderr, " %s=%.1f%%", wn[k], wt ? 100.0 * h[8 + k] / wt : 0.0);
-            fprintf(stderr, " cycles/pair=%.0f\n", pairs ? wt / pairs : 0.0);
-            return GCRF_OK;
-        }
         static const char *names[10] = {"setup", "wait_ids", "walk", "unary", "contig", "short", "dp", "pool", "loop", "-"};
         unsigned long long tot = 0;
         for (int k = 0; k < 9; ++k) tot += h[k];

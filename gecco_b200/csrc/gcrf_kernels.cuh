@@ -70,11 +70,6 @@ bool stream_supported(const WindowedArgs &args);
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan);
 cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches);
 
-// The same path with warp-specialised roles (gather warpgroup | window warpgroup) in one persistent CTA (gcrf_ws.cu).
-bool ws_supported(const WindowedArgs &args);
-cudaError_t plan_ws(const WindowedArgs &args, int num_sms, WindowedPlan *plan);
-cudaError_t launch_ws(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream, int64_t *launches);
-
 struct ChainArgs {
     ModelDev model;
     CsrDev csr;

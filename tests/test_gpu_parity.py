@@ -13,13 +13,11 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(autouse=True, params=["fused", "ws", "generic"])
+@pytest.fixture(autouse=True, params=["fused", "generic"])
 def device_path(request, monkeypatch):
-    """Every parity test runs through the device paths for W=20: the fused streaming kernel, its warp-specialised
-    twin and the generic kernel that serves every other window size (the library reads GCRF_PATH /
-    GCRF_FORCE_GENERIC at call time)."""
+    """Every parity test runs through both device paths for W=20: the fused streaming kernel (default) and the
+    generic kernel that serves every other window size (the library reads GCRF_FORCE_GENERIC at call time)."""
     monkeypatch.setenv("GCRF_FORCE_GENERIC", "1" if request.param == "generic" else "0")
-    monkeypatch.setenv("GCRF_PATH", request.param)
     return request.param
 
 

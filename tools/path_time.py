@@ -3,7 +3,7 @@
     python tools/path_time.py [config2|sparse|config4|config5 ...]
 
 Per shape: per-call time (events inside the ABI around the kernel) and back-to-back time (20 calls between two
-stream events), for the fused streaming kernel, its warp-specialised twin and the generic kernel.
+stream events), for the fused streaming kernel and the generic kernel.
 """
 import os
 import pathlib
@@ -32,7 +32,6 @@ eng.set_stream(stream.cuda_stream)
 
 def measure(b, path):
     os.environ["GCRF_FORCE_GENERIC"] = "1" if path == "generic" else "0"
-    os.environ["GCRF_PATH"] = path
     cp = torch.from_numpy(b.contig_ptr).to(dev); gp = torch.from_numpy(b.gene_ptr).to(dev); ai = torch.from_numpy(b.attr_idx).to(dev)
     out = torch.full((b.G,), -1.0, dtype=torch.float64, device=dev)
 
@@ -61,7 +60,7 @@ for name in (sys.argv[1:] or ["config2"]):
     b = shapes[name]()
     print(f"== {name}: C={b.C} G={b.G} nnz={b.nnz}", flush=True)
     ref = None
-    for label in ("fused", "ws", "generic"):
+    for label in ("fused", "generic"):
         lo, med, b2b, got = measure(b, label)
         if ref is None:
             ref = got
