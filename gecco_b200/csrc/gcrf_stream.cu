@@ -446,23 +446,24 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 // The 21 unary odds the two windows touch, loaded ONCE (ten 8-byte loads and one 4-byte load) and kept
                 // in registers for both chains: per-step operand loads were 320 of a tile's ~1,740 shared-memory
                 // wavefronts.  Odd steps pair registers of two different loads — two scalar multiplies, no load.
-                float uu[W + 1];
+                float uu[W + 2];
 #pragma unroll
-                for (int i = 0; i < W / 2; ++i) {
+                for (int i = 0; i < (W + 1) / 2; ++i) {
                     const float2 p = *reinterpret_cast<const float2 *>(&sU0[b0 + 2 * i]);
                     uu[2 * i] = p.x;
                     uu[2 * i + 1] = p.y;
                 }
-                uu[W] = sU0[b0 + W];
+                if ((W & 1) == 0) uu[W] = sU0[b0 + W];
                 auto upair = [&](int k) -> float2 { return make_float2(uu[k], uu[k + 1]); };
                 const float2 M01 = make_float2(m01 * va, m01 * vb);  // masked: an invalid slot keeps odds == 0
                 const float2 M10 = make_float2(m10, m10), M11 = make_float2(m11, m11), ONE = make_float2(1.f, 1.f);
                 const float2 B01 = make_float2(m01, m01);
                 // The forward chain R_k (odds of alpha) and the backward chain S_k (odds of beta) are independent:
                 // run them side by side, first halves stored, second halves combined with the stored other half.
-                constexpr int H = W / 2;  // positions [0, H) meet positions [H, W)
-                static_assert(W % 2 == 0 && W >= 4, "packed DP assumes an even window");
-                float2 ra[H], sb[H];      // ra[k] = R_k for k < H;  sb[i] = S_{H+i}
+                constexpr int H = W / 2;         // the chains meet between positions H-1 and H (even W) or at H (odd W)
+                constexpr int ODD = W & 1;
+                static_assert(W >= 2, "packed DP needs two positions");
+                float2 ra[H], sb[H];      // ra[k] = R_k for k < H;  sb[i] = S_{H+ODD+i}
                 auto fwd = [&](float2 R, int k) -> float2 {
                     const float2 num = __ffma2_rn(R, M11, M01);
                     const float2 den = __ffma2_rn(R, M10, ONE);
@@ -487,20 +488,27 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                     S = bwd(S, W - 1 - k);
                     sb[H - 1 - k] = S;
                 }
-                // second halves: Q_k = R_k S_k upward from H, downward from H-1; m[j] = max(q_a[j], q_b[j-1])
-                R = fwd(R, H);
-                S = bwd(S, H - 1);
-                float2 Qup = __fmul2_rn(R, sb[0]);       // Q_H
-                float2 Qdn = __fmul2_rn(ra[H - 1], S);   // Q_{H-1}
-                sPool[H * kPitch + tid] = fmaxf(Qup.x, Qdn.y);
+                // second halves: Q_k = R_k S_k upward and downward from the meeting point; m[j] = max(q_a[j], q_b[j-1])
+                float2 Qup, Qdn;
+                if (ODD) {
+                    R = fwd(R, H);
+                    S = bwd(S, H);
+                    Qup = Qdn = __fmul2_rn(R, S);  // Q_H, the middle position: both directions start from it
+                } else {
+                    R = fwd(R, H);
+                    S = bwd(S, H - 1);
+                    Qup = __fmul2_rn(R, sb[0]);       // Q_H
+                    Qdn = __fmul2_rn(ra[H - 1], S);   // Q_{H-1}
+                    sPool[H * kPitch + tid] = fmaxf(Qup.x, Qdn.y);
+                }
 #pragma unroll
-                for (int i = 1; i < H; ++i) {
-                    R = fwd(R, H + i);
-                    const float2 Qu = __fmul2_rn(R, sb[i]);           // Q_{H+i}
-                    sPool[(H + i) * kPitch + tid] = fmaxf(Qu.x, Qup.y);
+                for (int i = 1 - ODD; i < H; ++i) {
+                    R = fwd(R, H + ODD + i);
+                    const float2 Qu = __fmul2_rn(R, sb[i]);                 // Q_{H+ODD+i}
+                    sPool[(H + ODD + i) * kPitch + tid] = fmaxf(Qu.x, Qup.y);
                     Qup = Qu;
                     S = bwd(S, H - 1 - i);
-                    const float2 Qd = __fmul2_rn(ra[H - 1 - i], S);   // Q_{H-1-i}
+                    const float2 Qd = __fmul2_rn(ra[H - 1 - i], S);         // Q_{H-1-i}
                     sPool[(H - i) * kPitch + tid] = fmaxf(Qdn.x, Qd.y);
                     Qdn = Qd;
                 }
@@ -564,36 +572,64 @@ cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, NT, tl.bytes());
 }
 
+
+// Window sizes with a compiled streaming kernel: GECCO's shipped model (20), the default of `gecco train` (5,
+// gecco/cli/commands/_parser.py:364-372) and one in between; every other size runs the generic kernel.
+#define GCRF_STREAM_WINDOWS(X) X(5) X(10) X(20)
+
+template <int W>
+cudaError_t configure_window(const WindowedArgs &args, int *per_sm, size_t *bytes, int *tile_out) {
+    *tile_out = StreamTiling<W, 128>::tile_out;
+    return args.csr.gene_ptr64 ? configure_stream<W, 128, 4, int64_t>(args.model.A, per_sm, bytes)
+                               : configure_stream<W, 128, 4, int32_t>(args.model.A, per_sm, bytes);
+}
+
+template <int W>
+cudaError_t launch_window(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int num_tiles, int tiles_per_cta) {
+    return args.csr.gene_ptr64
+               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, 128, 4, int64_t>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
+               : cudaLaunchKernelEx(&cfg, stream_kernel<W, 128, 4, int32_t>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
+}
+
 }  // namespace
 
 bool stream_supported(const WindowedArgs &args) {
-    if (args.window != 20) return false;
-    const StreamTiling<20, 128> tl(args.model.A);
+    bool known = false;
+#define X(W) known = known || args.window == W;
+    GCRF_STREAM_WINDOWS(X)
+#undef X
+    if (!known) return false;
+    const StreamTiling<20, 128> tl(args.model.A);  // the largest of the compiled windows
     if (tl.bytes() > 100 * 1024) return false;
     // tile arithmetic is 32-bit: G + one tile of slack must fit
     return args.csr.G < 0x7fff0000;
 }
 
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
-    // the kernel attribute / occupancy query depend on (device, A, pointer width) only: cache them per thread
-    struct Cached { int device = -1, A = -1, p64 = -1, per_sm = 0; size_t bytes = 0; };
+    // the kernel attribute / occupancy query depend on (device, A, pointer width, window) only: cache them per thread
+    struct Cached { int device = -1, A = -1, p64 = -1, window = -1, per_sm = 0, tile_out = 0; size_t bytes = 0; };
     static thread_local Cached cache;
     int device = 0;
     cudaGetDevice(&device);
     const bool p64 = args.csr.gene_ptr64 != nullptr;
-    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64) {
-        int q = 0;
+    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64 || cache.window != args.window) {
+        int q = 0, tile_out = 0;
         size_t b = 0;
-        cudaError_t err = p64 ? configure_stream<20, 128, 4, int64_t>(args.model.A, &q, &b)
-                              : configure_stream<20, 128, 4, int32_t>(args.model.A, &q, &b);
+        cudaError_t err = cudaErrorInvalidValue;
+        switch (args.window) {
+#define X(W) case W: err = configure_window<W>(args, &q, &b, &tile_out); break;
+            GCRF_STREAM_WINDOWS(X)
+#undef X
+        }
         if (err != cudaSuccess) return err;
-        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.per_sm = q; cache.bytes = b;
+        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.window = args.window;
+        cache.per_sm = q; cache.bytes = b; cache.tile_out = tile_out;
     }
     const int per_sm = cache.per_sm;
     const size_t bytes = cache.bytes;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     plan->threads = 128;
-    plan->tile_out = StreamTiling<20, 128>::tile_out;
+    plan->tile_out = cache.tile_out;
     plan->chunk = 128 * kWalk;
     plan->smem_bytes = bytes;
     plan->num_tiles = (args.csr.G + plan->tile_out - 1) / plan->tile_out;
@@ -620,11 +656,12 @@ cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cu
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t err;
-    if (args.csr.gene_ptr64)
-        err = cudaLaunchKernelEx(&cfg, stream_kernel<20, 128, 4, int64_t>, args, args.csr.gene_ptr64, nt_, tpc);
-    else
-        err = cudaLaunchKernelEx(&cfg, stream_kernel<20, 128, 4, int32_t>, args, args.csr.gene_ptr32, nt_, tpc);
+    cudaError_t err = cudaErrorInvalidValue;
+    switch (args.window) {
+#define X(W) case W: err = launch_window<W>(cfg, args, nt_, tpc); break;
+        GCRF_STREAM_WINDOWS(X)
+#undef X
+    }
     if (launches) *launches += 1;
     return err;
 }

@@ -68,7 +68,8 @@ def test_mibig_real_features(engine, mibig, weights):
 
 
 @pytest.mark.parametrize("window,step,pad", [(20, 1, True), (20, 1, False), (20, 3, True), (5, 1, True), (5, 2, False),
-                                             (7, 7, True), (1, 1, True), (33, 4, True), (64, 1, True), (128, 5, True)])
+                                             (10, 1, True), (10, 3, False), (7, 7, True), (1, 1, True), (33, 4, True),
+                                             (64, 1, True), (128, 5, True)])
 def test_ragged_edge_cases(engine, weights, window, step, pad):
     from gecco_b200 import synth
 
@@ -76,6 +77,22 @@ def test_ragged_edge_cases(engine, weights, window, step, pad):
     want = oracle(weights, batch, window, step, pad)
     got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window, step=step, pad=pad)
     assert_close(got, want, what=f"W={window} step={step} pad={pad}")
+
+
+@pytest.mark.parametrize("window", [5, 10])
+def test_other_streaming_windows_on_dense_and_short_contigs(engine, weights, window):
+    """The streaming kernel is also compiled for W = 5 (`gecco train`'s default) and W = 10: odd and even meeting
+    points of the two DP chains, on the dense shape and on the metagenome shape (padding and skipping)."""
+    from gecco_b200 import synth
+
+    batch = synth.config2(len(weights.attrs), contigs=200)
+    assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window),
+                 oracle(weights, batch, window=window), what=f"config2 W={window}")
+    batch = synth.config4(len(weights.attrs), contigs=3000, mean_domains=4.0)
+    for pad in (True, False):
+        for step in (1, 2):
+            got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window, step=step, pad=pad)
+            assert_close(got, oracle(weights, batch, window=window, step=step, pad=pad), what=f"config4 W={window} step={step} pad={pad}")
 
 
 def test_f32_output_and_int64_pointers(engine, weights):
