@@ -95,6 +95,33 @@ def test_other_streaming_windows_on_dense_and_short_contigs(engine, weights, win
             assert_close(got, oracle(weights, batch, window=window, step=step, pad=pad), what=f"config4 W={window} step={step} pad={pad}")
 
 
+def test_random_shapes_fuzz(engine, weights):
+    """Seeded fuzz over everything that shapes the control flow: window, step, padding, contig lengths from one gene
+    to several tiles, domain density from none to rows longer than the fixed-point guard, unknown ids."""
+    from gecco_b200 import synth
+
+    rng = numpy.random.default_rng(2024)
+    for case in range(36):
+        window = int(rng.choice([5, 10, 20, 20, 20, rng.integers(1, 41)]))
+        step = int(rng.integers(1, window + 1)) if rng.random() < 0.4 else 1
+        pad = bool(rng.random() < 0.7)
+        kind = case % 4
+        if kind == 0:
+            lens = rng.integers(1, 2 * window + 2, size=int(rng.integers(1, 400)))
+        elif kind == 1:
+            lens = numpy.maximum(1, rng.poisson(rng.choice([30, 250, 900]), size=int(rng.integers(1, 40))))
+        elif kind == 2:
+            lens = numpy.concatenate([rng.integers(1, 4, size=300), [int(rng.integers(500, 3000))], rng.integers(1, 60, size=50)])
+            rng.shuffle(lens)
+        else:
+            lens = numpy.array([int(rng.integers(1, 5000))])
+        density = float(rng.choice([0.0, 0.3, 1.4, 8.0, 25.0, 45.0]))
+        batch = synth.make_batch(rng, lens, density, len(weights.attrs), float(rng.choice([0.0, 0.05, 0.5])))
+        got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window, step=step, pad=pad)
+        want = oracle(weights, batch, window, step, pad)
+        assert_close(got, want, what=f"case {case}: W={window} step={step} pad={pad} C={batch.C} G={batch.G} d={density}")
+
+
 def test_f32_output_and_int64_pointers(engine, weights):
     from gecco_b200 import synth
 

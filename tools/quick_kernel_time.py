@@ -13,6 +13,7 @@ from gecco_b200._lib import CRFEngine
 
 w = model_io.load_tsv_model(model_io.bundled_model_dir())
 mean_domains = float(os.environ.get("QK_DOMAINS", "25"))
+window = int(os.environ.get("QK_WINDOW", "20"))
 b = synth.config2(len(w.attrs), mean_domains=mean_domains)
 dev = torch.device("cuda:0")
 eng = CRFEngine(w, 0)
@@ -24,7 +25,7 @@ out = torch.empty(b.G, dtype=torch.float64, device=dev)
 def run(n):
     ts = []
     for _ in range(n):
-        eng.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), b.C, b.G, b.nnz, out.data_ptr())
+        eng.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), b.C, b.G, b.nnz, out.data_ptr(), window=window)
         ts.append(eng.last_kernel_ms())
     return ts
 
