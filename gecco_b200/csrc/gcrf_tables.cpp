@@ -24,9 +24,11 @@
 
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -46,11 +48,53 @@ struct GeneRow {
     int64_t start = 0, end = 0;
 };
 
+// What is kept of a feature row once it has been checked against its gene (48 bytes + two views).
 struct DomainRow {
-    sv seq, prot, strand, name, hmm;
-    int64_t start = 0, end = 0, dstart = 0, dend = 0;
-    double i_evalue = 0, pvalue = 0;
-    int32_t gene = -1;  // index into the sorted genes
+    sv name, hmm;
+    int64_t dstart, dend;
+    double i_evalue, pvalue;
+    int32_t gene;  // index into the sorted genes; -1 = dropped by a filter
+};
+
+// protein_id -> row number of the genes table: open addressing over precomputed hashes (one flat array, no node
+// allocations; the std::unordered_map it replaces took a third of a second per million genes)
+struct NameIndex {
+    std::vector<int32_t> slot;
+    std::vector<uint64_t> hash;
+    uint64_t mask = 0;
+    static uint64_t hash_of(sv s) {
+        uint64_t h = 1469598103934665603ull;  // FNV-1a, folded
+        for (unsigned char c : s) h = (h ^ c) * 1099511628211ull;
+        return h ^ (h >> 29);
+    }
+    void reserve(size_t n) {
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        slot.assign(cap, -1);
+        hash.assign(cap, 0);
+        mask = cap - 1;
+    }
+    // returns false if the name is already present
+    template <typename KeyOf>
+    bool insert(sv name, int32_t id, KeyOf &&key_of) {
+        const uint64_t h = hash_of(name);
+        for (uint64_t i = h & mask;; i = (i + 1) & mask) {
+            if (slot[i] < 0) {
+                slot[i] = id;
+                hash[i] = h;
+                return true;
+            }
+            if (hash[i] == h && key_of(slot[i]) == name) return false;
+        }
+    }
+    template <typename KeyOf>
+    int32_t find(sv name, KeyOf &&key_of) const {
+        const uint64_t h = hash_of(name);
+        for (uint64_t i = h & mask;; i = (i + 1) & mask) {
+            if (slot[i] < 0) return -1;
+            if (hash[i] == h && key_of(slot[i]) == name) return slot[i];
+        }
+    }
 };
 
 struct ParseError {
@@ -127,8 +171,9 @@ size_t read_header(sv buf, Header *h) {
     return nl == sv::npos ? buf.size() : nl + 1;
 }
 
-// Calls row(fields, line_number) for every non-empty data line of buf[begin, end), on `threads` threads over
-// newline-aligned chunks; results keep the file order because every chunk fills its own vector.
+// Calls make_row(fields, offset) for every non-empty data line of buf[begin, end) on `threads` threads over
+// newline-aligned chunks.  Two passes: the lines of every chunk are counted first, so that each thread writes its
+// rows straight into its slice of the result (file order, no reallocation, no concatenation).
 template <typename Row, typename Fn>
 void parse_lines(sv buf, size_t begin, int threads, std::vector<Row> *rows, Fn &&make_row) {
     const size_t n = buf.size();
@@ -145,40 +190,53 @@ void parse_lines(sv buf, size_t begin, int threads, std::vector<Row> *rows, Fn &
         cut[t] = nl == sv::npos ? n : nl + 1;
         if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     }
-    std::vector<std::vector<Row>> parts(threads);
+    auto next_line = [&](size_t p, size_t stop, sv *line) -> size_t {  // returns the offset after the line
+        const void *hit = p < stop ? memchr(buf.data() + p, '\n', stop - p) : nullptr;
+        const size_t nl = hit ? (size_t)(static_cast<const char *>(hit) - buf.data()) : stop;
+        *line = strip_cr(buf.substr(p, nl - p));
+        return nl + 1;
+    };
+    std::vector<size_t> count(threads + 1, 0);
     std::vector<std::string> errors(threads);
-    auto work = [&](int t) {
+    auto run = [&](auto &&work) {
+        if (threads == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+            for (auto &th : pool) th.join();
+        }
+    };
+    run([&](int t) {
+        size_t c = 0;
+        sv line;
+        for (size_t p = cut[t]; p < cut[t + 1];) {
+            p = next_line(p, cut[t + 1], &line);
+            c += !line.empty();
+        }
+        count[t + 1] = c;
+    });
+    const size_t base = rows->size();
+    for (int t = 0; t < threads; ++t) count[t + 1] += count[t];
+    rows->resize(base + count[threads]);
+    run([&](int t) {
         std::vector<sv> f;
-        size_t p = cut[t];
-        const size_t stop = cut[t + 1];
+        sv line;
+        Row *out = rows->data() + base + count[t];
         try {
-            while (p < stop) {
-                size_t nl = buf.find('\n', p);
-                if (nl == sv::npos || nl > stop) nl = stop;
-                sv line = strip_cr(buf.substr(p, nl - p));
-                if (!line.empty()) {
-                    split_tabs(line, f);
-                    parts[t].push_back(make_row(f, p));
-                }
-                p = nl + 1;
+            for (size_t p = cut[t]; p < cut[t + 1];) {
+                const size_t at = p;
+                p = next_line(p, cut[t + 1], &line);
+                if (line.empty()) continue;
+                split_tabs(line, f);
+                *out++ = make_row(f, at);
             }
         } catch (const ParseError &e) {
             errors[t] = e.message;
         }
-    };
-    if (threads == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
-        for (auto &th : pool) th.join();
-    }
+    });
     for (const auto &e : errors)
         if (!e.empty()) throw ParseError{e};
-    size_t total = rows->size();
-    for (const auto &p : parts) total += p.size();
-    rows->reserve(total);
-    for (auto &p : parts) rows->insert(rows->end(), p.begin(), p.end());
 }
 
 size_t line_number(sv buf, size_t offset) { return 1 + (size_t)std::count(buf.begin(), buf.begin() + offset, '\n'); }
@@ -258,8 +316,34 @@ void append_int(std::string &out, int64_t v) {
 
 }  // namespace
 
+// A file's bytes; not zero-filled before the read (a std::string would be), never copied.
+struct FileBuffer {
+    char *data = nullptr;
+    size_t size = 0;
+    FileBuffer() = default;
+    FileBuffer(const FileBuffer &) = delete;
+    FileBuffer &operator=(const FileBuffer &) = delete;
+    FileBuffer(FileBuffer &&o) noexcept : data(o.data), size(o.size) { o.data = nullptr; o.size = 0; }
+    FileBuffer &operator=(FileBuffer &&o) noexcept {
+        if (this != &o) {
+            free(data);
+            data = o.data; size = o.size;
+            o.data = nullptr; o.size = 0;
+        }
+        return *this;
+    }
+    ~FileBuffer() { free(data); }
+    bool allocate(size_t n) {
+        free(data);
+        data = static_cast<char *>(malloc(n ? n : 1));
+        size = data ? n : 0;
+        return data != nullptr;
+    }
+    sv view() const { return sv(data, size); }
+};
+
 struct gcrf_table {
-    std::vector<std::string> buffers;  // the files; every string_view below points into one of them
+    std::vector<FileBuffer> buffers;  // the files; every string_view below points into one of them
     // genes, in the reference's order (sequence_id, start, end)
     std::vector<GeneRow> genes;
     std::vector<int32_t> contig_ptr;           // [C+1] into genes
@@ -286,16 +370,19 @@ int tfail(int code, const char *fmt, ...) {
     return code;
 }
 
-int read_file(const char *path, std::string *out) {
+int read_file(const char *path, FileBuffer *out) {
     FILE *f = fopen(path, "rb");
     if (!f) return tfail(GCRF_EINVAL, "cannot open %s", path);
     fseek(f, 0, SEEK_END);
     const long n = ftell(f);
     fseek(f, 0, SEEK_SET);
-    out->resize(n > 0 ? (size_t)n : 0);
-    const size_t got = n > 0 ? fread(out->data(), 1, (size_t)n, f) : 0;
+    if (!out->allocate(n > 0 ? (size_t)n : 0)) {
+        fclose(f);
+        return tfail(GCRF_ENOMEM, "out of host memory reading %s", path);
+    }
+    const size_t got = n > 0 ? fread(out->data, 1, (size_t)n, f) : 0;
     fclose(f);
-    if (got != out->size()) return tfail(GCRF_EINVAL, "short read on %s", path);
+    if (got != out->size) return tfail(GCRF_EINVAL, "short read on %s", path);
     return GCRF_OK;
 }
 
@@ -305,7 +392,19 @@ int column(const Header &h, const char *name, const char *what) {
     return i;
 }
 
+struct PhaseTimer {
+    bool on = getenv("GCRF_TABLE_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gcrf tables] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    }
+};
+
 void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, double e_filter, double p_filter, int threads) {
+    PhaseTimer timer;
     // ---- genes table
     std::vector<GeneRow> rows;
     {
@@ -327,39 +426,100 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             return g;
         });
     }
+    timer.mark("parse genes");
     if (rows.size() > 0x7fffff00u) throw ParseError{"too many genes for int32 row pointers; shard the table"};
     // annotate_genes: gene names are unique (_common.py:217-219)
-    std::unordered_map<sv, int32_t> by_name;
-    by_name.reserve(rows.size() * 2);
+    auto prot_of = [&](int32_t i) { return rows[(size_t)i].prot; };
+    NameIndex by_name;
+    by_name.reserve(rows.size());
     for (size_t i = 0; i < rows.size(); ++i)
-        if (!by_name.emplace(rows[i].prot, (int32_t)i).second) throw ParseError{"Duplicate gene names in input genes"};
-    // sort by (sequence_id, start, end), stable (predict.py:81)
-    std::vector<int32_t> order(rows.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-        const GeneRow &x = rows[a], &y = rows[b];
-        const int c = x.seq.compare(y.seq);
-        if (c != 0) return c < 0;
-        if (x.start != y.start) return x.start < y.start;
-        return x.end < y.end;
-    });
-    std::vector<int32_t> rank(rows.size());
-    t->genes.resize(rows.size());
-    for (size_t k = 0; k < order.size(); ++k) {
-        t->genes[k] = rows[order[k]];
-        rank[order[k]] = (int32_t)k;
-    }
-    const size_t G = t->genes.size();
-    t->contig_ptr.assign(1, 0);
-    for (size_t k = 0; k < G; ++k) {
-        if (k == 0 || t->genes[k].seq != t->genes[k - 1].seq) {
-            if (k) t->contig_ptr.push_back((int32_t)k);
-            t->contig_ids.emplace_back(t->genes[k].seq);
+        if (!by_name.insert(rows[i].prot, (int32_t)i, prot_of)) throw ParseError{"Duplicate gene names in input genes"};
+    timer.mark("index genes by name");
+    // sort by (sequence_id, start, end), stable (predict.py:81).  The ids are compared once per CONTIG, not once per
+    // comparison: distinct ids are ranked, genes are bucketed by rank (stable), and every bucket is sorted by numbers.
+    const size_t G = rows.size();
+    std::vector<int32_t> contig_of(G);
+    std::vector<sv> ids;  // distinct sequence ids in order of first appearance
+    {
+        auto id_of = [&](int32_t c) { return ids[(size_t)c]; };
+        NameIndex seen;
+        seen.reserve(1024);
+        sv last;
+        int32_t last_id = -1;
+        for (size_t i = 0; i < G; ++i) {
+            if (last_id >= 0 && rows[i].seq == last) {  // tables are usually grouped by contig
+                contig_of[i] = last_id;
+                continue;
+            }
+            int32_t c = seen.find(rows[i].seq, id_of);
+            if (c < 0) {
+                c = (int32_t)ids.size();
+                ids.push_back(rows[i].seq);
+                if (2 * ids.size() + 2 > seen.slot.size()) {  // grow and re-insert
+                    seen.reserve(4 * ids.size());
+                    for (size_t k = 0; k < ids.size(); ++k) seen.insert(ids[k], (int32_t)k, id_of);
+                } else {
+                    seen.insert(rows[i].seq, c, id_of);
+                }
+            }
+            contig_of[i] = c;
+            last = rows[i].seq;
+            last_id = c;
         }
     }
-    if (G) t->contig_ptr.push_back((int32_t)G);
+    const size_t C = ids.size();
+    std::vector<int32_t> by_id(C), rank_of(C);
+    std::iota(by_id.begin(), by_id.end(), 0);
+    std::sort(by_id.begin(), by_id.end(), [&](int32_t a, int32_t b) { return ids[(size_t)a] < ids[(size_t)b]; });
+    for (size_t r = 0; r < C; ++r) rank_of[(size_t)by_id[r]] = (int32_t)r;
+    t->contig_ptr.assign(C + 1, 0);
+    for (size_t i = 0; i < G; ++i) ++t->contig_ptr[(size_t)rank_of[(size_t)contig_of[i]] + 1];
+    for (size_t r = 0; r < C; ++r) t->contig_ptr[r + 1] += t->contig_ptr[r];
+    std::vector<int32_t> order(G);
+    {
+        std::vector<int32_t> cursor(t->contig_ptr.begin(), t->contig_ptr.end() - 1);
+        for (size_t i = 0; i < G; ++i) order[(size_t)cursor[(size_t)rank_of[(size_t)contig_of[i]]]++] = (int32_t)i;
+    }
+    {
+        auto sort_contigs = [&](size_t r0, size_t r1) {
+            for (size_t r = r0; r < r1; ++r)
+                std::stable_sort(order.begin() + t->contig_ptr[r], order.begin() + t->contig_ptr[r + 1], [&](int32_t a, int32_t b) {
+                    const GeneRow &x = rows[(size_t)a], &y = rows[(size_t)b];
+                    if (x.start != y.start) return x.start < y.start;
+                    return x.end < y.end;
+                });
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, G / 50000));
+        if (nt <= 1) {
+            sort_contigs(0, C);
+        } else {  // contiguous contig ranges of about equal gene counts
+            std::vector<std::thread> pool;
+            size_t r0 = 0;
+            for (int k = 0; k < nt; ++k) {
+                const int64_t want = (int64_t)G * (k + 1) / nt;
+                size_t r1 = r0;
+                while (r1 < C && t->contig_ptr[r1 + 1] <= want) ++r1;
+                if (k == nt - 1) r1 = C;
+                pool.emplace_back(sort_contigs, r0, r1);
+                r0 = r1;
+            }
+            for (auto &th : pool) th.join();
+        }
+    }
+    std::vector<int32_t> rank(G);
+    t->genes.resize(G);
+    for (size_t k = 0; k < G; ++k) {
+        t->genes[k] = rows[(size_t)order[k]];
+        rank[(size_t)order[k]] = (int32_t)k;
+    }
+    t->contig_ids.reserve(C);
+    for (size_t r = 0; r < C; ++r) t->contig_ids.emplace_back(ids[(size_t)by_id[r]]);
+    if (G == 0) t->contig_ptr.assign(1, 0);
+    timer.mark("sort genes, contigs");
 
-    // ---- feature tables, concatenated in the order given (load_features, _common.py:193-208)
+    // ---- feature tables, concatenated in the order given (load_features, _common.py:193-208).  Every row is
+    //      attached to its gene (annotate_genes, _common.py:226-249) and filtered (filter_domains, :419-448: NaN < x is
+    //      false, so NaN rows go as well) by the thread that parses it; what is stored is the compact DomainRow.
     std::vector<DomainRow> drows;
     for (sv fb : feature_bufs) {
         Header h;
@@ -376,73 +536,135 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             auto where = [&] { return " on line " + std::to_string(line_number(fb, off)) + " of a features table"; };
             if (f.size() < need) throw ParseError{"too few fields" + where()};
             DomainRow d;
-            d.seq = unquote(f[c_seq]);
-            d.prot = unquote(f[c_prot]);
-            d.strand = unquote(f[c_strand]);
             d.name = unquote(f[c_dom]);
             d.hmm = unquote(f[c_hmm]);
-            if (!parse_int(f[c_start], &d.start) || !parse_int(f[c_end], &d.end) || !parse_int(f[c_ds], &d.dstart) ||
+            int64_t start, end;
+            if (!parse_int(f[c_start], &start) || !parse_int(f[c_end], &end) || !parse_int(f[c_ds], &d.dstart) ||
                 !parse_int(f[c_de], &d.dend))
                 throw ParseError{"bad integer" + where()};
             if (!parse_float(f[c_ev], &d.i_evalue) || !parse_float(f[c_pv], &d.pvalue)) throw ParseError{"bad number" + where()};
+            const sv prot = unquote(f[c_prot]), seq = unquote(f[c_seq]), strand = unquote(f[c_strand]);
+            const int32_t row = by_name.find(prot, prot_of);
+            if (row < 0) throw ParseError{"Unknown protein " + std::string(prot) + " in features table"};
+            const GeneRow &g = rows[(size_t)row];
+            if (g.seq != seq || g.end - g.start != end - start || g.start != start || g.end != end || g.strand != strand) {
+                const std::string id(prot);
+                if (g.seq != seq) throw ParseError{"Mismatched source sequence for '" + id + "': '" + std::string(g.seq) + "' != '" + std::string(seq) + "'"};
+                if (g.end - g.start != end - start)
+                    throw ParseError{"Mismatched gene length for '" + id + "': " + std::to_string(g.end - g.start) + " != " + std::to_string(end - start)};
+                if (g.start != start) throw ParseError{"Mismatched gene start for '" + id + "': " + std::to_string(g.start) + " != " + std::to_string(start)};
+                if (g.end != end) throw ParseError{"Mismatched gene end for '" + id + "': " + std::to_string(g.end) + " != " + std::to_string(end)};
+                throw ParseError{"Mismatched gene strand for '" + id + "': '" + std::string(g.strand) + "' != '" + std::string(strand) + "'"};
+            }
+            const bool keep = (std::isnan(e_filter) || d.i_evalue < e_filter) && (std::isnan(p_filter) || d.pvalue < p_filter);
+            d.gene = keep ? rank[(size_t)row] : -1;
             return d;
         });
     }
-    // annotate_genes: attach by protein_id, check the row against its gene (_common.py:226-249)
-    std::vector<int64_t> count(G + 1, 0);
-    for (DomainRow &d : drows) {
-        auto it = by_name.find(d.prot);
-        if (it == by_name.end()) throw ParseError{"Unknown protein " + std::string(d.prot) + " in features table"};
-        const GeneRow &g = rows[it->second];
-        const std::string id(d.prot);
-        if (g.seq != d.seq) throw ParseError{"Mismatched source sequence for '" + id + "': '" + std::string(g.seq) + "' != '" + std::string(d.seq) + "'"};
-        if (g.end - g.start != d.end - d.start)
-            throw ParseError{"Mismatched gene length for '" + id + "': " + std::to_string(g.end - g.start) + " != " + std::to_string(d.end - d.start)};
-        if (g.start != d.start) throw ParseError{"Mismatched gene start for '" + id + "': " + std::to_string(g.start) + " != " + std::to_string(d.start)};
-        if (g.end != d.end) throw ParseError{"Mismatched gene end for '" + id + "': " + std::to_string(g.end) + " != " + std::to_string(d.end)};
-        if (g.strand != d.strand) throw ParseError{"Mismatched gene strand for '" + id + "': '" + std::string(g.strand) + "' != '" + std::string(d.strand) + "'"};
-        d.gene = rank[it->second];
-        // filter_domains (_common.py:419-448): NaN < x is false, so NaN rows go as well
-        const bool keep = (std::isnan(e_filter) || d.i_evalue < e_filter) && (std::isnan(p_filter) || d.pvalue < p_filter);
-        if (!keep) d.gene = -1;
-        else ++count[(size_t)d.gene + 1];
-    }
+    timer.mark("parse + annotate features");
     // group by gene keeping the row order (counting sort), then order every gene's rows by (start, end), stable
     t->dom_ptr.assign(G + 1, 0);
-    for (size_t g = 0; g < G; ++g) t->dom_ptr[g + 1] = t->dom_ptr[g] + count[g + 1];
+    for (const DomainRow &d : drows)
+        if (d.gene >= 0) ++t->dom_ptr[(size_t)d.gene + 1];
+    for (size_t g = 0; g < G; ++g) t->dom_ptr[g + 1] += t->dom_ptr[g];
     t->domains.resize((size_t)t->dom_ptr[G]);
     {
-        std::vector<int64_t> cursor(t->dom_ptr.begin(), t->dom_ptr.end() - 1);
-        for (const DomainRow &d : drows)
-            if (d.gene >= 0) t->domains[(size_t)cursor[d.gene]++] = d;
-    }
-    t->annotated.assign(G, 0);
-    for (size_t g = 0; g < G; ++g) {
-        auto b = t->domains.begin() + t->dom_ptr[g], e = t->domains.begin() + t->dom_ptr[g + 1];
-        t->annotated[g] = b != e;
-        if (e - b > 1)
-            std::stable_sort(b, e, [](const DomainRow &x, const DomainRow &y) {
-                if (x.dstart != y.dstart) return x.dstart < y.dstart;
-                return x.dend < y.dend;
+        // Rows that already arrive in gene order (sorted tables: the usual case) only need compaction, which every
+        // thread can do for its own slice; otherwise a sequential, order-preserving scatter.
+        const size_t R = drows.size();
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, R / 200000));
+        std::vector<size_t> kept(nt + 1, 0);
+        std::vector<char> sorted(nt, 1);
+        std::vector<int32_t> first(nt, -1), last(nt, -1);
+        auto scan = [&](int k) {
+            size_t c = 0;
+            int32_t prev = -1;
+            for (size_t i = R * k / nt; i < R * (k + 1) / nt; ++i) {
+                const int32_t g = drows[i].gene;
+                if (g < 0) continue;
+                if (first[k] < 0) first[k] = g;
+                if (g < prev) sorted[k] = 0;
+                prev = g;
+                ++c;
+            }
+            last[k] = prev;
+            kept[k + 1] = c;
+        };
+        auto in_threads = [&](auto &&fn) {
+            if (nt <= 1) {
+                fn(0);
+                return;
+            }
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nt; ++k) pool.emplace_back(fn, k);
+            for (auto &th : pool) th.join();
+        };
+        in_threads(scan);
+        bool in_order = true;
+        int32_t prev = -1;
+        for (int k = 0; k < nt; ++k) {
+            in_order = in_order && sorted[k] && (first[k] < 0 || first[k] >= prev);
+            if (last[k] >= 0) prev = last[k];
+            kept[k + 1] += kept[k];
+        }
+        if (in_order) {
+            in_threads([&](int k) {
+                DomainRow *out = t->domains.data() + kept[k];
+                for (size_t i = R * k / nt; i < R * (k + 1) / nt; ++i)
+                    if (drows[i].gene >= 0) *out++ = drows[i];
             });
+        } else {
+            std::vector<int64_t> cursor(t->dom_ptr.begin(), t->dom_ptr.end() - 1);
+            for (const DomainRow &d : drows)
+                if (d.gene >= 0) t->domains[(size_t)cursor[(size_t)d.gene]++] = d;
+        }
     }
+    drows.clear();
+    drows.shrink_to_fit();
+    t->annotated.assign(G, 0);
+    {
+        auto finish = [&](size_t g0, size_t g1) {
+            for (size_t g = g0; g < g1; ++g) {
+                auto b = t->domains.begin() + t->dom_ptr[g], e = t->domains.begin() + t->dom_ptr[g + 1];
+                t->annotated[g] = b != e;
+                if (e - b > 1)
+                    std::stable_sort(b, e, [](const DomainRow &x, const DomainRow &y) {
+                        if (x.dstart != y.dstart) return x.dstart < y.dstart;
+                        return x.dend < y.dend;
+                    });
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, G / 50000));
+        if (nt <= 1) {
+            finish(0, G);
+        } else {
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nt; ++k) pool.emplace_back(finish, G * k / nt, G * (k + 1) / nt);
+            for (auto &th : pool) th.join();
+        }
+    }
+    timer.mark("group + sort domains");
 }
 
 int default_threads() {
+    if (const char *env = getenv("GCRF_TABLE_THREADS")) {
+        const int v = atoi(env);
+        if (v >= 1) return v > 64 ? 64 : v;
+    }
     unsigned n = std::thread::hardware_concurrency();
     if (n == 0) n = 1;
     if (n > 32) n = 32;
     return (int)n;
 }
 
-int load_buffers(std::vector<std::string> &&bufs, double e_filter, double p_filter, gcrf_table **out) {
+int load_buffers(std::vector<FileBuffer> &&bufs, double e_filter, double p_filter, gcrf_table **out) {
     gcrf_table *t = new (std::nothrow) gcrf_table();
     if (!t) return tfail(GCRF_ENOMEM, "out of host memory");
     t->buffers = std::move(bufs);
     std::vector<sv> feats;
-    for (size_t i = 1; i < t->buffers.size(); ++i) feats.emplace_back(t->buffers[i]);
+    for (size_t i = 1; i < t->buffers.size(); ++i) feats.emplace_back(t->buffers[i].view());
     try {
-        build(t, sv(t->buffers[0]), feats, e_filter, p_filter, default_threads());
+        build(t, t->buffers[0].view(), feats, e_filter, p_filter, default_threads());
     } catch (const ParseError &e) {
         delete t;
         return tfail(GCRF_EINVAL, "%s", e.message.c_str());
@@ -491,6 +713,34 @@ int write_all(const char *path, const std::string &text) {
     return GCRF_OK;
 }
 
+// header + the rows of genes [0, G): `emit(out, g)` appends gene g's lines; gene ranges are formatted by separate
+// threads into their own strings and written in order.
+template <typename Emit>
+int write_by_genes(const char *path, const std::string &header, size_t G, size_t bytes_per_gene, Emit &&emit) {
+    const int nt = (int)std::min<size_t>((size_t)default_threads(), std::max<size_t>(1, G / 20000));
+    std::vector<std::string> parts((size_t)nt);
+    auto work = [&](int k) {
+        std::string &out = parts[(size_t)k];
+        const size_t g0 = G * k / nt, g1 = G * (k + 1) / nt;
+        out.reserve((g1 - g0) * bytes_per_gene + 64);
+        for (size_t g = g0; g < g1; ++g) emit(out, g);
+    };
+    if (nt <= 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int k = 0; k < nt; ++k) pool.emplace_back(work, k);
+        for (auto &th : pool) th.join();
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) return tfail(GCRF_EINVAL, "cannot open %s for writing", path);
+    bool ok = fwrite(header.data(), 1, header.size(), f) == header.size();
+    for (const std::string &part : parts) ok = ok && fwrite(part.data(), 1, part.size(), f) == part.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return tfail(GCRF_EINVAL, "short write on %s", path);
+    return GCRF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -502,7 +752,7 @@ int gcrf_table_load(const char *genes_tsv, const char *const *features_tsv, int3
     if (!out) return tfail(GCRF_EINVAL, "out is NULL");
     *out = nullptr;
     if (!genes_tsv || n_features < 0 || (n_features > 0 && !features_tsv)) return tfail(GCRF_EINVAL, "bad arguments");
-    std::vector<std::string> bufs((size_t)n_features + 1);
+    std::vector<FileBuffer> bufs((size_t)n_features + 1);
     int rc = read_file(genes_tsv, &bufs[0]);
     if (rc != GCRF_OK) return rc;
     for (int32_t i = 0; i < n_features; ++i) {
@@ -519,9 +769,17 @@ int gcrf_table_parse(const char *genes, uint64_t genes_len, const char *const *f
     *out = nullptr;
     if ((!genes && genes_len) || n_features < 0 || (n_features > 0 && (!features || !features_len)))
         return tfail(GCRF_EINVAL, "bad arguments");
-    std::vector<std::string> bufs((size_t)n_features + 1);
-    bufs[0].assign(genes ? genes : "", (size_t)genes_len);
-    for (int32_t i = 0; i < n_features; ++i) bufs[(size_t)i + 1].assign(features[i] ? features[i] : "", (size_t)features_len[i]);
+    std::vector<FileBuffer> bufs((size_t)n_features + 1);
+    auto copy_in = [](FileBuffer &b, const char *p, uint64_t n) {
+        if (!b.allocate((size_t)n)) return false;
+        if (n) memcpy(b.data, p, (size_t)n);
+        return true;
+    };
+    if (!copy_in(bufs[0], genes, genes_len)) return tfail(GCRF_ENOMEM, "out of host memory");
+    for (int32_t i = 0; i < n_features; ++i) {
+        if (features_len[i] && !features[i]) return tfail(GCRF_EINVAL, "features buffer %d is NULL", i);
+        if (!copy_in(bufs[(size_t)i + 1], features[i], features_len[i])) return tfail(GCRF_ENOMEM, "out of host memory");
+    }
     return load_buffers(std::move(bufs), e_filter, p_filter, out);
 }
 
@@ -647,13 +905,11 @@ int gcrf_table_write_genes(const gcrf_table *t, const double *row_prob, const ch
         any_avg |= !std::isnan(avg[g]);
         any_max |= !std::isnan(mx[g]);
     }
-    std::string out;
-    out.reserve(G * 96 + 128);
-    out += "sequence_id\tprotein_id\tstart\tend\tstrand";
-    if (any_avg) out += "\taverage_p";  // a column of nothing but its default is left out (gecco/_base.py:136-144)
-    if (any_max) out += "\tmax_p";
-    out += '\n';
-    for (size_t g = 0; g < G; ++g) {
+    std::string header = "sequence_id\tprotein_id\tstart\tend\tstrand";
+    if (any_avg) header += "\taverage_p";  // a column of nothing but its default is left out (gecco/_base.py:136-144)
+    if (any_max) header += "\tmax_p";
+    header += '\n';
+    return write_by_genes(path, header, G, 96, [&](std::string &out, size_t g) {
         const GeneRow &r = t->genes[g];
         out.append(r.seq);
         out += '\t';
@@ -673,8 +929,7 @@ int gcrf_table_write_genes(const gcrf_table *t, const double *row_prob, const ch
             if (!std::isnan(mx[g])) append_repr(out, mx[g]);
         }
         out += '\n';
-    }
-    return write_all(path, out);
+    });
 }
 
 int gcrf_table_write_clusters(const gcrf_table *t, const double *row_prob, const int32_t *seg_contig, const int32_t *seg_begin,
@@ -763,12 +1018,11 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
         }
         for (double p : dp) any |= !std::isnan(p);
     }
-    std::string out;
-    out.reserve(t->domains.size() * 160 + 160);
-    out += "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end";
-    if (any) out += "\tcluster_probability";
-    out += '\n';
-    for (size_t g = 0; g < G; ++g) {
+    std::string header = "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end";
+    if (any) header += "\tcluster_probability";
+    header += '\n';
+    const size_t per_gene = G ? 160 * (t->domains.size() / G + 1) : 160;
+    return write_by_genes(path, header, G, per_gene, [&](std::string &out, size_t g) {
         const GeneRow &r = t->genes[g];
         for (int64_t k = t->dom_ptr[g]; k < t->dom_ptr[g + 1]; ++k) {
             const DomainRow &d = t->domains[(size_t)k];
@@ -799,8 +1053,7 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
             }
             out += '\n';
         }
-    }
-    return write_all(path, out);
+    });
 }
 
 }  // extern "C"
