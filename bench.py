@@ -34,8 +34,16 @@ import time
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# stdout carries exactly one JSON line: NCCL's version banner (printed to its debug file, stdout by default) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner at NCCL_DEBUG=WARN/VERSION):
+# file descriptor 1 is pointed at stderr for the life of the process and the JSON line goes to the saved descriptor.
+sys.stdout.flush()
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 import numpy  # noqa: E402
 
@@ -127,7 +135,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -394,7 +402,7 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "parity_max_abs_err_vs_oracle": parity,
         }
-        print(json.dumps(line))
+        emit(line)
     for p in pins + [pout, pin16, pout32]:
         p.free()
     engine.close()
