@@ -191,6 +191,45 @@ def test_larger_shuffled_tables_in_two_feature_files(weights, tmp_path):
         assert tables.domains == ftexts[0].count("\n") - 1
 
 
+def test_random_small_tables_property(weights, tmp_path):
+    """Hypothesis: random tiny tables — equal starts, shared ids across files, NaN / empty numeric fields, unknown and
+    repeated domain names, every filter combination — native result == row-by-row restatement, both feature types."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    names = list(weights.attrs[:6]) + ["PF99999", "X"]
+    gene = st.tuples(st.sampled_from(["b", "a", "a.1", "c10", "c9"]), st.integers(1, 60), st.integers(1, 40), st.sampled_from("+-"))
+    number = st.one_of(st.just(""), st.just("nan"), st.floats(1e-30, 1e-3).map(repr), st.just("0.0"), st.just("1e-09"))
+    domain = st.tuples(st.integers(0, 11), st.sampled_from(names), number, number, st.integers(1, 30), st.integers(1, 30))
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(st.lists(gene, min_size=0, max_size=12), st.lists(domain, max_size=30), st.sampled_from([None, 1e-9, 1e-5]),
+           st.sampled_from([None, 1e-6]), st.integers(0, 3))
+    def check(genes, domains, p_filter, e_filter, split):
+        rows = [(seq, f"{seq}_g{k}", start, start + 3 * length, strand) for k, (seq, start, length, strand) in enumerate(genes)]
+        gtext = "sequence_id\tprotein_id\tstart\tend\tstrand\n" + "".join("\t".join(map(str, r)) + "\n" for r in rows)
+        head = "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end\n"
+        frows = []
+        for g, name, ev, pv, ds, length in domains:
+            if rows:
+                r = rows[g % len(rows)]
+                frows.append("\t".join(map(str, (*r, name, "Pfam", ev, pv, ds, ds + length))) + "\n")
+        cut = min(split, len(frows))
+        ftexts = [head + "".join(frows[:cut]), head + "".join(frows[cut:])]
+        want = tables_oracle.load(gtext, ftexts, e_filter=e_filter, p_filter=p_filter)
+        with native(gtext, ftexts, e_filter=e_filter, p_filter=p_filter) as tables:
+            assert tables.gene_ids == [g["protein_id"] for g in want]
+            assert tables.annotated.tolist() == [int(bool(g["domains"])) for g in want]
+            for feature_type in ("protein", "domain"):
+                packed = assert_same_pack(tables, want, weights, feature_type)
+                prob = [0.25 + 0.5 * ((7 * k) % 11) / 11 for k in range(packed.G)]
+                tables.write_genes(tmp_path / "g.tsv", numpy.array(prob))
+                tables.write_features(tmp_path / "f.tsv", numpy.array(prob))
+                assert (tmp_path / "g.tsv").read_text() == tables_oracle.dump_genes(want, prob, feature_type)
+                assert (tmp_path / "f.tsv").read_text() == tables_oracle.dump_features(want, prob, feature_type)
+
+    check()
+
+
 def test_table_errors_are_the_reference_s_value_errors(bgc):
     gtext, ftext = bgc_tables(bgc)
     lines = gtext.splitlines()
