@@ -325,7 +325,7 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
             } else {
                 skipped = true;  // :228-234 — contig too short and padding disabled
             }
-            float p = fast_div(q, 1.0f + q);
+            float p = fminf(fast_div(q, 1.0f + q), 1.0f);  // the approximate reciprocal can land one ulp above
             if (skipped) p = __int_as_float(0x7fc00000);
             const int g = T0 + (tid - lo);
             if (args.out_f32) static_cast<float *>(args.out)[g] = p;
