@@ -108,7 +108,10 @@ struct SegmentsArgs {
     int64_t *count;             // device: number of valid clusters found (may exceed capacity)
     // scratch, carved by launch_segments
     uint8_t *flag, *cmark;
-    int32_t *ann_prefix, *end_prefix, *ann_pos, *run_start;
+    int32_t *ann_prefix, *ann_pos;                       // [G+1], [G]
+    int32_t *run_end, *run_start, *run_contig;           // one record per run (at most G)
+    int32_t *contig_first_run;                           // [C] runs that ended before the contig's first gene
+    int32_t *n_runs;                                     // device scalar
 };
 size_t segments_scratch_bytes(int64_t G, int num_sms);
 cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaStream_t stream, int64_t *launches);

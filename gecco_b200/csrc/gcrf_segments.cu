@@ -11,11 +11,15 @@
 //                                   (a gene without one — NaN — inherits the state of the last gene that has)
 //   round 2  annotated-gene count   sum-scan (exclusive prefix + compaction array of annotated positions),
 //            raw-run ordinal        sum-scan of run ends (the reference numbers clusters per contig BEFORE validation),
-//            run start              max-scan of "latest breaker": an out-of-cluster gene or a contig start
-//   round 3  valid-cluster count    sum-scan -> clusters are written in the reference's order, no atomics, no sort
+//            run start              max-scan of "latest breaker": an out-of-cluster gene or a contig start,
+//            contig index           sum-scan of contig starts
+//            -> one RECORD per run (last gene, first gene, contig), written where the run ends, and the number of
+//               runs that ended before each contig
+//   round 3  valid-cluster count    sum-scan over the RUNS (not the genes) -> clusters are written in the reference's
+//            order, no atomics, no sort
 //
-// Every run end evaluates trim + validation in O(1) from those arrays (one binary search over contig_ptr per run).
-// HBM-bound integer/byte work: 9 B/gene read in round 1, <= 18 B/gene of scratch written and read once after that.
+// Every run evaluates trim + validation in O(1) from its record and the annotated-gene prefix.
+// HBM-bound integer/byte work: 9 B/gene read in round 1, ~6 B/gene of scratch written in round 2, the rest is per run.
 #include "gcrf_kernels.cuh"
 
 namespace gcrf {
@@ -27,17 +31,17 @@ constexpr int kItems = 8;
 constexpr int kTile = kThreads * kItems;
 
 struct SumMax {
-    int32_t ann, ends, brk;  // annotated genes, run ends, latest breaker position (max)
+    int32_t ann, ends, brk, cst;  // annotated genes, run ends, latest breaker position (max), contig starts
 };
 __device__ __forceinline__ SumMax combine(const SumMax &a, const SumMax &b) {
-    return SumMax{a.ann + b.ann, a.ends + b.ends, max(a.brk, b.brk)};
+    return SumMax{a.ann + b.ann, a.ends + b.ends, max(a.brk, b.brk), a.cst + b.cst};
 }
 __device__ __forceinline__ uint32_t combine(uint32_t a, uint32_t b) { return max(a, b); }
 __device__ __forceinline__ int32_t combine(int32_t a, int32_t b) { return a + b; }
 
 __device__ __forceinline__ SumMax shfl_up(const SumMax &v, int d) {
     return SumMax{__shfl_up_sync(0xffffffffu, v.ann, d), __shfl_up_sync(0xffffffffu, v.ends, d),
-                  __shfl_up_sync(0xffffffffu, v.brk, d)};
+                  __shfl_up_sync(0xffffffffu, v.brk, d), __shfl_up_sync(0xffffffffu, v.cst, d)};
 }
 __device__ __forceinline__ uint32_t shfl_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ int32_t shfl_up(int32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
@@ -156,7 +160,7 @@ template <bool kReplay>
 __global__ void __launch_bounds__(kThreads)
 runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
     __shared__ SumMax sWarp[kThreads / 32 + 1];
-    const SumMax ident{0, 0, 0};
+    const SumMax ident{0, 0, 0, 0};
     const int64_t c0 = (int64_t)blockIdx.x * geo.chunk, c1 = min(geo.G, c0 + geo.chunk);
     SumMax carry = ident;
     if (kReplay) carry = block_fold(partial, (int)blockIdx.x, ident, sWarp);
@@ -174,6 +178,7 @@ runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
                 item[i].ends = is_run_end(a, g, geo.G) ? 1 : 0;
                 // latest place a run can have started: right after an out-of-cluster gene, or at a contig start
                 item[i].brk = !fl ? (int32_t)(g + 1) : (a.cmark[g] ? (int32_t)g : 0);
+                item[i].cst = a.cmark[g] ? 1 : 0;
             }
             mine = combine(mine, item[i]);
         }
@@ -187,16 +192,21 @@ runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
                 const int64_t g = g0 + i;
                 if (g < c1) {
                     a.ann_prefix[g] = run.ann;    // annotated genes in [0, g)
-                    a.end_prefix[g] = run.ends;   // run ends in [0, g)
                     if (item[i].ann) a.ann_pos[run.ann] = (int32_t)g;
+                    if (item[i].cst) a.contig_first_run[run.cst] = run.ends;  // runs that ended before this contig
                 }
+                const int32_t r = run.ends;  // runs that ended before g: the index of a run ending at g
                 run = combine(run, item[i]);
-                if (g < c1) a.run_start[g] = run.brk;  // meaningful where flag[g] is set
+                if (g < c1 && item[i].ends) {
+                    a.run_end[r] = (int32_t)g;
+                    a.run_start[r] = run.brk;
+                    a.run_contig[r] = run.cst - 1;
+                }
             }
             carry = combine(carry, total);
             if (t0 + kTile >= c1 && c1 == geo.G && threadIdx.x == 0) {
                 a.ann_prefix[geo.G] = carry.ann;
-                a.end_prefix[geo.G] = carry.ends;
+                *a.n_runs = carry.ends;
             }
         }
     }
@@ -217,9 +227,9 @@ __device__ __forceinline__ int32_t overlap(int32_t a0, int32_t a1, int32_t b0, i
     return max(0, min(a1, b1) - max(a0, b0));
 }
 
-__device__ Segment evaluate_run(const SegmentsArgs &a, int64_t g) {
+__device__ Segment evaluate_run(const SegmentsArgs &a, int32_t r) {
     Segment s;
-    const int32_t rs = a.run_start[g], re = (int32_t)g + 1;
+    const int32_t rs = a.run_start[r], re = a.run_end[r] + 1, c = a.run_contig[r];
     int32_t b = rs, t = re;
     int32_t k0 = a.ann_prefix[b], k1 = a.ann_prefix[t];
     if (a.trim) {  // _trim_cluster: genes without domains are dropped from both ends
@@ -230,47 +240,45 @@ __device__ Segment evaluate_run(const SegmentsArgs &a, int64_t g) {
             t = b;  // nothing annotated: the cluster is emptied
         }
     }
-    // contig of the run: largest c with contig_ptr[c] <= rs
-    int64_t lo = 0, hi = a.C;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(a.contig_ptr + mid) <= rs) lo = mid; else hi = mid;
-    }
-    const int32_t cs = __ldg(a.contig_ptr + lo), ce = __ldg(a.contig_ptr + lo + 1);
     // _validate_cluster, criterion "gecco": annotated genes of the cluster >= n_cds, and genes of the cluster that
     // are not among the contig's first / last `edge_distance` ANNOTATED genes >= n_cds
     const int32_t n_annot = k1 - k0;
     int32_t n_edge = 0;
     if (a.edge_distance > 0) {
+        const int32_t cs = __ldg(a.contig_ptr + c), ce = __ldg(a.contig_ptr + c + 1);
         const int32_t A0 = a.ann_prefix[cs], nA = a.ann_prefix[ce] - A0;
         const int32_t r0 = k0 - A0, r1 = k1 - A0;  // ranks (within the contig) of the cluster's annotated genes
         const int32_t low1 = min(a.edge_distance, nA), high0 = max(0, nA - a.edge_distance);
         n_edge = overlap(r0, r1, 0, low1) + overlap(r0, r1, high0, nA) - overlap(r0, r1, high0, low1);
     }
-    s.contig = (int32_t)lo;
+    s.contig = c;
     s.begin = b;
     s.end = t;
-    s.ordinal = a.end_prefix[g] - a.end_prefix[cs] + 1;  // enumerate(clusters) per contig, :199-200
+    s.ordinal = r - a.contig_first_run[c] + 1;  // enumerate(clusters) per contig, :199-200
     s.valid = n_annot >= a.n_cds && (t - b) - n_edge >= a.n_cds;
     return s;
 }
 
+// The scan of round 3 runs over the run records; the number of runs is known on the device only, so both launches
+// derive the same chunking from it.
 template <bool kReplay>
 __global__ void __launch_bounds__(kThreads)
-emit_kernel(const SegmentsArgs a, const Geometry geo, int32_t *partial) {
+emit_kernel(const SegmentsArgs a, int32_t *partial) {
     __shared__ int32_t sWarp[kThreads / 32 + 1];
-    const int64_t c0 = (int64_t)blockIdx.x * geo.chunk, c1 = min(geo.G, c0 + geo.chunk);
+    const int64_t R = *a.n_runs;
+    const int64_t tiles = (R + kTile - 1) / kTile;
+    const int64_t chunk = ((tiles + gridDim.x - 1) / gridDim.x) * kTile;
+    const int64_t c0 = min(R, (int64_t)blockIdx.x * chunk), c1 = min(R, c0 + chunk);
     int32_t carry = 0;
     if (kReplay) carry = block_fold(partial, (int)blockIdx.x, 0, sWarp);
     for (int64_t t0 = c0; t0 < c1; t0 += kTile) {
-        const int64_t g0 = t0 + (int64_t)threadIdx.x * kItems;
+        const int64_t r0 = t0 + (int64_t)threadIdx.x * kItems;
         Segment seg[kItems];
         int32_t mine = 0;
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
-            const int64_t g = g0 + i;
             seg[i].valid = false;
-            if (g < c1 && is_run_end(a, g, geo.G)) seg[i] = evaluate_run(a, g);
+            if (r0 + i < c1) seg[i] = evaluate_run(a, (int32_t)(r0 + i));
             mine += seg[i].valid ? 1 : 0;
         }
         if (!kReplay) {
@@ -336,9 +344,10 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(const SegmentsArgs a) {
 }  // namespace
 
 size_t segments_scratch_bytes(int64_t G, int num_sms) {
-    // flag[G] cmark[G+1] (bytes, padded) + ann_prefix[G+1] end_prefix[G+1] ann_pos[G] run_start[G] + chunk summaries
+    // flag[G] cmark[G+1] (bytes, padded) + ann_prefix[G+1] ann_pos[G] run_end/run_start/run_contig[<= G]
+    // contig_first_run[<= G+1] + the run count + chunk summaries
     const size_t bytes8 = (((size_t)G + 16) & ~(size_t)15) * 2 + 32;
-    return bytes8 + 4 * ((size_t)G + 4) * 4 + (size_t)num_sms * 8 * sizeof(SumMax) + 64;
+    return bytes8 + 6 * ((size_t)G + 4) * 4 + 16 + (size_t)num_sms * 8 * sizeof(SumMax) + 64;
 }
 
 cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaStream_t stream, int64_t *launches) {
@@ -351,9 +360,12 @@ cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaS
     args.flag = reinterpret_cast<uint8_t *>(p); p += bytes8;
     args.cmark = reinterpret_cast<uint8_t *>(p); p += bytes8 + 32;
     args.ann_prefix = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
-    args.end_prefix = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
     args.ann_pos = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.run_end = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
     args.run_start = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.run_contig = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.contig_first_run = reinterpret_cast<int32_t *>(p); p += ((size_t)G + 4) * 4;
+    args.n_runs = reinterpret_cast<int32_t *>(p); p += 16;
     void *partial = p;
 
     const int64_t tiles = (G + kTile - 1) / kTile;
@@ -371,8 +383,8 @@ cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaS
     state_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<uint32_t *>(partial));
     runs_kernel<false><<<n, kThreads, 0, stream>>>(args, geo, static_cast<SumMax *>(partial));
     runs_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<SumMax *>(partial));
-    emit_kernel<false><<<n, kThreads, 0, stream>>>(args, geo, static_cast<int32_t *>(partial));
-    emit_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<int32_t *>(partial));
+    emit_kernel<false><<<n, kThreads, 0, stream>>>(args, static_cast<int32_t *>(partial));
+    emit_kernel<true><<<n, kThreads, 0, stream>>>(args, static_cast<int32_t *>(partial));
     stats_kernel<<<num_sms * 2, kThreads, 0, stream>>>(args);
     if (launches) *launches += 8;
     return cudaGetLastError();
