@@ -152,10 +152,6 @@ __global__ void __launch_bounds__(kThreads) mark_kernel(const int32_t *__restric
 }
 
 // ---- round 2
-__device__ __forceinline__ bool is_run_end(const SegmentsArgs &a, int64_t g, int64_t G) {
-    return a.flag[g] && (g + 1 == G || !a.flag[g + 1] || a.cmark[g + 1]);
-}
-
 template <bool kReplay>
 __global__ void __launch_bounds__(kThreads)
 runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
@@ -168,17 +164,40 @@ runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
         const int64_t g0 = t0 + (int64_t)threadIdx.x * kItems;
         SumMax item[kItems];
         SumMax mine = ident;
+        // eight genes per thread: their flag / annotation / contig-start bytes come as ONE 8-byte load per array
+        // (g0 is a multiple of 8 and the arrays are 16-byte aligned; the scratch is padded past G), plus the two
+        // bytes of the gene behind them
+        static_assert(kItems == 8, "byte arrays are read eight at a time");
+        uint64_t fl8 = 0, an8 = 0, cm8 = 0;
+        unsigned next_fl = 0, next_cm = 1;
+        if (g0 < c1) {
+            fl8 = *reinterpret_cast<const uint64_t *>(a.flag + g0);
+            cm8 = *reinterpret_cast<const uint64_t *>(a.cmark + g0);
+            if (g0 + 8 <= geo.G && (reinterpret_cast<uintptr_t>(a.annotated) & 7) == 0) {  // a caller's device array
+                an8 = __ldg(reinterpret_cast<const unsigned long long *>(a.annotated + g0));
+            } else {
+                for (int i = 0; i < 8 && g0 + i < geo.G; ++i) an8 |= (uint64_t)(a.annotated[g0 + i] != 0) << (8 * i);
+            }
+            if (g0 + 8 < geo.G) {
+                next_fl = a.flag[g0 + 8];
+                next_cm = a.cmark[g0 + 8];
+            }
+        }
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
             const int64_t g = g0 + i;
             item[i] = ident;
             if (g < c1) {
-                const bool fl = a.flag[g] != 0;
-                item[i].ann = a.annotated[g] ? 1 : 0;
-                item[i].ends = is_run_end(a, g, geo.G) ? 1 : 0;
+                const bool fl = ((fl8 >> (8 * i)) & 0xff) != 0;
+                const bool cm = ((cm8 >> (8 * i)) & 0xff) != 0;
+                const bool fl_next = i + 1 < kItems ? ((fl8 >> (8 * (i + 1))) & 0xff) != 0 : next_fl != 0;
+                const bool cm_next = i + 1 < kItems ? ((cm8 >> (8 * (i + 1))) & 0xff) != 0 : next_cm != 0;
+                item[i].ann = ((an8 >> (8 * i)) & 0xff) ? 1 : 0;
+                // is_run_end: in a cluster, and the next gene is not, or opens another contig, or does not exist
+                item[i].ends = (fl && (g + 1 == geo.G || !fl_next || cm_next)) ? 1 : 0;
                 // latest place a run can have started: right after an out-of-cluster gene, or at a contig start
-                item[i].brk = !fl ? (int32_t)(g + 1) : (a.cmark[g] ? (int32_t)g : 0);
-                item[i].cst = a.cmark[g] ? 1 : 0;
+                item[i].brk = !fl ? (int32_t)(g + 1) : (cm ? (int32_t)g : 0);
+                item[i].cst = cm ? 1 : 0;
             }
             mine = combine(mine, item[i]);
         }
@@ -187,11 +206,12 @@ runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
         } else {
             SumMax total;
             SumMax run = combine(carry, block_exclusive_scan(mine, ident, sWarp, &total));
+            int32_t pre[kItems];
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
                 const int64_t g = g0 + i;
+                pre[i] = run.ann;  // annotated genes in [0, g)
                 if (g < c1) {
-                    a.ann_prefix[g] = run.ann;    // annotated genes in [0, g)
                     if (item[i].ann) a.ann_pos[run.ann] = (int32_t)g;
                     if (item[i].cst) a.contig_first_run[run.cst] = run.ends;  // runs that ended before this contig
                 }
@@ -201,6 +221,15 @@ runs_kernel(const SegmentsArgs a, const Geometry geo, SumMax *partial) {
                     a.run_end[r] = (int32_t)g;
                     a.run_start[r] = run.brk;
                     a.run_contig[r] = run.cst - 1;
+                }
+            }
+            if (g0 < c1) {  // two 16-byte stores (the array is padded past G; slots beyond c1 are rewritten by their owner)
+                int4 *dst = reinterpret_cast<int4 *>(a.ann_prefix + g0);
+                if (g0 + kItems <= c1) {
+                    dst[0] = make_int4(pre[0], pre[1], pre[2], pre[3]);
+                    dst[1] = make_int4(pre[4], pre[5], pre[6], pre[7]);
+                } else {
+                    for (int i = 0; g0 + i < c1; ++i) a.ann_prefix[g0 + i] = pre[i];
                 }
             }
             carry = combine(carry, total);
@@ -264,6 +293,9 @@ __device__ Segment evaluate_run(const SegmentsArgs &a, int32_t r) {
 template <bool kReplay>
 __global__ void __launch_bounds__(kThreads)
 emit_kernel(const SegmentsArgs a, int32_t *partial) {
+    // runs are few (one per cluster candidate) and every evaluation is a chain of dependent loads: two runs per thread
+    // spread them over as many CTAs as possible
+    constexpr int kItems = 2, kTile = kThreads * kItems;
     __shared__ int32_t sWarp[kThreads / 32 + 1];
     const int64_t R = *a.n_runs;
     const int64_t tiles = (R + kTile - 1) / kTile;
@@ -385,7 +417,7 @@ cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaS
     runs_kernel<true><<<n, kThreads, 0, stream>>>(args, geo, static_cast<SumMax *>(partial));
     emit_kernel<false><<<n, kThreads, 0, stream>>>(args, static_cast<int32_t *>(partial));
     emit_kernel<true><<<n, kThreads, 0, stream>>>(args, static_cast<int32_t *>(partial));
-    stats_kernel<<<num_sms * 2, kThreads, 0, stream>>>(args);
+    stats_kernel<<<num_sms * 16, kThreads, 0, stream>>>(args);  // the cluster count lives on the device: a wide grid-stride
     if (launches) *launches += 8;
     return cudaGetLastError();
 }
