@@ -327,13 +327,14 @@ class CRFEngine:
             C, G, nnz, out.ctypes.data if G else None, flags))
         return out
 
-    def features_from_accessions(self, accession, gene_ptr) -> numpy.ndarray:
+    def features_from_accessions(self, accession, gene_ptr, *, ptr64: bool = False) -> numpy.ndarray:
         """Integer domain accessions (row by row, domain-start order) -> attribute ids, -1 for unknown accessions
-        and for repeats inside a gene (``gcrf_features_from_accessions``, host buffers, blocking)."""
+        and for repeats inside a gene (``gcrf_features_from_accessions``, host buffers, blocking).  ``ptr64``
+        passes 64-bit row pointers even when 32 bits would do."""
         accession = numpy.ascontiguousarray(accession, dtype=numpy.int32)
         gene_ptr = numpy.asarray(gene_ptr)
         flags = 0
-        if gene_ptr.dtype == numpy.int64 and gene_ptr.size and int(gene_ptr[-1]) > 0x7FFFFFFF:
+        if ptr64 or (gene_ptr.dtype == numpy.int64 and gene_ptr.size and int(gene_ptr[-1]) > 0x7FFFFFFF):
             gene_ptr = numpy.ascontiguousarray(gene_ptr, dtype=numpy.int64)
             flags = GCRF_FLAG_PTR64
         else:

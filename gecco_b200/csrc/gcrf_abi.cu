@@ -596,8 +596,8 @@ int gcrf_features_from_accessions(gcrf_model *m, const int32_t *accession, const
         d_out = static_cast<int32_t *>(m->b_attr.ptr);
     }
     cudaError_t err = gcrf::launch_features(d_acc, ptr64 ? nullptr : static_cast<const int32_t *>(d_ptr),
-                                            ptr64 ? static_cast<const int64_t *>(d_ptr) : nullptr, G, m->d_lut,
-                                            m->lut_size, d_out, m->num_sms, m->stream, &m->launches);
+                                            ptr64 ? static_cast<const int64_t *>(d_ptr) : nullptr, G, nnz, m->d_lut,
+                                            m->lut_size, m->A, d_out, m->num_sms, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_features");
     if (host) {
         GCRF_CUDA(cudaMemcpyAsync(attr_idx_out, d_out, (size_t)nnz * 4, cudaMemcpyDeviceToHost, m->stream));

@@ -85,8 +85,8 @@ cudaError_t launch_chain(const ChainArgs &args, int num_sms, cudaStream_t stream
 
 // accession -> attribute id with the reference's set semantics (repeats inside a gene and unknown accessions -> -1)
 cudaError_t launch_features(const int32_t *accession, const int32_t *gene_ptr32, const int64_t *gene_ptr64, int64_t G,
-                            const int32_t *lut, int32_t lut_size, int32_t *attr_idx_out, int num_sms,
-                            cudaStream_t stream, int64_t *launches);
+                            int64_t nnz, const int32_t *lut, int32_t lut_size, int32_t num_attrs, int32_t *attr_idx_out,
+                            int num_sms, cudaStream_t stream, int64_t *launches);
 
 // uint16 attribute ids -> int32 (0xFFFF -> -1); out holds at least round_up(n, 8) entries
 cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int num_sms, cudaStream_t stream, int64_t *launches);

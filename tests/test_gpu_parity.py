@@ -451,3 +451,52 @@ def test_feature_extraction_on_device(engine, mibig, weights):
     out = engine.features_from_accessions(acc, numpy.array([0, 5, 7], dtype=numpy.int32))
     ix = weights.attr_index
     assert out.tolist() == [ix["PF00109"], -1, -1, ix["PF00005"], -1, ix["PF00005"], ix["PF02801"]]
+
+
+def _features_restated(accession, gene_ptr, lut):
+    """features.py:13-35 on arrays: a gene's features are a dict keyed by domain name, so the first row of each
+    accession keeps the id; the tagger drops names its dictionary does not hold."""
+    out = numpy.full(len(accession), -1, dtype=numpy.int32)
+    for g in range(len(gene_ptr) - 1):
+        seen = set()
+        for p in range(int(gene_ptr[g]), int(gene_ptr[g + 1])):
+            a = int(accession[p])
+            if 0 <= a < len(lut) and lut[a] >= 0 and a not in seen:
+                out[p] = lut[a]
+                seen.add(a)
+    return out
+
+
+@pytest.mark.parametrize("mean_rows", [0.7, 1.4, 5.0, 9.0, 25.0])
+def test_feature_extraction_fuzz(engine, weights, mean_rows, monkeypatch):
+    """Ragged genes with repeats (inside one 32-row step, across steps and across batches), unknown and negative
+    accessions, empty genes, genes of hundreds of rows: both bitmap kernels (sparse / dense grouping), both pointer
+    widths and the gene-by-gene kernel against the row-by-row restatement."""
+    from gecco_b200.packer import pfam_lut
+
+    lut = pfam_lut(weights.attrs)
+    known = numpy.flatnonzero(lut >= 0)
+    rng = numpy.random.default_rng(int(mean_rows * 10))
+    for G in (1, 31, 32, 33, 700, 5003):
+        rows = rng.poisson(mean_rows, size=G)
+        rows[rng.random(G) < 0.02] = rng.integers(33, 700)  # a few long genes
+        if G > 40:
+            rows[7:19] = 0
+        gene_ptr = numpy.concatenate([[0], numpy.cumsum(rows)]).astype(numpy.int64)
+        n = int(gene_ptr[-1])
+        acc = rng.choice(known, size=n).astype(numpy.int32)
+        small = rng.choice(known, size=12)  # a small pool makes repeats common
+        pick = rng.random(n) < 0.3
+        acc[pick] = rng.choice(small, size=int(pick.sum()))
+        acc[rng.random(n) < 0.05] = 3  # PF00003 is not in the model
+        acc[rng.random(n) < 0.01] = -7
+        acc[rng.random(n) < 0.01] = len(lut) + 11
+        want = _features_restated(acc, gene_ptr, lut)
+        for simple in ("0", "1"):
+            monkeypatch.setenv("GCRF_FEATURES_SIMPLE", simple)
+            for ptr64 in (False, True):
+                got = engine.features_from_accessions(acc, gene_ptr, ptr64=ptr64)
+                assert numpy.array_equal(got, want), (G, simple, ptr64, numpy.flatnonzero(got != want)[:10])
+        monkeypatch.setenv("GCRF_FEATURES_SIMPLE", "0")
+        # a second call on the same handle: the kernels leave their bitmaps clean
+        assert numpy.array_equal(engine.features_from_accessions(acc, gene_ptr), want)
