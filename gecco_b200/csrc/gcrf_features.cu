@@ -44,32 +44,88 @@ features_simple_kernel(const int32_t *__restrict__ accession, const PtrT *__rest
         gene_rows_simple(accession, (int64_t)__ldg(gene_ptr + g), (int64_t)__ldg(gene_ptr + g + 1), lut, lut_size, out, lane);
 }
 
+// old value of the word when `id` is an attribute id (not 0xFFFF), else 0 and no access: predicated, no branch
+__device__ __forceinline__ uint32_t atom_or_shared_if_id(uint32_t addr, uint32_t bits, uint32_t id) {
+    uint32_t old;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0xFFFF;\n\tmov.u32 %0, 0;\n\t@p atom.shared.or.b32 %0, [%1], %2;\n\t}"
+        : "=r"(old)
+        : "r"(addr), "r"(bits), "r"(id)
+        : "memory");
+    return old;
+}
+// idx += step when bound <= row (one level of the upper-bound search; a predicated add, not a select and an add)
+__device__ __forceinline__ void advance_if_le(int &idx, int bound, int row, int step) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.s32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}" : "+r"(idx) : "r"(bound), "r"(row), "r"(step));
+}
+// A value every lane holds, handed to the compiler as provably warp-uniform (REDUX writes a uniform register): branches
+// on it need no reconvergence bookkeeping and the shuffles behind them no divergence check.
+__device__ __forceinline__ int uniform(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ void store_shared_zero4(uint32_t addr) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void store_shared_zero(uint32_t addr) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ uint32_t load_shared_u16(uint32_t addr) {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
 // The streaming kernel.  A warp takes a block of 32 consecutive genes (33 row pointers: one coalesced load, kept in
 // registers as offsets from the block's first row, the next block's already in flight) and cuts it into groups of GG
 // genes.  A group's rows are one contiguous range, read 32 rows per step with lane = row — every load and store is a
-// full 128-byte line whatever the genes' sizes — U steps in flight (accession loads, then the LUT gathers, then the
-// stores).  A row finds its gene inside the group with log2(GG) shuffles over the pointer registers (upper bound, so
-// empty genes are skipped).  Repeats: a bitmap per gene of the group over the attribute ids in shared memory
-// (atomicOr; a set bit means another row of this gene has the id).  Only a batch that really holds a repeat — rare in
-// real tables, never in the synthetic ones — pays for the exact answer: its rows compare their accession with the
-// earlier rows of their gene, so the FIRST of equal rows keeps the key (features.py:32).  Lanes clear the words they
-// set when the group fitted one batch; a longer group is cleared wholesale.
-template <typename PtrT, int GG, int U>
-__global__ void __launch_bounds__(kThreads)
+// full 128-byte line whatever the genes' sizes — in batches of U steps.  The accession loads of the NEXT batch (next
+// group, or the next block's first group) are issued before the current batch is worked on, so the HBM round trip
+// overlaps the table lookups and the bitmap work instead of preceding them.  A row finds its gene inside the group
+// with log2(GG) shuffles over the pointer registers (upper bound, so empty genes are skipped).  Repeats: per warp a
+// bitmap over (attribute id, gene of the group) in shared memory — bit id * GG + gene, so the word follows from the id
+// alone — set with atomicOr; a bit found set means another row of this gene has the id.  Only a batch that really
+// holds a repeat — rare in real tables, never in the synthetic ones — pays for the exact answer: its rows compare
+// their accession with the earlier rows of their gene, so the FIRST of equal rows keeps the key (features.py:32).
+// Lanes clear the words they set when the group fitted one batch; a longer group is cleared wholesale.
+//
+// The kernel is bound by instruction issue, not by memory (ncu: 80 % issue-active at 23 % of the DRAM peak), hence the
+// raw shared-memory addresses, the clamped table index with a sentinel entry, and ids kept as 0xFFFF = "none" until
+// the store.
+//
+// SLUT: the accession -> id table is staged in shared memory as uint16 (0xFFFF = unknown).  A gather of 32 scattered
+// words through L1 costs one wavefront per distinct line — 32 cycles of the SM's load pipe per 32 rows — while the
+// same gather from shared memory costs its bank conflicts (~3.5 wavefronts).
+template <typename PtrT, int GG, int U, int THREADS, bool SLUT>
+__global__ void __launch_bounds__(THREADS, SLUT ? 2 : 1)
 features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ gene_ptr, int64_t G,
                 const int32_t *__restrict__ lut, int32_t lut_size, int32_t words, int32_t *__restrict__ out) {
     constexpr unsigned kFull = 0xffffffffu;
-    extern __shared__ uint32_t sBitmap[];  // GG * words per warp
+    constexpr uint32_t kNone = 0xFFFFu;
+    constexpr int kIdsPerWord = 32 / GG;  // GG = 8: four ids per bitmap word
+    constexpr int kIdShift = GG == 8 ? 2 : GG == 16 ? 1 : 0;
+    static_assert(GG == 8 || GG == 16 || GG == 32, "group sizes with a whole number of ids per word");
+    // Dense groups wipe their bitmap with 16-byte stores (6 per lane for 2,659 attributes) — fewer instructions than
+    // every row clearing its own word; sparse groups (a few rows against 5 KB of bitmap) clear what they set.
+    constexpr bool kOwnClear = GG != 8;
+    extern __shared__ __align__(16) uint32_t sBitmap[];  // `words` (a multiple of 4) per warp, then the uint16 table (SLUT)
     const int lane = threadIdx.x & 31;
-    uint32_t *bm = sBitmap + (threadIdx.x >> 5) * (GG * words);
-    for (int i = lane; i < GG * words; i += 32) bm[i] = 0;
+    uint32_t *bm = sBitmap + (threadIdx.x >> 5) * words;
+    for (int i = lane; i < words; i += 32) bm[i] = 0;
+    const uint32_t bm_addr = (uint32_t)__cvta_generic_to_shared(bm);
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(sBitmap + (THREADS / 32) * words);
+    if (SLUT) {
+        uint16_t *dst = reinterpret_cast<uint16_t *>(sBitmap + (THREADS / 32) * words);
+        for (int i = threadIdx.x; i < lut_size; i += THREADS) dst[i] = (uint16_t)__ldg(lut + i);  // -1 -> 0xFFFF
+        if (threadIdx.x == 0) dst[lut_size] = (uint16_t)kNone;  // where out-of-range accessions are clamped to
+        __syncthreads();
+    }
     __syncwarp();
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
+    const int64_t warp0 = (int64_t)blockIdx.x * (THREADS / 32) + uniform((int)(threadIdx.x >> 5));
+    const int64_t stride = (int64_t)gridDim.x * THREADS;  // genes per sweep of the grid: 32 per warp
     int64_t base = warp0 * 32;
     if (base >= G) return;
     int64_t p_lo = (int64_t)__ldg(gene_ptr + min(base + lane, G));  // first row of gene base + lane
     int64_t p_end = (int64_t)__ldg(gene_ptr + min(base + 32, G));   // end of the block's rows
+    int32_t acc_n[U];       // accessions of the pending batch
+    int pend_off = -1, pend_r1 = -1;  // ... which covers rows [pend_off, pend_r1) of the block it belongs to
     for (; base < G; base += stride) {
         const int ng = (int)min((int64_t)32, G - base);
         const int64_t P0 = __shfl_sync(kFull, p_lo, 0);
@@ -84,40 +140,72 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
             for (int g = 0; g < ng; ++g)
                 gene_rows_simple(accession, (int64_t)__ldg(gene_ptr + base + g), (int64_t)__ldg(gene_ptr + base + g + 1),
                                  lut, lut_size, out, lane);
+            pend_off = -1;
             continue;
         }
         const int32_t *__restrict__ acc_b = accession + P0;
         int32_t *__restrict__ out_b = out + P0;
         for (int sg = 0; sg < ng; sg += GG) {
-            const int r0 = __shfl_sync(kFull, rel, sg);
-            const int r1 = sg + GG >= ng ? (int)block_rows : __shfl_sync(kFull, rel, (sg + GG) & 31);
+            const int r0 = uniform(__shfl_sync(kFull, rel, sg));
+            const int r1 = uniform(sg + GG >= ng ? (int)block_rows : __shfl_sync(kFull, rel, (sg + GG) & 31));
             bool dirty = false;
             for (int off = r0; off < r1; off += 32 * U) {
-                int32_t acc[U], id[U];
-                int slot[U];
+                if (pend_off != off || pend_r1 != r1) {  // nothing in flight for this batch (warp-uniform)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int r = off + u * 32 + lane;
+                        acc_n[u] = r < r1 ? __ldcs(acc_b + r) : -1;
+                    }
+                }
+                uint32_t id[U];  // attribute id or kNone
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = off + u * 32 + lane;
-                    acc[u] = r < r1 ? __ldg(acc_b + r) : -1;
+                    if (SLUT) {
+                        id[u] = load_shared_u16(lut_addr + 2u * min((uint32_t)acc_n[u], (uint32_t)lut_size));
+                    } else {
+                        const int v = (unsigned)acc_n[u] < (unsigned)lut_size ? __ldg(lut + acc_n[u]) : -1;
+                        id[u] = v < 0 ? kNone : (uint32_t)v;
+                    }
                 }
+                // the loads of the batch behind this one
+                pend_off = -1;
+                if (off + 32 * U < r1) {
+                    pend_off = off + 32 * U;
+                    pend_r1 = r1;
+                } else if (sg + GG < ng) {
+                    pend_off = r1;  // the next group's rows follow this group's
+                    pend_r1 = uniform(sg + 2 * GG >= ng ? (int)block_rows : __shfl_sync(kFull, rel, (sg + 2 * GG) & 31));
+                }
+                if (pend_off >= 0) {
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    id[u] = (unsigned)acc[u] < (unsigned)lut_size ? __ldg(lut + acc[u]) : -1;
+                    for (int u = 0; u < U; ++u) {
+                        const int r = pend_off + u * 32 + lane;
+                        acc_n[u] = r < pend_r1 ? __ldcs(acc_b + r) : -1;
+                    }
+                } else if (next < G) {  // the first group of the warp's next block (its pointers have arrived by now)
+                    const int64_t P0n = __shfl_sync(kFull, p_lo, 0);
+                    const int ngn = (int)min((int64_t)32, G - next);
+                    const int64_t r1n = (GG >= ngn ? p_end : __shfl_sync(kFull, p_lo, GG & 31)) - P0n;
+                    if (p_end - P0n <= 0x7fffffff) {
+                        pend_off = 0;
+                        pend_r1 = uniform((int)r1n);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int r = u * 32 + lane;
+                            acc_n[u] = r < pend_r1 ? __ldcs(accession + P0n + r) : -1;
+                        }
+                    }
+                }
                 uint32_t seen = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    slot[u] = -1;
                     if (off + u * 32 < r1) {  // warp-uniform
                         const int r = off + u * 32 + lane;
-                        int pos = 0;  // the last gene of the group that starts at or before row r
+                        int g = sg;  // the last gene of the group that starts at or before row r
 #pragma unroll
-                        for (int s = GG / 2; s >= 1; s >>= 1)
-                            if (__shfl_sync(kFull, rel, sg + pos + s) <= r) pos += s;
-                        if (id[u] >= 0) {
-                            slot[u] = pos * words + (id[u] >> 5);
-                            const uint32_t bit = 1u << (id[u] & 31);
-                            seen |= atomicOr(&bm[slot[u]], bit) & bit;
-                        }
+                        for (int s = GG / 2; s >= 1; s >>= 1) advance_if_le(g, __shfl_sync(kFull, rel, g + s), r, s);
+                        const uint32_t bit = 1u << ((id[u] & (kIdsPerWord - 1)) * GG + (g - sg));
+                        seen |= atom_or_shared_if_id(bm_addr + ((id[u] >> kIdShift) << 2), bit, id[u]) & bit;
                     }
                 }
                 if (__any_sync(kFull, seen != 0)) {
@@ -130,31 +218,34 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
                             for (int s = GG / 2; s >= 1; s >>= 1)
                                 if (__shfl_sync(kFull, rel, sg + pos + s) <= r) pos += s;
                             const int gs = __shfl_sync(kFull, rel, sg + pos);
-                            if (id[u] >= 0)
+                            if (id[u] != kNone && r < r1) {
+                                const int32_t mine = __ldg(acc_b + r);
                                 for (int q = gs; q < r; ++q)
-                                    if (__ldg(acc_b + q) == acc[u]) {
-                                        id[u] = -1;
+                                    if (__ldg(acc_b + q) == mine) {
+                                        id[u] |= 0x10000u;  // a repeat: stored as -1, its bitmap word still cleared below
                                         break;
                                     }
+                            }
                         }
                     }
                 }
+                const bool own_clear = kOwnClear && !dirty && off + 32 * U >= r1;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int r = off + u * 32 + lane;
-                    if (r < r1) out_b[r] = id[u];
+                    if (r < r1) __stcs(out_b + r, id[u] >= kNone ? -1 : (int32_t)id[u]);
                 }
                 __syncwarp();
-                if (!dirty && off + 32 * U >= r1) {
+                if (own_clear) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (slot[u] >= 0) bm[slot[u]] = 0;  // all writers store the same zero
+                    for (int u = 0; u < U; ++u)  // all writers store the same zero
+                        if ((id[u] & 0xFFFFu) != kNone) store_shared_zero(bm_addr + (((id[u] & 0xFFFFu) >> kIdShift) << 2));
                 } else {
                     dirty = true;
                 }
             }
             if (dirty)
-                for (int i = lane; i < GG * words; i += 32) bm[i] = 0;
+                for (int i = lane * 4; i < words; i += 128) store_shared_zero4(bm_addr + i * 4);
             __syncwarp();
         }
     }
@@ -199,42 +290,47 @@ cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int nu
 
 namespace {
 
-template <typename PtrT, int GG, int U>
+template <typename PtrT, int GG, int U, int THREADS, bool SLUT>
 cudaError_t launch_features_bitmap(const int32_t *accession, const PtrT *gene_ptr, int64_t G, const int32_t *lut,
                                    int32_t lut_size, int32_t words, int32_t *out, int num_sms, cudaStream_t stream) {
-    auto kernel = features_kernel<PtrT, GG, U>;
-    const size_t smem = (size_t)GG * words * (kThreads / 32) * sizeof(uint32_t);
+    auto kernel = features_kernel<PtrT, GG, U, THREADS, SLUT>;
+    const size_t smem = (size_t)words * (THREADS / 32) * sizeof(uint32_t) + (SLUT ? ((size_t)lut_size * 2 + 2 + 15) / 16 * 16 : 0);
     cudaError_t err = cudaSuccess;
     if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
     }
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
-    int64_t blocks = ((G + 31) / 32 + kThreads / 32 - 1) / (kThreads / 32);  // one warp per 32 genes
+    int64_t blocks = ((G + 31) / 32 + THREADS / 32 - 1) / (THREADS / 32);  // one warp per 32 genes
     if (blocks > (int64_t)num_sms * per_sm) blocks = (int64_t)num_sms * per_sm;  // one resident wave, grid-stride
-    kernel<<<(int)blocks, kThreads, smem, stream>>>(accession, gene_ptr, G, lut, lut_size, words, out);
+    kernel<<<(int)blocks, THREADS, smem, stream>>>(accession, gene_ptr, G, lut, lut_size, words, out);
     return cudaGetLastError();
 }
 
 template <typename PtrT>
 cudaError_t launch_features_t(const int32_t *accession, const PtrT *gene_ptr, int64_t G, int64_t nnz, const int32_t *lut,
                               int32_t lut_size, int32_t num_attrs, int32_t *out, int num_sms, cudaStream_t stream) {
-    const int32_t words = (num_attrs + 31) / 32;
     // sparse tables (real annotation: 1.4 rows per gene) are cut into groups of 16 genes, dense ones into groups of 8
     const bool sparse = nnz < 6 * G;
-    const size_t smem = (size_t)(sparse ? 16 : 8) * words * (kThreads / 32) * sizeof(uint32_t);
-    const char *force = getenv("GCRF_FEATURES_SIMPLE");  // A/B and tests
-    if (words == 0 || smem > 96 * 1024 || (force && force[0] == '1')) {  // bitmaps do not fit: the exact gene-by-gene kernel
+    const int32_t words = (int32_t)(((int64_t)num_attrs * (sparse ? 16 : 8) + 127) / 128 * 4);  // bitmap words per warp (16-byte units)
+    const size_t bitmaps = (size_t)words * (kThreads / 32) * sizeof(uint32_t);
+    const char *force = getenv("GCRF_FEATURES_SIMPLE");  // A/B and tests: 1 = gene by gene, 2 = table never / 3 = always in shared memory
+    if (words == 0 || num_attrs >= 0xFFFF || bitmaps > 96 * 1024 || (force && force[0] == '1')) {  // bitmaps do not fit: the exact gene-by-gene kernel
         int64_t blocks = (G * 32 + kThreads - 1) / kThreads;
         if (blocks > (int64_t)num_sms * 16) blocks = (int64_t)num_sms * 16;
         features_simple_kernel<PtrT><<<(int)blocks, kThreads, 0, stream>>>(accession, gene_ptr, G, lut, lut_size, out);
         return cudaGetLastError();
     }
-    if (sparse) return launch_features_bitmap<PtrT, 16, 2>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
-    return launch_features_bitmap<PtrT, 8, 8>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
+    if (sparse) return launch_features_bitmap<PtrT, 16, 2, kThreads, false>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
+    // dense tables with enough rows to pay for staging the table (82 KB of L2 reads per CTA): two 512-thread CTAs per SM
+    const size_t staged = 2 * bitmaps + (size_t)lut_size * 2 + 16;
+    if (staged <= 110 * 1024 && !(force && force[0] == '2') &&
+        (nnz >= (int64_t)num_sms * 8192 || (force && force[0] == '3')))
+        return launch_features_bitmap<PtrT, 8, 8, 512, true>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
+    return launch_features_bitmap<PtrT, 8, 8, kThreads, false>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
 }
 
 }  // namespace
