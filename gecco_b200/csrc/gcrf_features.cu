@@ -54,23 +54,39 @@ __device__ __forceinline__ uint32_t atom_or_shared_if_id(uint32_t addr, uint32_t
         : "memory");
     return old;
 }
-// idx += step when bound <= row (one level of the upper-bound search; a predicated add, not a select and an add)
-__device__ __forceinline__ void advance_if_le(int &idx, int bound, int row, int step) {
-    asm("{\n\t.reg .pred p;\n\tsetp.le.s32 p, %1, %2;\n\t@p add.s32 %0, %0, %3;\n\t}" : "+r"(idx) : "r"(bound), "r"(row), "r"(step));
-}
 // A value every lane holds, handed to the compiler as provably warp-uniform (REDUX writes a uniform register): branches
 // on it need no reconvergence bookkeeping and the shuffles behind them no divergence check.
 __device__ __forceinline__ int uniform(int v) { return __reduce_max_sync(0xffffffffu, v); }
+// out[imm] = v when row < end (streaming store, predicated: no branch, the offset an immediate)
+template <int kByteOffset>
+__device__ __forceinline__ void store_row_if(int32_t *base, int32_t v, int row, int end) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.cs.s32 [%0 + %4], %1;\n\t}" ::"l"(base), "r"(v), "r"(row),
+                 "r"(end), "n"(kByteOffset)
+                 : "memory");
+}
 __device__ __forceinline__ void store_shared_zero4(uint32_t addr) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void store_shared_zero(uint32_t addr) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(0u) : "memory");
 }
+__device__ __forceinline__ uint32_t load_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t load_shared_u16(uint32_t addr) {
     uint16_t v;
     asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
+}
+
+template <int U, int u = 0>
+__device__ __forceinline__ void store_rows(int32_t *out_p, const uint32_t (&id)[U], int row, int end) {
+    if constexpr (u < U) {
+        store_row_if<u * 128>(out_p, id[u] >= 0xFFFFu ? -1 : (int32_t)id[u], row + u * 32, end);
+        store_rows<U, u + 1>(out_p, id, row, end);
+    }
 }
 
 // The streaming kernel.  A warp takes a block of 32 consecutive genes (33 row pointers: one coalesced load, kept in
@@ -107,12 +123,15 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
     constexpr bool kOwnClear = GG != 8;
     extern __shared__ __align__(16) uint32_t sBitmap[];  // `words` (a multiple of 4) per warp, then the uint16 table (SLUT)
     const int lane = threadIdx.x & 31;
-    uint32_t *bm = sBitmap + (threadIdx.x >> 5) * words;
+    static_assert(U <= 8, "eight start-mask words per warp");
+    uint32_t *bm = sBitmap + (threadIdx.x >> 5) * (words + 8);  // the warp's bitmap, then its start masks
     for (int i = lane; i < words; i += 32) bm[i] = 0;
     const uint32_t bm_addr = (uint32_t)__cvta_generic_to_shared(bm);
-    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(sBitmap + (THREADS / 32) * words);
+    const uint32_t mask_addr = bm_addr + words * 4;
+    const uint32_t lanemask_le = 0xffffffffu >> (31 - lane);
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(sBitmap + (THREADS / 32) * (words + 8));
     if (SLUT) {
-        uint16_t *dst = reinterpret_cast<uint16_t *>(sBitmap + (THREADS / 32) * words);
+        uint16_t *dst = reinterpret_cast<uint16_t *>(sBitmap + (THREADS / 32) * (words + 8));
         for (int i = threadIdx.x; i < lut_size; i += THREADS) dst[i] = (uint16_t)__ldg(lut + i);  // -1 -> 0xFFFF
         if (threadIdx.x == 0) dst[lut_size] = (uint16_t)kNone;  // where out-of-range accessions are clamped to
         __syncthreads();
@@ -149,6 +168,7 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
             const int r0 = uniform(__shfl_sync(kFull, rel, sg));
             const int r1 = uniform(sg + GG >= ng ? (int)block_rows : __shfl_sync(kFull, rel, (sg + GG) & 31));
             bool dirty = false;
+            int slot = -1;  // gene slot of the last row seen so far (warp-uniform)
             for (int off = r0; off < r1; off += 32 * U) {
                 if (pend_off != off || pend_r1 != r1) {  // nothing in flight for this batch (warp-uniform)
 #pragma unroll
@@ -196,17 +216,25 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
                         }
                     }
                 }
+                // The group's gene starts inside this batch, one 32-bit mask per step (a handful of lanes set them): a
+                // row's gene slot is the number of distinct starts at or before it, minus one — one popc instead of a
+                // search.  Genes without rows share their successor's start, so slots stay below GG.
+                if (lane < U) store_shared_zero(mask_addr + lane * 4);
+                __syncwarp();
+                {
+                    const int d = rel - off;
+                    if (lane >= sg && lane < sg + GG && d >= 0 && d < 32 * U && rel < r1)
+                        atom_or_shared_if_id(mask_addr + ((d >> 5) << 2), 1u << (d & 31), 0u);
+                }
+                __syncwarp();
                 uint32_t seen = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (off + u * 32 < r1) {  // warp-uniform
-                        const int r = off + u * 32 + lane;
-                        int g = sg;  // the last gene of the group that starts at or before row r
-#pragma unroll
-                        for (int s = GG / 2; s >= 1; s >>= 1) advance_if_le(g, __shfl_sync(kFull, rel, g + s), r, s);
-                        const uint32_t bit = 1u << ((id[u] & (kIdsPerWord - 1)) * GG + (g - sg));
-                        seen |= atom_or_shared_if_id(bm_addr + ((id[u] >> kIdShift) << 2), bit, id[u]) & bit;
-                    }
+                    const uint32_t starts = load_shared_u32(mask_addr + u * 4);
+                    const int g = slot + __popc(starts & lanemask_le);
+                    slot += __popc(starts);
+                    const uint32_t bit = 1u << ((id[u] & (kIdsPerWord - 1)) * GG + g);
+                    seen |= atom_or_shared_if_id(bm_addr + ((id[u] >> kIdShift) << 2), bit, id[u]) & bit;
                 }
                 if (__any_sync(kFull, seen != 0)) {
 #pragma unroll
@@ -230,10 +258,9 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
                     }
                 }
                 const bool own_clear = kOwnClear && !dirty && off + 32 * U >= r1;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int r = off + u * 32 + lane;
-                    if (r < r1) __stcs(out_b + r, id[u] >= kNone ? -1 : (int32_t)id[u]);
+                {
+                    int32_t *out_p = out_b + off + lane;
+                    store_rows<U>(out_p, id, off + lane, r1);
                 }
                 __syncwarp();
                 if (own_clear) {
@@ -294,7 +321,7 @@ template <typename PtrT, int GG, int U, int THREADS, bool SLUT>
 cudaError_t launch_features_bitmap(const int32_t *accession, const PtrT *gene_ptr, int64_t G, const int32_t *lut,
                                    int32_t lut_size, int32_t words, int32_t *out, int num_sms, cudaStream_t stream) {
     auto kernel = features_kernel<PtrT, GG, U, THREADS, SLUT>;
-    const size_t smem = (size_t)words * (THREADS / 32) * sizeof(uint32_t) + (SLUT ? ((size_t)lut_size * 2 + 2 + 15) / 16 * 16 : 0);
+    const size_t smem = (size_t)(words + 8) * (THREADS / 32) * sizeof(uint32_t) + (SLUT ? ((size_t)lut_size * 2 + 2 + 15) / 16 * 16 : 0);
     cudaError_t err = cudaSuccess;
     if (smem > 48 * 1024) {
         err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -316,7 +343,7 @@ cudaError_t launch_features_t(const int32_t *accession, const PtrT *gene_ptr, in
     // sparse tables (real annotation: 1.4 rows per gene) are cut into groups of 16 genes, dense ones into groups of 8
     const bool sparse = nnz < 6 * G;
     const int32_t words = (int32_t)(((int64_t)num_attrs * (sparse ? 16 : 8) + 127) / 128 * 4);  // bitmap words per warp (16-byte units)
-    const size_t bitmaps = (size_t)words * (kThreads / 32) * sizeof(uint32_t);
+    const size_t bitmaps = (size_t)(words + 8) * (kThreads / 32) * sizeof(uint32_t);
     const char *force = getenv("GCRF_FEATURES_SIMPLE");  // A/B and tests: 1 = gene by gene, 2 = table never / 3 = always in shared memory
     if (words == 0 || num_attrs >= 0xFFFF || bitmaps > 96 * 1024 || (force && force[0] == '1')) {  // bitmaps do not fit: the exact gene-by-gene kernel
         int64_t blocks = (G * 32 + kThreads - 1) / kThreads;
