@@ -363,6 +363,32 @@ def run_ours(args) -> None:
                "layout": "uint16 attribute ids, float32 marginals",
                "identical_to_float32_of_device_path": bool(numpy.array_equal(pout32.array, out.cpu().numpy().astype(numpy.float32)))}
 
+    # ---- the stage in front of the marginals: accession -> attribute id on device, same batch.
+    # Outside the headline's timed region; reported so that "accessions in, marginals out" has a measured number.
+    features_stage = None
+    if rank == 0 and engine.has_vocabulary:
+        nums = numpy.array([int(a[2:]) for a in weights.attrs], dtype=numpy.int32)
+        acc_host = numpy.where(batch.attr_idx >= 0, nums[numpy.clip(batch.attr_idx, 0, len(nums) - 1)], 99_999).astype(numpy.int32)
+        d_acc = torch.from_numpy(acc_host).to(dev)
+        d_ids = torch.empty(batch.nnz, dtype=torch.int32, device=dev)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f_ms = []
+        for it in range(3 + 8):
+            f0.record(stream)
+            engine.features_from_accessions_device(d_acc.data_ptr(), gp.data_ptr(), batch.G, batch.nnz, d_ids.data_ptr())
+            f1.record(stream)
+            torch.cuda.synchronize(dev)
+            if it >= 3:
+                f_ms.append(f0.elapsed_time(f1))
+        f_ms_avg = sum(f_ms) / len(f_ms)
+        f_bytes = 8 * batch.nnz + 4 * (batch.G + 1)  # accession in, id out, row pointers
+        features_stage = {"kernel": "gcrf::features_kernel<int,8,8,512,true>", "kernel_ms_avg": f_ms_avg,
+                          "rows": int(batch.nnz), "algorithmic_bytes_per_launch": int(f_bytes),
+                          "achieved_gbs": f_bytes / (f_ms_avg * 1e-3) / 1e9,
+                          "ids_equal_packer": bool(torch.equal(d_ids, ai)),
+                          "genes_per_s_features_plus_marginals": batch.G / ((f_ms_avg + kernel_ms_avg) * 1e-3)}
+        del d_acc, d_ids
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -398,6 +424,7 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "bit_identical_to_device_path": e2e_equal},
             "e2e_compact": compact,
+            "features_stage": features_stage,
             "gpu_launches": launches,
             "clocks": clocks,
             "parity_max_abs_err_vs_oracle": parity,

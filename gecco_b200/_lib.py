@@ -395,6 +395,12 @@ class CRFEngine:
         _check(self._lib, self._lib.gcrf_marginals_windowed(
             self._handle, contig_ptr, gene_ptr, attr_idx, C, G, nnz, int(window), int(step), int(bool(pad)), out, flags))
 
+    def features_from_accessions_device(self, accession: int, gene_ptr: int, G: int, nnz: int, out: int, *,
+                                        ptr64: bool = False) -> None:
+        """``gcrf_features_from_accessions`` on device-resident arrays (raw device addresses); returns without syncing."""
+        flags = GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_PTR64 if ptr64 else 0)
+        _check(self._lib, self._lib.gcrf_features_from_accessions(self._handle, accession, gene_ptr, G, nnz, out, flags))
+
     def marginals_chain_device(self, contig_ptr: int, gene_ptr: int, attr_idx: int, C: int, G: int, nnz: int,
                                out: int, *, f32: bool = False, ptr64: bool = False) -> None:
         flags = GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_OUT_F32 if f32 else 0) | (GCRF_FLAG_PTR64 if ptr64 else 0)
