@@ -22,7 +22,12 @@
 //     result tables (tests/test_cli/data/BGC0001866.*.tsv, diffed by the Galaxy tool test) contain.
 #include "../../include/gecco_crf_b200.h"
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <charconv>
 #include <chrono>
 #include <cmath>
@@ -253,59 +258,63 @@ void append_repr(std::string &out, double x) {
         out += x < 0 ? "-inf" : "inf";
         return;
     }
-    char buf[64];
-    auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
-    sv s(buf, (size_t)(r.ptr - buf));
-    if (s.front() == '-') {
-        out += '-';
-        s.remove_prefix(1);
-    }
-    const size_t epos = s.find('e');
-    sv mant = s.substr(0, epos);
-    int exp10 = 0;
-    {
-        sv e = s.substr(epos + 1);
-        const bool neg = e.front() == '-';
-        if (e.front() == '-' || e.front() == '+') e.remove_prefix(1);
-        std::from_chars(e.data(), e.data() + e.size(), exp10);
-        if (neg) exp10 = -exp10;
-    }
-    std::string digits;
-    for (char c : mant)
-        if (c != '.') digits += c;
     if (x == 0.0) {
-        out += "0.0";
+        out += std::signbit(x) ? "-0.0" : "0.0";
         return;
     }
+    // shortest round-trip digits in scientific form: [-]d[.ddd]e[+-]XX
+    char sci[40];
+    const char *end = std::to_chars(sci, sci + sizeof(sci), x, std::chars_format::scientific).ptr;
+    const char *p = sci;
+    char res[48];  // the laid-out number: at most sign + "0.000" + 17 digits, or 17 digits + '.' + "e-308"
+    char *o = res;
+    if (*p == '-') *o++ = *p++;
+    char digits[20];
+    int nd = 0;
+    for (; *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    ++p;  // 'e'
+    const bool eneg = *p == '-';
+    ++p;  // sign (to_chars always writes one)
+    int a = 0;
+    for (; p < end; ++p) a = a * 10 + (*p - '0');
+    const int exp10 = eneg ? -a : a;
     if (exp10 >= -4 && exp10 < 16) {
         if (exp10 < 0) {
-            out += "0.";
-            out.append((size_t)(-exp10 - 1), '0');
-            out += digits;
+            *o++ = '0';
+            *o++ = '.';
+            for (int k = 0; k < -exp10 - 1; ++k) *o++ = '0';
+            memcpy(o, digits, (size_t)nd);
+            o += nd;
         } else {
-            const size_t ip = (size_t)exp10 + 1;  // digits in front of the point
-            if (digits.size() <= ip) {
-                out += digits;
-                out.append(ip - digits.size(), '0');
-                out += ".0";
+            const int ip = exp10 + 1;  // digits in front of the point
+            if (nd <= ip) {
+                memcpy(o, digits, (size_t)nd);
+                o += nd;
+                for (int k = nd; k < ip; ++k) *o++ = '0';
+                *o++ = '.';
+                *o++ = '0';
             } else {
-                out.append(digits, 0, ip);
-                out += '.';
-                out.append(digits, ip, std::string::npos);
+                memcpy(o, digits, (size_t)ip);
+                o += ip;
+                *o++ = '.';
+                memcpy(o, digits + ip, (size_t)(nd - ip));
+                o += nd - ip;
             }
         }
     } else {
-        out += digits[0];
-        if (digits.size() > 1) {
-            out += '.';
-            out.append(digits, 1, std::string::npos);
+        *o++ = digits[0];
+        if (nd > 1) {
+            *o++ = '.';
+            memcpy(o, digits + 1, (size_t)(nd - 1));
+            o += nd - 1;
         }
-        out += 'e';
-        out += exp10 < 0 ? '-' : '+';
-        const int a = exp10 < 0 ? -exp10 : exp10;
-        if (a < 10) out += '0';
-        out += std::to_string(a);
+        *o++ = 'e';
+        *o++ = eneg ? '-' : '+';
+        if (a < 10) *o++ = '0';
+        o = std::to_chars(o, res + sizeof(res), a).ptr;
     }
+    out.append(res, (size_t)(o - res));
 }
 
 void append_int(std::string &out, int64_t v) {
@@ -370,19 +379,42 @@ int tfail(int code, const char *fmt, ...) {
     return code;
 }
 
+int default_threads();
+
+// The whole file into one malloc'd buffer; files of more than 16 MB are read by several threads (pread into disjoint
+// slices: the copies out of the page cache and the first touch of the buffer's pages run in parallel).
 int read_file(const char *path, FileBuffer *out) {
-    FILE *f = fopen(path, "rb");
-    if (!f) return tfail(GCRF_EINVAL, "cannot open %s", path);
-    fseek(f, 0, SEEK_END);
-    const long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (!out->allocate(n > 0 ? (size_t)n : 0)) {
-        fclose(f);
-        return tfail(GCRF_ENOMEM, "out of host memory reading %s", path);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return tfail(GCRF_EINVAL, "cannot open %s", path);
+    const off_t n = lseek(fd, 0, SEEK_END);
+    if (n < 0 || !out->allocate((size_t)(n > 0 ? n : 0))) {
+        close(fd);
+        return n < 0 ? tfail(GCRF_EINVAL, "cannot read %s", path) : tfail(GCRF_ENOMEM, "out of host memory reading %s", path);
     }
-    const size_t got = n > 0 ? fread(out->data, 1, (size_t)n, f) : 0;
-    fclose(f);
-    if (got != out->size) return tfail(GCRF_EINVAL, "short read on %s", path);
+    const size_t size = out->size;
+    auto slice = [&](size_t b, size_t e) {
+        while (b < e) {
+            const ssize_t got = pread(fd, out->data + b, e - b, (off_t)b);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) return false;
+            b += (size_t)got;
+        }
+        return true;
+    };
+    const int nt = (int)std::min<size_t>((size_t)default_threads(), size >> 24);
+    std::atomic<bool> ok{true};
+    if (nt <= 1) {
+        ok = slice(0, size);
+    } else {
+        std::vector<std::thread> pool;
+        for (int k = 0; k < nt; ++k)
+            pool.emplace_back([&, k] {
+                if (!slice(size * k / nt, size * (k + 1) / nt)) ok.store(false);
+            });
+        for (auto &th : pool) th.join();
+    }
+    close(fd);
+    if (!ok.load()) return tfail(GCRF_EINVAL, "short read on %s", path);
     return GCRF_OK;
 }
 
@@ -717,27 +749,58 @@ int write_all(const char *path, const std::string &text) {
 // threads into their own strings and written in order.
 template <typename Emit>
 int write_by_genes(const char *path, const std::string &header, size_t G, size_t bytes_per_gene, Emit &&emit) {
-    const int nt = (int)std::min<size_t>((size_t)default_threads(), std::max<size_t>(1, G / 20000));
-    std::vector<std::string> parts((size_t)nt);
-    auto work = [&](int k) {
-        std::string &out = parts[(size_t)k];
-        const size_t g0 = G * k / nt, g1 = G * (k + 1) / nt;
-        out.reserve((g1 - g0) * bytes_per_gene + 64);
-        for (size_t g = g0; g < g1; ++g) emit(out, g);
+    // Genes are cut into chunks handed out in order; a thread formats its chunk into a buffer it reuses (no fresh pages
+    // per chunk), learns its file offset from the chunk in front (offset + size, published as soon as that chunk is
+    // formatted) and writes with pwrite, so formatting and the copies into the page cache both run in parallel.
+    PhaseTimer timer;
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return tfail(GCRF_EINVAL, "cannot open %s for writing", path);
+    auto put = [fd](const char *data, size_t n, int64_t at) {
+        while (n) {
+            const ssize_t w = pwrite(fd, data, n, (off_t)at);
+            if (w < 0) {
+                if (errno == EINTR) continue;
+                return false;
+            }
+            data += w;
+            n -= (size_t)w;
+            at += w;
+        }
+        return true;
+    };
+    std::atomic<bool> ok{put(header.data(), header.size(), 0)};
+    const size_t chunk_genes = std::max<size_t>(256, std::min<size_t>(8192, (1u << 20) / std::max<size_t>(1, bytes_per_gene)));
+    const size_t nchunks = (G + chunk_genes - 1) / chunk_genes;
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)default_threads(), nchunks / 2));
+    std::vector<std::atomic<int64_t>> chunk_end(nchunks);
+    for (auto &e : chunk_end) e.store(-1, std::memory_order_relaxed);
+    std::atomic<size_t> next_chunk{0};
+    auto work = [&]() {
+        std::string out;
+        out.reserve(chunk_genes * bytes_per_gene + 4096);
+        for (;;) {
+            const size_t i = next_chunk.fetch_add(1, std::memory_order_relaxed);
+            if (i >= nchunks) break;
+            out.clear();
+            const size_t g1 = std::min(G, (i + 1) * chunk_genes);
+            for (size_t g = i * chunk_genes; g < g1; ++g) emit(out, g);
+            int64_t at = (int64_t)header.size();
+            if (i > 0)
+                while ((at = chunk_end[i - 1].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+            chunk_end[i].store(at + (int64_t)out.size(), std::memory_order_release);
+            if (!put(out.data(), out.size(), at)) ok.store(false);
+        }
     };
     if (nt <= 1) {
-        work(0);
+        work();
     } else {
         std::vector<std::thread> pool;
-        for (int k = 0; k < nt; ++k) pool.emplace_back(work, k);
+        for (int k = 0; k < nt; ++k) pool.emplace_back(work);
         for (auto &th : pool) th.join();
     }
-    FILE *f = fopen(path, "wb");
-    if (!f) return tfail(GCRF_EINVAL, "cannot open %s for writing", path);
-    bool ok = fwrite(header.data(), 1, header.size(), f) == header.size();
-    for (const std::string &part : parts) ok = ok && fwrite(part.data(), 1, part.size(), f) == part.size();
-    ok = (fclose(f) == 0) && ok;
-    if (!ok) return tfail(GCRF_EINVAL, "short write on %s", path);
+    const bool closed = close(fd) == 0;
+    timer.mark("format + write rows");
+    if (!ok.load() || !closed) return tfail(GCRF_EINVAL, "short write on %s", path);
     return GCRF_OK;
 }
 
