@@ -110,7 +110,7 @@ __device__ __forceinline__ void store_rows(int32_t *out_p, const uint32_t (&id)[
 // words through L1 costs one wavefront per distinct line — 32 cycles of the SM's load pipe per 32 rows — while the
 // same gather from shared memory costs its bank conflicts (~3.5 wavefronts).
 template <typename PtrT, int GG, int U, int THREADS, bool SLUT>
-__global__ void __launch_bounds__(THREADS, SLUT ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, SLUT ? 2 : GG == 32 ? 5 : 1)
 features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ gene_ptr, int64_t G,
                 const int32_t *__restrict__ lut, int32_t lut_size, int32_t words, int32_t *__restrict__ out) {
     constexpr unsigned kFull = 0xffffffffu;
@@ -120,7 +120,11 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
     static_assert(GG == 8 || GG == 16 || GG == 32, "group sizes with a whole number of ids per word");
     // Dense groups wipe their bitmap with 16-byte stores (6 per lane for 2,659 attributes) — fewer instructions than
     // every row clearing its own word; sparse groups (a few rows against 5 KB of bitmap) clear what they set.
-    constexpr bool kOwnClear = GG != 8;
+    constexpr bool kOwnClear = GG == 16;
+    // GG = 32 (sparse tables: the whole 32-gene block is one group, usually one batch): 64 bits per gene slot, keyed by
+    // id & 63 — 256 bytes of bitmap per warp instead of 10 KB.  Two different ids of a gene that share a bit only send the
+    // batch through the exact comparison; with the one or two rows a gene has there, that is a few percent of the batches.
+    constexpr bool kHashed = GG == 32;
     extern __shared__ __align__(16) uint32_t sBitmap[];  // `words` (a multiple of 4) per warp, then the uint16 table (SLUT)
     const int lane = threadIdx.x & 31;
     static_assert(U <= 8, "eight start-mask words per warp");
@@ -143,6 +147,13 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
     if (base >= G) return;
     int64_t p_lo = (int64_t)__ldg(gene_ptr + min(base + lane, G));  // first row of gene base + lane
     int64_t p_end = (int64_t)__ldg(gene_ptr + min(base + 32, G));   // end of the block's rows
+    // ... and of the warp's next block: pointers run two blocks ahead, so that the next block's first accession loads
+    // can be issued from this block's last batch without waiting for them
+    int64_t p_lo1 = 0, p_end1 = 0;
+    if (base + stride < G) {
+        p_lo1 = (int64_t)__ldg(gene_ptr + min(base + stride + lane, G));
+        p_end1 = (int64_t)__ldg(gene_ptr + min(base + stride + 32, G));
+    }
     int32_t acc_n[U];       // accessions of the pending batch
     int pend_off = -1, pend_r1 = -1;  // ... which covers rows [pend_off, pend_r1) of the block it belongs to
     for (; base < G; base += stride) {
@@ -151,9 +162,11 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
         const int64_t block_rows = p_end - P0;
         const int rel = (int)min(p_lo - P0, (int64_t)0x7fffffff);  // lanes past the last gene hold the block's end
         const int64_t next = base + stride;
-        if (next < G) {
-            p_lo = (int64_t)__ldg(gene_ptr + min(next + lane, G));
-            p_end = (int64_t)__ldg(gene_ptr + min(next + 32, G));
+        p_lo = p_lo1;  // from here on: the next block's pointers
+        p_end = p_end1;
+        if (next + stride < G) {
+            p_lo1 = (int64_t)__ldg(gene_ptr + min(next + stride + lane, G));
+            p_end1 = (int64_t)__ldg(gene_ptr + min(next + stride + 32, G));
         }
         if (block_rows > 0x7fffffff) {  // offsets would not fit 32 bits: gene by gene
             for (int g = 0; g < ng; ++g)
@@ -233,8 +246,9 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
                     const uint32_t starts = load_shared_u32(mask_addr + u * 4);
                     const int g = slot + __popc(starts & lanemask_le);
                     slot += __popc(starts);
-                    const uint32_t bit = 1u << ((id[u] & (kIdsPerWord - 1)) * GG + g);
-                    seen |= atom_or_shared_if_id(bm_addr + ((id[u] >> kIdShift) << 2), bit, id[u]) & bit;
+                    const uint32_t bit = kHashed ? 1u << (id[u] & 31) : 1u << ((id[u] & (kIdsPerWord - 1)) * GG + g);
+                    const uint32_t word = kHashed ? (uint32_t)(g * 2) + ((id[u] >> 5) & 1u) : id[u] >> kIdShift;
+                    seen |= atom_or_shared_if_id(bm_addr + (word << 2), bit, id[u]) & bit;
                 }
                 if (__any_sync(kFull, seen != 0)) {
 #pragma unroll
@@ -340,18 +354,22 @@ cudaError_t launch_features_bitmap(const int32_t *accession, const PtrT *gene_pt
 template <typename PtrT>
 cudaError_t launch_features_t(const int32_t *accession, const PtrT *gene_ptr, int64_t G, int64_t nnz, const int32_t *lut,
                               int32_t lut_size, int32_t num_attrs, int32_t *out, int num_sms, cudaStream_t stream) {
-    // sparse tables (real annotation: 1.4 rows per gene) are cut into groups of 16 genes, dense ones into groups of 8
+    // sparse tables (real annotation: 1.4 rows per gene) take the 32-gene block as one group with hashed 64-bit bitmaps
+    // (4 = exact bitmaps over groups of 16 genes instead), dense ones groups of 8 genes with exact bitmaps
     const bool sparse = nnz < 6 * G;
-    const int32_t words = (int32_t)(((int64_t)num_attrs * (sparse ? 16 : 8) + 127) / 128 * 4);  // bitmap words per warp (16-byte units)
+    const char *force = getenv("GCRF_FEATURES_SIMPLE");  // A/B and tests
+    const bool sparse_exact = sparse && force && force[0] == '4';
+    const int32_t words = sparse && !sparse_exact ? 64 : (int32_t)(((int64_t)num_attrs * (sparse ? 16 : 8) + 127) / 128 * 4);  // bitmap words per warp (16-byte units)
     const size_t bitmaps = (size_t)(words + 8) * (kThreads / 32) * sizeof(uint32_t);
-    const char *force = getenv("GCRF_FEATURES_SIMPLE");  // A/B and tests: 1 = gene by gene, 2 = table never / 3 = always in shared memory
+    // 1 = gene by gene, 2 = table never / 3 = always in shared memory
     if (words == 0 || num_attrs >= 0xFFFF || bitmaps > 96 * 1024 || (force && force[0] == '1')) {  // bitmaps do not fit: the exact gene-by-gene kernel
         int64_t blocks = (G * 32 + kThreads - 1) / kThreads;
         if (blocks > (int64_t)num_sms * 16) blocks = (int64_t)num_sms * 16;
         features_simple_kernel<PtrT><<<(int)blocks, kThreads, 0, stream>>>(accession, gene_ptr, G, lut, lut_size, out);
         return cudaGetLastError();
     }
-    if (sparse) return launch_features_bitmap<PtrT, 16, 2, kThreads, false>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
+    if (sparse_exact) return launch_features_bitmap<PtrT, 16, 2, kThreads, false>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
+    if (sparse) return launch_features_bitmap<PtrT, 32, 2, kThreads, false>(accession, gene_ptr, G, lut, lut_size, words, out, num_sms, stream);
     // dense tables with enough rows to pay for staging the table (82 KB of L2 reads per CTA): two 512-thread CTAs per SM
     const size_t staged = 2 * bitmaps + (size_t)lut_size * 2 + 16;
     if (staged <= 110 * 1024 && !(force && force[0] == '2') &&

@@ -492,7 +492,7 @@ def test_feature_extraction_fuzz(engine, weights, mean_rows, monkeypatch):
         acc[rng.random(n) < 0.01] = -7
         acc[rng.random(n) < 0.01] = len(lut) + 11
         want = _features_restated(acc, gene_ptr, lut)
-        for simple in ("0", "1", "2", "3"):  # default choice, gene by gene, table in global / in shared memory
+        for simple in ("0", "1", "2", "3", "4"):  # default, gene by gene, table in global / shared memory, exact sparse bitmaps
             monkeypatch.setenv("GCRF_FEATURES_SIMPLE", simple)
             for ptr64 in (False, True):
                 got = engine.features_from_accessions(acc, gene_ptr, ptr64=ptr64)
