@@ -270,6 +270,27 @@ def test_float_layout_is_python_repr(tmp_path):
     assert got == [repr(v) for v in values]
 
 
+def test_writers_are_independent_of_threads_and_chunks(weights, tmp_path, monkeypatch):
+    """~30k genes / ~60k domain rows: the writers cut the genes into chunks that threads format and place with pwrite at
+    chained offsets; one thread or eight, the files are the same bytes, and every row is the restatement's row."""
+    names = list(weights.attrs[:300]) + ["PF99999"]
+    gtext, ftexts = synthetic_tables(5, 300, 100, names)
+    genes = tables_oracle.load(gtext, ftexts)
+    rng = numpy.random.default_rng(0)
+    outs = {}
+    for threads in ("1", "8", "3"):
+        monkeypatch.setenv("GCRF_TABLE_THREADS", threads)
+        with native(gtext, ftexts) as tables:
+            packed = tables.pack(weights.attrs)
+            prob = rng.random(packed.G) if threads == "1" else prob
+            tables.write_genes(tmp_path / f"g{threads}.tsv", prob)
+            tables.write_features(tmp_path / f"f{threads}.tsv", prob)
+        outs[threads] = ((tmp_path / f"g{threads}.tsv").read_bytes(), (tmp_path / f"f{threads}.tsv").read_bytes())
+    assert outs["1"] == outs["8"] == outs["3"]
+    assert outs["1"][0].decode() == tables_oracle.dump_genes(genes, prob.tolist())
+    assert outs["1"][1].decode() == tables_oracle.dump_features(genes, prob.tolist())
+
+
 @pytest.mark.skipif(not (REFERENCE / "mibig-2.0.proG2.features.tsv").exists(), reason="reference checkout not mounted")
 def test_reference_mibig_tables(weights, mibig):
     """The reference's own 15,158-gene / 123,031-row training tables: same CSR as the golden arrays."""
