@@ -23,6 +23,7 @@ GCRF_FLAG_PTR64 = 0x4
 GCRF_FLAG_PROB_F32 = 0x8
 GCRF_FLAG_RESET_PER_CONTIG = 0x10
 GCRF_FLAG_IDX_U16 = 0x20
+GCRF_FLAG_ACCESSIONS = 0x40
 
 # every symbol include/gecco_crf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTED_SYMBOLS = (
@@ -56,6 +57,7 @@ EXPORTED_SYMBOLS = (
     "gcrf_table_annotated",
     "gcrf_table_gene_coordinates",
     "gcrf_table_pack",
+    "gcrf_table_pack_accessions",
     "gcrf_table_row_gene",
     "gcrf_table_gene_probabilities",
     "gcrf_table_write_genes",
@@ -157,6 +159,9 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_table_pack.restype = ctypes.c_int
     lib.gcrf_table_pack.argtypes = [vp, ctypes.POINTER(cp), i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                     ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.gcrf_table_pack_accessions.restype = ctypes.c_int
+    lib.gcrf_table_pack_accessions.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                               ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.gcrf_table_row_gene.restype = vp
     lib.gcrf_table_row_gene.argtypes = [vp]
     lib.gcrf_table_gene_probabilities.restype = ctypes.c_int
@@ -294,9 +299,15 @@ class CRFEngine:
     # ------------------------------------------------------------------ host-pointer calls
     def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window: Optional[int] = None,
                            step: Optional[int] = None, pad: bool = True, out: Optional[numpy.ndarray] = None,
-                           f32: bool = False) -> numpy.ndarray:
-        """Per-gene cluster probability (``gcrf_marginals_windowed``, host buffers, blocking)."""
+                           f32: bool = False, accessions: bool = False) -> numpy.ndarray:
+        """Per-gene cluster probability (``gcrf_marginals_windowed``, host buffers, blocking).  ``accessions``:
+        ``attr_idx`` holds integer domain accessions, one row per domain in domain-start order; they are mapped to
+        attribute ids and de-duplicated per gene on the device (``GCRF_FLAG_ACCESSIONS``)."""
         contig_ptr, gene_ptr, attr_idx, flags = self._host_csr(contig_ptr, gene_ptr, attr_idx)
+        if accessions:
+            if not self.has_vocabulary:
+                raise ValueError("the model's attributes are not Pfam-style accessions; pack attribute ids on the host")
+            flags |= GCRF_FLAG_ACCESSIONS
         C, G, nnz = len(contig_ptr) - 1, len(gene_ptr) - 1, len(attr_idx)
         dtype = numpy.float32 if f32 else numpy.float64
         if out is None:
@@ -313,9 +324,11 @@ class CRFEngine:
         return out
 
     def marginals_chain(self, contig_ptr, gene_ptr, attr_idx, *, out: Optional[numpy.ndarray] = None,
-                        f32: bool = False) -> numpy.ndarray:
+                        f32: bool = False, accessions: bool = False) -> numpy.ndarray:
         """Whole-contig marginals (``gcrf_marginals_chain``): one chain per contig, no windows."""
         contig_ptr, gene_ptr, attr_idx, flags = self._host_csr(contig_ptr, gene_ptr, attr_idx)
+        if accessions:
+            flags |= GCRF_FLAG_ACCESSIONS
         C, G, nnz = len(contig_ptr) - 1, len(gene_ptr) - 1, len(attr_idx)
         dtype = numpy.float32 if f32 else numpy.float64
         if out is None:

@@ -134,8 +134,9 @@ class ClusterCRF(object):
         """Bulk entry point: per-row cluster probability of an already packed batch (NaN = skipped contig)."""
         if self.model is None:
             raise NotFittedError("This ClusterCRF instance is not fitted yet.")
+        extra = {"accessions": True} if getattr(packed, "accessions", False) else {}
         return self._get_engine().marginals_windowed(packed.contig_ptr, packed.gene_ptr, packed.attr_idx,
-                                                     window=self.window_size, step=self.window_step, pad=pad)
+                                                     window=self.window_size, step=self.window_step, pad=pad, **extra)
 
     # ------------------------------------------------------------------ the hot path
     def predict_probabilities(self, genes: Iterable[Any], *, pad: bool = True,

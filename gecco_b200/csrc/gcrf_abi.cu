@@ -86,6 +86,7 @@ struct gcrf_model {
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
+    DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
 };
 
 namespace {
@@ -125,8 +126,12 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
                 int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags, Batch *b, bool defer_copies = false) {
     const int32_t *attr_idx = static_cast<const int32_t *>(attr_idx_any);
     const bool idx16 = (flags & GCRF_FLAG_IDX_U16) != 0;
+    const bool accessions = (flags & GCRF_FLAG_ACCESSIONS) != 0;
     if (idx16 && m && m->A >= 0xFFFF) return fail(GCRF_EINVAL, "GCRF_FLAG_IDX_U16 needs a model with fewer than 65535 attributes");
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (accessions && idx16) return fail(GCRF_EINVAL, "GCRF_FLAG_ACCESSIONS and GCRF_FLAG_IDX_U16 exclude each other");
+    if (accessions && !m->d_lut && m->A > 0) return fail(GCRF_EINVAL, "gcrf_model_set_vocabulary has not been called");
+    if (accessions && defer_copies) return fail(GCRF_EINVAL, "GCRF_FLAG_ACCESSIONS cannot be combined with sliced copies");
     if (C < 0 || G < 0 || nnz < 0) return fail(GCRF_EINVAL, "negative size");
     if (G > 0x7fffffff - 1024) return fail(GCRF_EINVAL, "G must fit in int32 (shard the batch)");
     if ((C == 0) != (G == 0)) return fail(GCRF_EINVAL, "C and G must both be zero or both be positive");
@@ -150,6 +155,15 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
             cudaError_t werr = gcrf::launch_widen_u16(static_cast<const uint16_t *>(attr_idx_any), static_cast<int32_t *>(m->b_attr.ptr),
                                                       nnz, m->num_sms, m->stream, &m->launches);
             if (werr != cudaSuccess) return fail_cuda(werr, "launch_widen_u16");
+            attr_idx = static_cast<const int32_t *>(m->b_attr.ptr);
+        }
+        if (accessions && nnz > 0) {  // accession -> attribute id, repeats inside a gene dropped, into the library's buffer
+            GCRF_CUDA(m->b_attr.reserve((size_t)nnz * 4 + 64));
+            cudaError_t ferr = gcrf::launch_features(attr_idx, ptr64 ? nullptr : static_cast<const int32_t *>(gene_ptr),
+                                                     ptr64 ? static_cast<const int64_t *>(gene_ptr) : nullptr, G, nnz, m->d_lut,
+                                                     m->lut_size, m->A, static_cast<int32_t *>(m->b_attr.ptr), m->num_sms,
+                                                     m->stream, &m->launches);
+            if (ferr != cudaSuccess) return fail_cuda(ferr, "launch_features");
             attr_idx = static_cast<const int32_t *>(m->b_attr.ptr);
         }
         b->csr.contig_ptr = contig_ptr;
@@ -177,6 +191,15 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
             cudaError_t werr = gcrf::launch_widen_u16(static_cast<const uint16_t *>(m->b_idx16.ptr), static_cast<int32_t *>(m->b_attr.ptr),
                                                       nnz, m->num_sms, m->stream, &m->launches);
             if (werr != cudaSuccess) return fail_cuda(werr, "launch_widen_u16");
+        } else if (nnz > 0 && accessions) {
+            GCRF_CUDA(m->b_acc.reserve((size_t)nnz * 4 + 16));
+            GCRF_CUDA(cudaMemcpyAsync(m->b_acc.ptr, attr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
+            cudaError_t ferr = gcrf::launch_features(static_cast<const int32_t *>(m->b_acc.ptr),
+                                                     ptr64 ? nullptr : static_cast<const int32_t *>(m->b_gene.ptr),
+                                                     ptr64 ? static_cast<const int64_t *>(m->b_gene.ptr) : nullptr, G, nnz, m->d_lut,
+                                                     m->lut_size, m->A, static_cast<int32_t *>(m->b_attr.ptr), m->num_sms,
+                                                     m->stream, &m->launches);
+            if (ferr != cudaSuccess) return fail_cuda(ferr, "launch_features");
         } else if (nnz > 0) {
             GCRF_CUDA(cudaMemcpyAsync(m->b_attr.ptr, attr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
         }
@@ -329,6 +352,7 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_ann.release();
     m->b_seg.release();
     m->b_idx16.release();
+    m->b_acc.release();
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
     if (m->d_table_fx) cudaFree(m->d_table_fx);
@@ -473,7 +497,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     const bool prof = prof_env && prof_env[0] == '1';
     // host buffers, PCIe-bound size: overlap the two copy directions over contig-aligned slices
     int slices = 1;
-    if (!(flags & (GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_IDX_U16)) && !m->timing && !prof && C >= 2) {
+    if (!(flags & (GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_IDX_U16 | GCRF_FLAG_ACCESSIONS)) && !m->timing && !prof && C >= 2) {
         const double bytes = 4.0 * (double)nnz + 12.0 * (double)G;
         const char *env = getenv("GCRF_HOST_SLICES");  // tuning / A-B: 1 turns the overlap off
         // Off unless asked for: on the PCIe Gen5 hosts measured (config 2, 207 MB in / 16 MB out) the D2H overlap

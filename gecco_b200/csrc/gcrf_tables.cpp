@@ -941,6 +941,82 @@ int gcrf_table_pack(gcrf_table *t, const char *const *attr_names, int32_t A, int
     return GCRF_OK;
 }
 
+int gcrf_table_pack_accessions(gcrf_table *t, int32_t feature_type, const int32_t **contig_ptr, const int32_t **row_ptr,
+                               const int32_t **accession, int64_t *rows, int64_t *nnz) {
+    if (!t) return tfail(GCRF_EINVAL, "table is NULL");
+    if (feature_type != 0 && feature_type != 1) return tfail(GCRF_EINVAL, "invalid feature type: %d", feature_type);
+    try {
+        const size_t G = t->genes.size(), C = t->contig_ids.size(), D = t->domains.size();
+        if (D > 0x7fffff00u || G + D > 0x7fffff00u) return tfail(GCRF_EINVAL, "table too large for int32 row pointers; shard it");
+        // "PF" + digits -> the number; anything else is not in a Pfam-only vocabulary
+        t->attr_idx.resize(D);
+        auto numbers = [&](size_t d0, size_t d1) {
+            for (size_t d = d0; d < d1; ++d) {
+                const sv name = t->domains[d].name;
+                int32_t v = -1;
+                if (name.size() > 2 && name.size() <= 11 && name[0] == 'P' && name[1] == 'F') {
+                    int64_t x = 0;
+                    bool digits = true;
+                    for (size_t i = 2; i < name.size(); ++i) {
+                        if (name[i] < '0' || name[i] > '9') {
+                            digits = false;
+                            break;
+                        }
+                        x = x * 10 + (name[i] - '0');
+                    }
+                    if (digits && x <= 0x7fffffff) v = (int32_t)x;
+                }
+                t->attr_idx[d] = v;
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)default_threads(), std::max<size_t>(1, D / 100000));
+        if (nt <= 1) {
+            numbers(0, D);
+        } else {
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nt; ++k) pool.emplace_back(numbers, D * k / nt, D * (k + 1) / nt);
+            for (auto &th : pool) th.join();
+        }
+        t->row_contig_ptr.resize(C + 1);
+        if (feature_type == 0) {  // one row per gene: the domain pointers are the row pointers
+            t->row_ptr.resize(G + 1);
+            for (size_t g = 0; g <= G; ++g) t->row_ptr[g] = (int32_t)t->dom_ptr[g];
+            t->row_gene.resize(G);
+            std::iota(t->row_gene.begin(), t->row_gene.end(), 0);
+            for (size_t c = 0; c <= C; ++c) t->row_contig_ptr[c] = t->contig_ptr[c];
+        } else {  // one row per domain, one empty row per domain-less gene (features.py:44-46)
+            t->row_ptr.assign(1, 0);
+            t->row_gene.clear();
+            t->row_ptr.reserve(G + D + 1);
+            t->row_gene.reserve(G + D);
+            size_t c = 0;
+            for (size_t g = 0; g < G; ++g) {
+                while (c < C && (int64_t)g == t->contig_ptr[c]) t->row_contig_ptr[c++] = (int32_t)(t->row_ptr.size() - 1);
+                const int64_t b = t->dom_ptr[g], e = t->dom_ptr[g + 1];
+                for (int64_t k = b; k < e; ++k) {
+                    t->row_ptr.push_back((int32_t)(k + 1));
+                    t->row_gene.push_back((int32_t)g);
+                }
+                if (b == e) {
+                    t->row_ptr.push_back((int32_t)b);
+                    t->row_gene.push_back((int32_t)g);
+                }
+            }
+            t->row_contig_ptr[C] = (int32_t)(t->row_ptr.size() - 1);
+        }
+        if (G == 0) t->row_contig_ptr.assign(1, 0);
+        t->packed_mode = feature_type;
+    } catch (const std::bad_alloc &) {
+        return tfail(GCRF_ENOMEM, "out of host memory");
+    }
+    if (contig_ptr) *contig_ptr = t->row_contig_ptr.data();
+    if (row_ptr) *row_ptr = t->row_ptr.data();
+    if (accession) *accession = t->attr_idx.data();
+    if (rows) *rows = (int64_t)t->row_ptr.size() - 1;
+    if (nnz) *nnz = (int64_t)t->attr_idx.size();
+    return GCRF_OK;
+}
+
 const int32_t *gcrf_table_row_gene(const gcrf_table *t) { return t && !t->row_gene.empty() ? t->row_gene.data() : nullptr; }
 
 int gcrf_table_gene_probabilities(const gcrf_table *t, const double *row_prob, double *average_p, double *max_p) {

@@ -29,6 +29,9 @@ class PackedGenes:
     contig_ids: List[Any] = field(default_factory=list)
     order: Optional[numpy.ndarray] = None  # packed position -> index in the caller's sequence
     gene_ids: List[Any] = field(default_factory=list)
+    # attr_idx holds integer domain accessions (every domain row, unknown names -1, repeats kept): feature extraction
+    # is left to the device (GCRF_FLAG_ACCESSIONS)
+    accessions: bool = False
 
     @property
     def C(self) -> int:

@@ -159,21 +159,29 @@ class FeatureTables:
         return start, end
 
     # ------------------------------------------------------------------ features
-    def pack(self, attrs: Sequence[str], feature_type: str = "protein") -> PackedGenes:
-        """CSR batch for the marginal kernels (views into the table: valid until the next ``pack`` / ``close``)."""
+    def pack(self, attrs: Optional[Sequence[str]], feature_type: str = "protein", *, accessions: bool = False) -> PackedGenes:
+        """CSR batch for the marginal kernels (views into the table: valid until the next ``pack`` / ``close``).
+
+        ``accessions=True`` (``gcrf_table_pack_accessions``): nothing is looked up or de-duplicated on the host; the
+        batch holds the Pfam number of every kept domain row and the device does the feature extraction
+        (``GCRF_FLAG_ACCESSIONS``; for models whose attributes are all ``PF`` + digits, ``attrs`` is not needed)."""
         if feature_type not in ("protein", "domain"):
             raise ValueError(f"invalid feature type: {feature_type!r}")
-        names = (ctypes.c_char_p * max(1, len(attrs)))(*[a.encode() for a in attrs])
         cp, rp, ai = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         rows, nnz = ctypes.c_int64(), ctypes.c_int64()
-        rc = self._lib.gcrf_table_pack(self._h, names, len(attrs), 0 if feature_type == "protein" else 1, ctypes.byref(cp),
-                                       ctypes.byref(rp), ctypes.byref(ai), ctypes.byref(rows), ctypes.byref(nnz))
+        if accessions:
+            rc = self._lib.gcrf_table_pack_accessions(self._h, 0 if feature_type == "protein" else 1, ctypes.byref(cp),
+                                                      ctypes.byref(rp), ctypes.byref(ai), ctypes.byref(rows), ctypes.byref(nnz))
+        else:
+            names = (ctypes.c_char_p * max(1, len(attrs)))(*[a.encode() for a in attrs])
+            rc = self._lib.gcrf_table_pack(self._h, names, len(attrs), 0 if feature_type == "protein" else 1, ctypes.byref(cp),
+                                           ctypes.byref(rp), ctypes.byref(ai), ctypes.byref(rows), ctypes.byref(nnz))
         if rc != 0:
             raise _table_error(self._lib, rc)
         C = self.contigs
         packed = PackedGenes(self._view(cp.value, C + 1, numpy.int32) if self.genes else numpy.zeros(1, dtype=numpy.int32),
                              self._view(rp.value, rows.value + 1, numpy.int32), self._view(ai.value, nnz.value, numpy.int32),
-                             contig_ids=self.contig_ids)
+                             contig_ids=self.contig_ids, accessions=accessions)
         self._packed, self.feature_type = packed, feature_type
         return packed
 
@@ -184,7 +192,10 @@ class FeatureTables:
 
     def predict(self, crf, *, pad: bool = True) -> numpy.ndarray:
         """Pack with the model's vocabulary and feature type, run the marginal kernels: one value per packed row."""
-        packed = self.pack(crf._weights.attrs, crf.feature_type)
+        # Pfam-only vocabularies (the shipped model): the table hands over raw accession numbers and the feature
+        # extraction runs on the device; GECCO_B200_HOST_FEATURES=1 keeps the host packer (A/B, other vocabularies)
+        on_device = os.environ.get("GECCO_B200_HOST_FEATURES", "0") != "1" and crf._get_engine().has_vocabulary
+        packed = self.pack(crf._weights.attrs, crf.feature_type, accessions=on_device)
         return crf.marginals(packed, pad=pad) if packed.G else numpy.zeros(0)
 
     # ------------------------------------------------------------------ results

@@ -60,6 +60,11 @@ typedef enum gcrf_status {
 #define GCRF_FLAG_PTR64       0x4u /* gene_ptr is int64_t[G+1] (nnz >= 2^31); contig_ptr stays int32 */
 #define GCRF_FLAG_IDX_U16     0x20u /* attr_idx is uint16_t[nnz] (0xFFFF = unknown attribute; models with fewer than
                                       65535 attributes): half the bytes over PCIe, widened on the device */
+#define GCRF_FLAG_ACCESSIONS  0x40u /* gcrf_marginals_*: attr_idx holds integer domain accessions (one row per domain in
+                                      domain-start order, e.g. 394 for PF00394), not attribute ids: they are mapped
+                                      through the vocabulary (gcrf_model_set_vocabulary) and de-duplicated per gene on
+                                      the device first — gcrf_features_from_accessions and the marginals in one call
+                                      (gecco/crf/features.py:13-35 + crf/__init__.py:253).  Not with GCRF_FLAG_IDX_U16 */
 #define GCRF_FLAG_PROB_F32    0x8u /* gcrf_segments: prob is float[G] instead of double[G] */
 #define GCRF_FLAG_RESET_PER_CONTIG 0x10u /* gcrf_segments: the in-cluster state starts at "out" in every
                                       contig, i.e. one ClusterRefiner.iter_clusters call per contig as
@@ -249,6 +254,15 @@ int gcrf_table_gene_coordinates(const gcrf_table *table, int64_t *start /* [G] o
 int gcrf_table_pack(gcrf_table *table, const char *const *attr_names, int32_t A, int32_t feature_type,
                     const int32_t **contig_ptr, const int32_t **row_ptr, const int32_t **attr_idx, int64_t *rows,
                     int64_t *nnz);
+/*
+ * The same batch with the feature extraction left to the device (GCRF_FLAG_ACCESSIONS): `accession` holds one entry
+ * per kept domain row — the number behind a "PF" prefix (PF00394 -> 394), -1 for any other name — in the table's
+ * domain order, nothing looked up or de-duplicated on the host (gecco/crf/features.py:13-35 then runs in
+ * gcrf::features_kernel).  Same feature types, ownership and row layout as gcrf_table_pack; for models whose
+ * attributes are all "PF" + digits (gcrf_model_set_vocabulary).
+ */
+int gcrf_table_pack_accessions(gcrf_table *table, int32_t feature_type, const int32_t **contig_ptr, const int32_t **row_ptr,
+                               const int32_t **accession, int64_t *rows, int64_t *nnz);
 const int32_t *gcrf_table_row_gene(const gcrf_table *table); /* [rows] gene of every packed row */
 
 /*

@@ -446,6 +446,27 @@ def test_feature_extraction_on_device(engine, mibig, weights):
     assert numpy.array_equal(numpy.bincount(gene_of[keep], minlength=len(dom_ptr) - 1), numpy.diff(packed.gene_ptr))
     p = engine.marginals_windowed(packed.contig_ptr, dom_ptr, ids)
     assert_close(p, mibig["ref_loop_prob"], what="device features + marginals vs reference loop")
+    # the same in ONE call (GCRF_FLAG_ACCESSIONS): accessions in, marginals out, host and device buffers
+    p1 = engine.marginals_windowed(packed.contig_ptr, dom_ptr, dom_pfam, accessions=True)
+    assert numpy.array_equal(p1, p)
+    assert numpy.array_equal(engine.marginals_chain(packed.contig_ptr, dom_ptr, dom_pfam, accessions=True),
+                             engine.marginals_chain(packed.contig_ptr, dom_ptr, ids))
+    import torch
+    from gecco_b200._lib import GCRF_FLAG_ACCESSIONS
+
+    dev = torch.device("cuda", engine.device)
+    with torch.cuda.device(dev):
+        cp = torch.from_numpy(numpy.ascontiguousarray(packed.contig_ptr, dtype=numpy.int32)).to(dev)
+        gp = torch.from_numpy(numpy.ascontiguousarray(dom_ptr, dtype=numpy.int32)).to(dev)
+        ac = torch.from_numpy(numpy.ascontiguousarray(dom_pfam, dtype=numpy.int32)).to(dev)
+        out = torch.empty(len(dom_ptr) - 1, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ac.data_ptr(), len(packed.contig_ptr) - 1, len(dom_ptr) - 1,
+                                         len(dom_pfam), out.data_ptr(), flags=GCRF_FLAG_ACCESSIONS)
+        engine.synchronize()
+        assert numpy.array_equal(out.cpu().numpy(), p)
+    with pytest.raises(Exception, match="exclude each other"):
+        engine.marginals_windowed(packed.contig_ptr, dom_ptr, dom_pfam.astype(numpy.uint16), accessions=True)
     # repeats and unknown accessions
     acc = numpy.array([109, 109, 99999, 5, 109, 5, 2801], dtype=numpy.int32)
     out = engine.features_from_accessions(acc, numpy.array([0, 5, 7], dtype=numpy.int32))
@@ -500,3 +521,39 @@ def test_feature_extraction_fuzz(engine, weights, mean_rows, monkeypatch):
         monkeypatch.setenv("GCRF_FEATURES_SIMPLE", "0")
         # a second call on the same handle: the kernels leave their bitmaps clean
         assert numpy.array_equal(engine.features_from_accessions(acc, gene_ptr), want)
+
+
+@pytest.mark.parametrize("feature_type", ["protein", "domain"])
+def test_table_path_with_feature_extraction_on_device(weights, mibig, feature_type, monkeypatch):
+    """FeatureTables.predict hands raw Pfam numbers to the device (GCRF_FLAG_ACCESSIONS) when the vocabulary allows:
+    same probabilities, bit for bit, as packing attribute ids on the host — on a synthetic table with repeated,
+    unknown and foreign domain names."""
+    import random
+
+    from gecco_b200.crf import ClusterCRF
+    from gecco_b200.tables import FeatureTables
+
+    rng = random.Random(5)
+    names = list(weights.attrs[:200]) + ["PF99999", "TIGR00001"]
+    glines, flines = ["sequence_id\tprotein_id\tstart\tend\tstrand"], [
+        "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end"]
+    for c in range(40):
+        pos = 1
+        for k in range(rng.randrange(1, 90)):
+            start, end = pos + 10, pos + 10 + 3 * rng.randrange(30, 300)
+            pos = end
+            head = f"c{c:03d}\tc{c:03d}_{k + 1}\t{start}\t{end}\t+"
+            glines.append(head)
+            for _ in range(rng.choice([0, 1, 1, 2, 5])):
+                ds = rng.randrange(1, 200)
+                flines.append(f"{head}\t{rng.choice(names)}\tPfam\t1e-20\t1e-22\t{ds}\t{ds + 50}")
+    crf = ClusterCRF.trained(None)
+    crf.feature_type = feature_type
+    with FeatureTables.parse(("\n".join(glines) + "\n").encode(), [("\n".join(flines) + "\n").encode()]) as tables:
+        monkeypatch.setenv("GECCO_B200_HOST_FEATURES", "1")
+        host = tables.predict(crf)
+        assert not tables._packed.accessions
+        monkeypatch.setenv("GECCO_B200_HOST_FEATURES", "0")
+        device = tables.predict(crf)
+        assert tables._packed.accessions
+    assert numpy.array_equal(host, device, equal_nan=True)

@@ -270,6 +270,37 @@ def test_float_layout_is_python_repr(tmp_path):
     assert got == [repr(v) for v in values]
 
 
+@pytest.mark.parametrize("feature_type", ["protein", "domain"])
+def test_accession_pack_is_the_id_pack_before_feature_extraction(weights, feature_type):
+    """gcrf_table_pack_accessions hands the device every kept domain row as a Pfam number; mapping those through the
+    vocabulary and keeping the first of equal names per row (features.py:13-35, what gcrf::features_kernel does) must
+    give the batch gcrf_table_pack builds on the host — same rows, same contigs, same row -> gene map."""
+    names = list(weights.attrs[:40]) + ["PF99999", "TIGR00001", "PFAM1", "PF", "PF12x"]
+    gtext, ftexts = synthetic_tables(23, 40, 30, names)
+    with native(gtext, ftexts) as tables:
+        ids = tables.pack(weights.attrs, feature_type)
+        want = (ids.contig_ptr.copy(), ids.gene_ptr.copy(), ids.attr_idx.copy(), tables.row_gene.copy())
+        acc = tables.pack(None, feature_type, accessions=True)
+        assert acc.accessions and not ids.accessions
+        assert numpy.array_equal(acc.contig_ptr, want[0])
+        assert numpy.array_equal(tables.row_gene, want[3])
+        assert acc.G == len(want[1]) - 1
+        number = {int(a[2:]): i for i, a in enumerate(weights.attrs)}
+        rows, ptr = [], [0]
+        for r in range(acc.G):
+            seen = []
+            for a in acc.attr_idx[acc.gene_ptr[r]:acc.gene_ptr[r + 1]].tolist():
+                if a in number and number[a] not in seen:
+                    seen.append(number[a])
+            rows.extend(seen)
+            ptr.append(len(rows))
+        assert ptr == want[1].tolist() and rows == want[2].tolist()
+        assert (acc.attr_idx == -1).sum() > 0 and 99999 in acc.attr_idx  # foreign names -> -1, unknown Pfam numbers kept
+    with native("sequence_id\tprotein_id\tstart\tend\tstrand\n", []) as tables:
+        empty = tables.pack(None, feature_type, accessions=True)
+        assert (empty.C, empty.G, empty.nnz) == (0, 0, 0)
+
+
 def test_writers_are_independent_of_threads_and_chunks(weights, tmp_path, monkeypatch):
     """~30k genes / ~60k domain rows: the writers cut the genes into chunks that threads format and place with pwrite at
     chained offsets; one thread or eight, the files are the same bytes, and every row is the restatement's row."""
