@@ -390,6 +390,27 @@ def run_ours(args) -> None:
                           "genes_per_s_features_plus_marginals": batch.G / ((f_ms_avg + kernel_ms_avg) * 1e-3)}
         engine.set_stream(None)
         del d_acc, d_ids
+        # ... and end to end from raw accessions (GCRF_FLAG_ACCESSIONS): H2D + features + marginals + D2H per step
+        pin_acc = PinnedArray(acc_host.shape, acc_host.dtype)
+        pin_acc.array[...] = acc_host
+
+        def step_host_accessions():
+            engine.marginals_windowed(pins[0].array, pins[1].array, pin_acc.array, window=WINDOW, step=STEP, pad=PAD,
+                                      out=pout.array, accessions=True)
+
+        for _ in range(2):
+            step_host_accessions()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host_accessions()
+        torch.cuda.synchronize(dev)
+        acc_s = time.perf_counter() - t0
+        features_stage["e2e_from_accessions"] = {
+            "value": batch.G * e2e_steps / acc_s, "unit": UNIT, "ms_per_step": 1e3 * acc_s / e2e_steps,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "n_gpus": 1,
+            "bit_identical_to_device_path": bool(numpy.array_equal(pout.array, out.cpu().numpy()))}
+        pin_acc.free()
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
