@@ -48,6 +48,28 @@ namespace {
 
 using sv = std::string_view;
 
+// Row storage that is not filled before the parsing threads write it: resize() on a plain std::vector would zero
+// (and fault in, on ONE thread) a few hundred MB that are overwritten right away.  Only for the trivially copyable
+// row structs below; every element is assigned before it is read.
+template <typename T>
+struct NoInitAllocator : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = NoInitAllocator<U>;
+    };
+    NoInitAllocator() = default;
+    template <typename U>
+    NoInitAllocator(const NoInitAllocator<U> &) noexcept {}
+    template <typename U>
+    void construct(U *) noexcept {}  // resize(): leave the storage as it is
+    template <typename U, typename... Args>
+    void construct(U *p, Args &&...args) {
+        ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
+    }
+};
+template <typename T>
+using RowVector = std::vector<T, NoInitAllocator<T>>;
+
 struct GeneRow {
     sv seq, prot, strand;
     int64_t start = 0, end = 0;
@@ -61,43 +83,48 @@ struct DomainRow {
     int32_t gene;  // index into the sorted genes; -1 = dropped by a filter
 };
 
-// protein_id -> row number of the genes table: open addressing over precomputed hashes (one flat array, no node
-// allocations; the std::unordered_map it replaces took a third of a second per million genes)
+// protein_id -> row number of the genes table: open addressing, one 64-bit word per slot — the upper half of the
+// name's hash and the row number — so that a slot is claimed with ONE compare-and-swap and several threads can fill
+// the table at once (no node allocations; the std::unordered_map it replaces took a third of a second per million
+// genes, the serial fill of this table 0.11 s).
 struct NameIndex {
-    std::vector<int32_t> slot;
-    std::vector<uint64_t> hash;
+    static constexpr uint64_t kEmpty = ~0ull;
+    std::vector<uint64_t> slot;
     uint64_t mask = 0;
     static uint64_t hash_of(sv s) {
         uint64_t h = 1469598103934665603ull;  // FNV-1a, folded
         for (unsigned char c : s) h = (h ^ c) * 1099511628211ull;
         return h ^ (h >> 29);
     }
+    static uint64_t word_of(uint64_t h, int32_t id) { return (h & 0xffffffff00000000ull) | (uint32_t)id; }
     void reserve(size_t n) {
         size_t cap = 16;
         while (cap < 2 * n + 2) cap <<= 1;
-        slot.assign(cap, -1);
-        hash.assign(cap, 0);
+        slot.assign(cap, kEmpty);
         mask = cap - 1;
     }
-    // returns false if the name is already present
+    size_t capacity() const { return slot.size(); }
+    // returns false if the name is already present; safe to call from several threads at once (ids are >= 0 and
+    // below 2^31, so no word equals kEmpty)
     template <typename KeyOf>
     bool insert(sv name, int32_t id, KeyOf &&key_of) {
-        const uint64_t h = hash_of(name);
+        const uint64_t h = hash_of(name), mine = word_of(h, id);
         for (uint64_t i = h & mask;; i = (i + 1) & mask) {
-            if (slot[i] < 0) {
-                slot[i] = id;
-                hash[i] = h;
-                return true;
+            uint64_t cur = __atomic_load_n(&slot[i], __ATOMIC_ACQUIRE);
+            if (cur == kEmpty) {
+                if (__atomic_compare_exchange_n(&slot[i], &cur, mine, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) return true;
+                // lost the race: `cur` now holds the winner's word
             }
-            if (hash[i] == h && key_of(slot[i]) == name) return false;
+            if ((cur >> 32) == (h >> 32) && key_of((int32_t)(uint32_t)cur) == name) return false;
         }
     }
     template <typename KeyOf>
     int32_t find(sv name, KeyOf &&key_of) const {
         const uint64_t h = hash_of(name);
         for (uint64_t i = h & mask;; i = (i + 1) & mask) {
-            if (slot[i] < 0) return -1;
-            if (hash[i] == h && key_of(slot[i]) == name) return slot[i];
+            const uint64_t cur = slot[i];
+            if (cur == kEmpty) return -1;
+            if ((cur >> 32) == (h >> 32) && key_of((int32_t)(uint32_t)cur) == name) return (int32_t)(uint32_t)cur;
         }
     }
 };
@@ -180,7 +207,7 @@ size_t read_header(sv buf, Header *h) {
 // newline-aligned chunks.  Two passes: the lines of every chunk are counted first, so that each thread writes its
 // rows straight into its slice of the result (file order, no reallocation, no concatenation).
 template <typename Row, typename Fn>
-void parse_lines(sv buf, size_t begin, int threads, std::vector<Row> *rows, Fn &&make_row) {
+void parse_lines(sv buf, size_t begin, int threads, RowVector<Row> *rows, Fn &&make_row) {
     const size_t n = buf.size();
     if (begin >= n) return;
     if (threads < 1) threads = 1;
@@ -354,12 +381,12 @@ struct FileBuffer {
 struct gcrf_table {
     std::vector<FileBuffer> buffers;  // the files; every string_view below points into one of them
     // genes, in the reference's order (sequence_id, start, end)
-    std::vector<GeneRow> genes;
+    RowVector<GeneRow> genes;
     std::vector<int32_t> contig_ptr;           // [C+1] into genes
     std::vector<std::string> contig_ids;       // [C]
     std::vector<std::string> gene_ids;         // [G] NUL-terminated copies, built lazily for the accessor
     // domain rows kept by the filters, grouped by gene, ordered by (domain_start, domain_end)
-    std::vector<DomainRow> domains;
+    RowVector<DomainRow> domains;
     std::vector<int64_t> dom_ptr;              // [G+1] into domains
     std::vector<uint8_t> annotated;            // [G] gene has >= 1 domain left
     // gcrf_table_pack results
@@ -438,7 +465,7 @@ struct PhaseTimer {
 void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, double e_filter, double p_filter, int threads) {
     PhaseTimer timer;
     // ---- genes table
-    std::vector<GeneRow> rows;
+    RowVector<GeneRow> rows;
     {
         Header h;
         const size_t body = read_header(genes_buf, &h);
@@ -464,8 +491,23 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
     auto prot_of = [&](int32_t i) { return rows[(size_t)i].prot; };
     NameIndex by_name;
     by_name.reserve(rows.size());
-    for (size_t i = 0; i < rows.size(); ++i)
-        if (!by_name.insert(rows[i].prot, (int32_t)i, prot_of)) throw ParseError{"Duplicate gene names in input genes"};
+    {
+        const size_t n = rows.size();
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, n / 50000));
+        std::atomic<bool> duplicate{false};
+        auto fill = [&](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i)
+                if (!by_name.insert(rows[i].prot, (int32_t)i, prot_of)) duplicate.store(true);
+        };
+        if (nt <= 1) {
+            fill(0, n);
+        } else {
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nt; ++k) pool.emplace_back(fill, n * k / nt, n * (k + 1) / nt);
+            for (auto &th : pool) th.join();
+        }
+        if (duplicate.load()) throw ParseError{"Duplicate gene names in input genes"};
+    }
     timer.mark("index genes by name");
     // sort by (sequence_id, start, end), stable (predict.py:81).  The ids are compared once per CONTIG, not once per
     // comparison: distinct ids are ranked, genes are bucketed by rank (stable), and every bucket is sorted by numbers.
@@ -487,7 +529,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             if (c < 0) {
                 c = (int32_t)ids.size();
                 ids.push_back(rows[i].seq);
-                if (2 * ids.size() + 2 > seen.slot.size()) {  // grow and re-insert
+                if (2 * ids.size() + 2 > seen.capacity()) {  // grow and re-insert
                     seen.reserve(4 * ids.size());
                     for (size_t k = 0; k < ids.size(); ++k) seen.insert(ids[k], (int32_t)k, id_of);
                 } else {
@@ -540,9 +582,21 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
     }
     std::vector<int32_t> rank(G);
     t->genes.resize(G);
-    for (size_t k = 0; k < G; ++k) {
-        t->genes[k] = rows[(size_t)order[k]];
-        rank[(size_t)order[k]] = (int32_t)k;
+    {
+        auto gather = [&](size_t k0, size_t k1) {
+            for (size_t k = k0; k < k1; ++k) {
+                t->genes[k] = rows[(size_t)order[k]];
+                rank[(size_t)order[k]] = (int32_t)k;
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, G / 50000));
+        if (nt <= 1) {
+            gather(0, G);
+        } else {
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nt; ++k) pool.emplace_back(gather, G * k / nt, G * (k + 1) / nt);
+            for (auto &th : pool) th.join();
+        }
     }
     t->contig_ids.reserve(C);
     for (size_t r = 0; r < C; ++r) t->contig_ids.emplace_back(ids[(size_t)by_id[r]]);
@@ -552,7 +606,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
     // ---- feature tables, concatenated in the order given (load_features, _common.py:193-208).  Every row is
     //      attached to its gene (annotate_genes, _common.py:226-249) and filtered (filter_domains, :419-448: NaN < x is
     //      false, so NaN rows go as well) by the thread that parses it; what is stored is the compact DomainRow.
-    std::vector<DomainRow> drows;
+    RowVector<DomainRow> drows;
     for (sv fb : feature_bufs) {
         Header h;
         const size_t body = read_header(fb, &h);

@@ -301,6 +301,25 @@ def test_accession_pack_is_the_id_pack_before_feature_extraction(weights, featur
         assert (empty.C, empty.G, empty.nnz) == (0, 0, 0)
 
 
+def test_concurrent_name_index_finds_duplicates_and_every_gene(monkeypatch):
+    """120k genes: the gene-name index is filled by several threads (one compare-and-swap per slot); a name that occurs
+    twice, far apart, is still the reference's "Duplicate gene names" error (_common.py:217-219), and without it every
+    feature row finds its gene."""
+    monkeypatch.setenv("GCRF_TABLE_THREADS", "8")
+    n = 120_000
+    head = "sequence_id\tprotein_id\tstart\tend\tstrand\n"
+    lines = [f"c{i // 50:05d}\tc{i // 50:05d}_{i % 50 + 1}\t{1 + 100 * (i % 50)}\t{90 + 100 * (i % 50)}\t+\n" for i in range(n)]
+    fhead = "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end\n"
+    frows = [lines[i][:-1] + "\tPF00005\tPfam\t1e-20\t1e-22\t1\t20\n" for i in range(0, n, 7)]
+    with native(head + "".join(lines), [fhead + "".join(frows)]) as tables:
+        assert (tables.genes, tables.domains) == (n, len(frows))
+        assert int(tables.annotated.sum()) == len(frows)
+    dup = list(lines)
+    dup[n - 5] = dup[n - 5].replace(f"c{(n - 5) // 50:05d}_{(n - 5) % 50 + 1}\t", "c00003_4\t")
+    with pytest.raises(ValueError, match="Duplicate gene names"):
+        native(head + "".join(dup), [])
+
+
 def test_writers_are_independent_of_threads_and_chunks(weights, tmp_path, monkeypatch):
     """~30k genes / ~60k domain rows: the writers cut the genes into chunks that threads format and place with pwrite at
     chained offsets; one thread or eight, the files are the same bytes, and every row is the restatement's row."""
