@@ -203,7 +203,13 @@ size_t read_header(sv buf, Header *h) {
     return nl == sv::npos ? buf.size() : nl + 1;
 }
 
-// Calls make_row(fields, offset) for every non-empty data line of buf[begin, end) on `threads` threads over
+// What a row callback may remember from the previous line of its chunk (the rows of a gene usually follow each other).
+struct LineMemo {
+    sv name;
+    int32_t row = -1;
+};
+
+// Calls make_row(fields, offset, memo) for every non-empty data line of buf[begin, end) on `threads` threads over
 // newline-aligned chunks.  Two passes: the lines of every chunk are counted first, so that each thread writes its
 // rows straight into its slice of the result (file order, no reallocation, no concatenation).
 template <typename Row, typename Fn>
@@ -254,6 +260,7 @@ void parse_lines(sv buf, size_t begin, int threads, RowVector<Row> *rows, Fn &&m
     run([&](int t) {
         std::vector<sv> f;
         sv line;
+        LineMemo memo;  // lives as long as this thread's pass over its chunk
         Row *out = rows->data() + base + count[t];
         try {
             for (size_t p = cut[t]; p < cut[t + 1];) {
@@ -261,7 +268,7 @@ void parse_lines(sv buf, size_t begin, int threads, RowVector<Row> *rows, Fn &&m
                 p = next_line(p, cut[t + 1], &line);
                 if (line.empty()) continue;
                 split_tabs(line, f);
-                *out++ = make_row(f, at);
+                *out++ = make_row(f, at, memo);
             }
         } catch (const ParseError &e) {
             errors[t] = e.message;
@@ -473,7 +480,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
                   c_start = column(h, "start", "genes"), c_end = column(h, "end", "genes"),
                   c_strand = column(h, "strand", "genes");
         const size_t need = (size_t)std::max({c_seq, c_prot, c_start, c_end, c_strand}) + 1;
-        parse_lines(genes_buf, body, threads, &rows, [&](const std::vector<sv> &f, size_t off) {
+        parse_lines(genes_buf, body, threads, &rows, [&](const std::vector<sv> &f, size_t off, LineMemo &) {
             if (f.size() < need) throw ParseError{"genes table: line " + std::to_string(line_number(genes_buf, off)) + " has too few fields"};
             GeneRow g;
             g.seq = unquote(f[c_seq]);
@@ -618,7 +625,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
                   c_pv = column(h, "pvalue", "features"), c_ds = column(h, "domain_start", "features"),
                   c_de = column(h, "domain_end", "features");
         const size_t need = (size_t)std::max({c_seq, c_prot, c_start, c_end, c_strand, c_dom, c_hmm, c_ev, c_pv, c_ds, c_de}) + 1;
-        parse_lines(fb, body, threads, &drows, [&](const std::vector<sv> &f, size_t off) {
+        parse_lines(fb, body, threads, &drows, [&](const std::vector<sv> &f, size_t off, LineMemo &memo) {
             auto where = [&] { return " on line " + std::to_string(line_number(fb, off)) + " of a features table"; };
             if (f.size() < need) throw ParseError{"too few fields" + where()};
             DomainRow d;
@@ -630,7 +637,15 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
                 throw ParseError{"bad integer" + where()};
             if (!parse_float(f[c_ev], &d.i_evalue) || !parse_float(f[c_pv], &d.pvalue)) throw ParseError{"bad number" + where()};
             const sv prot = unquote(f[c_prot]), seq = unquote(f[c_seq]), strand = unquote(f[c_strand]);
-            const int32_t row = by_name.find(prot, prot_of);
+            // the rows of a gene usually follow each other: remember the last answer (per parsing thread)
+            int32_t row;
+            if (memo.row >= 0 && prot == memo.name) {
+                row = memo.row;
+            } else {
+                row = by_name.find(prot, prot_of);
+                memo.name = prot;
+                memo.row = row;
+            }
             if (row < 0) throw ParseError{"Unknown protein " + std::string(prot) + " in features table"};
             const GeneRow &g = rows[(size_t)row];
             if (g.seq != seq || g.end - g.start != end - start || g.start != start || g.end != end || g.strand != strand) {
