@@ -1210,6 +1210,7 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
     if (!t || !path) return tfail(GCRF_EINVAL, "bad arguments");
     if (row_prob && t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");
     const size_t G = t->genes.size();
+    PhaseTimer timer;
     // per-domain probability: the gene's value in protein mode, the row's own in domain mode
     std::vector<double> dp(t->domains.size(), std::numeric_limits<double>::quiet_NaN());
     bool any = false;
@@ -1226,24 +1227,43 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
         }
         for (double p : dp) any |= !std::isnan(p);
     }
+    timer.mark("per-domain probabilities");
     std::string header = "sequence_id\tprotein_id\tstart\tend\tstrand\tdomain\thmm\ti_evalue\tpvalue\tdomain_start\tdomain_end";
     if (any) header += "\tcluster_probability";
     header += '\n';
     const size_t per_gene = G ? 160 * (t->domains.size() / G + 1) : 160;
+    const bool per_gene_prob = t->packed_mode == 0;  // protein mode: every domain row of a gene carries the gene's value
     return write_by_genes(path, header, G, per_gene, [&](std::string &out, size_t g) {
         const GeneRow &r = t->genes[g];
-        for (int64_t k = t->dom_ptr[g]; k < t->dom_ptr[g + 1]; ++k) {
+        const int64_t b = t->dom_ptr[g], e = t->dom_ptr[g + 1];
+        if (b == e) return;
+        // the five gene columns are the same text on every row of the gene: laid out once
+        const size_t p0 = out.size();
+        out.append(r.seq);
+        out += '\t';
+        out.append(r.prot);
+        out += '\t';
+        append_int(out, r.start);
+        out += '\t';
+        append_int(out, r.end);
+        out += '\t';
+        out.append(r.strand);
+        out += '\t';
+        const size_t plen = out.size() - p0;
+        char prob[40];
+        size_t prob_len = 0;
+        std::string tmp;
+        if (any && per_gene_prob && !std::isnan(dp[(size_t)b])) {
+            append_repr(tmp, dp[(size_t)b]);
+            prob_len = std::min(tmp.size(), sizeof(prob));
+            memcpy(prob, tmp.data(), prob_len);
+        }
+        for (int64_t k = b; k < e; ++k) {
             const DomainRow &d = t->domains[(size_t)k];
-            out.append(r.seq);
-            out += '\t';
-            out.append(r.prot);
-            out += '\t';
-            append_int(out, r.start);
-            out += '\t';
-            append_int(out, r.end);
-            out += '\t';
-            out.append(r.strand);
-            out += '\t';
+            if (k > b) {
+                out.reserve(out.size() + plen);  // no reallocation while the string copies from itself
+                out.append(out.data() + p0, plen);
+            }
             out.append(d.name);
             out += '\t';
             out.append(d.hmm);
@@ -1257,7 +1277,10 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
             append_int(out, d.dend);
             if (any) {
                 out += '\t';
-                if (!std::isnan(dp[(size_t)k])) append_repr(out, dp[(size_t)k]);
+                if (per_gene_prob)
+                    out.append(prob, prob_len);
+                else if (!std::isnan(dp[(size_t)k]))
+                    append_repr(out, dp[(size_t)k]);
             }
             out += '\n';
         }
