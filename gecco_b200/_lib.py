@@ -160,7 +160,7 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_table_pack.argtypes = [vp, ctypes.POINTER(cp), i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                     ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.gcrf_table_pack_accessions.restype = ctypes.c_int
-    lib.gcrf_table_pack_accessions.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+    lib.gcrf_table_pack_accessions.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                                ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.gcrf_table_row_gene.restype = vp
     lib.gcrf_table_row_gene.argtypes = [vp]
@@ -245,16 +245,21 @@ class CRFEngine:
                                                      self.device, ctypes.byref(handle)))
         self._handle = handle
         self.has_vocabulary = False
-        # Pfam-style attribute names ("PF" + digits): hand the integer vocabulary to the device so that feature
-        # extraction (accession -> attribute id, repeats inside a gene dropped) can run there
+        self.vocabulary_digits = 0
+        # Pfam-style attribute names ("PF" + a fixed number of ASCII digits, so that number <-> name is one to one):
+        # hand the integer vocabulary to the device so that feature extraction (accession -> attribute id, repeats
+        # inside a gene dropped) can run there
         accs = []
+        widths = set()
         for name in weights.attrs:
-            if len(name) > 2 and name[:2] == "PF" and name[2:].isdigit():
+            if len(name) > 2 and name[:2] == "PF" and name[2:].isascii() and name[2:].isdigit() and len(name) <= 11:
                 accs.append(int(name[2:]))
+                widths.add(len(name) - 2)
             else:
                 accs = None
                 break
-        if accs is not None and len(set(accs)) == len(accs):
+        if accs and len(widths) == 1 and len(set(accs)) == len(accs):
+            self.vocabulary_digits = widths.pop()
             arr = numpy.asarray(accs, dtype=numpy.int32)
             _check(self._lib, self._lib.gcrf_model_set_vocabulary(self._handle, arr.ctypes.data if len(arr) else None, len(arr)))
             self.has_vocabulary = True

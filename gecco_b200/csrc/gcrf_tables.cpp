@@ -1010,9 +1010,10 @@ int gcrf_table_pack(gcrf_table *t, const char *const *attr_names, int32_t A, int
     return GCRF_OK;
 }
 
-int gcrf_table_pack_accessions(gcrf_table *t, int32_t feature_type, const int32_t **contig_ptr, const int32_t **row_ptr,
-                               const int32_t **accession, int64_t *rows, int64_t *nnz) {
+int gcrf_table_pack_accessions(gcrf_table *t, int32_t feature_type, int32_t digits, const int32_t **contig_ptr,
+                               const int32_t **row_ptr, const int32_t **accession, int64_t *rows, int64_t *nnz) {
     if (!t) return tfail(GCRF_EINVAL, "table is NULL");
+    if (digits < 0 || digits > 9) return tfail(GCRF_EINVAL, "digits must be 0..9");
     if (feature_type != 0 && feature_type != 1) return tfail(GCRF_EINVAL, "invalid feature type: %d", feature_type);
     try {
         const size_t G = t->genes.size(), C = t->contig_ids.size(), D = t->domains.size();
@@ -1023,7 +1024,8 @@ int gcrf_table_pack_accessions(gcrf_table *t, int32_t feature_type, const int32_
             for (size_t d = d0; d < d1; ++d) {
                 const sv name = t->domains[d].name;
                 int32_t v = -1;
-                if (name.size() > 2 && name.size() <= 11 && name[0] == 'P' && name[1] == 'F') {
+                if (name.size() > 2 && name.size() <= 11 && name[0] == 'P' && name[1] == 'F' &&
+                    (digits == 0 || name.size() == (size_t)digits + 2)) {
                     int64_t x = 0;
                     bool digits = true;
                     for (size_t i = 2; i < name.size(); ++i) {

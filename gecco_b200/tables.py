@@ -159,18 +159,20 @@ class FeatureTables:
         return start, end
 
     # ------------------------------------------------------------------ features
-    def pack(self, attrs: Optional[Sequence[str]], feature_type: str = "protein", *, accessions: bool = False) -> PackedGenes:
+    def pack(self, attrs: Optional[Sequence[str]], feature_type: str = "protein", *, accessions: bool = False,
+             digits: int = 5) -> PackedGenes:
         """CSR batch for the marginal kernels (views into the table: valid until the next ``pack`` / ``close``).
 
         ``accessions=True`` (``gcrf_table_pack_accessions``): nothing is looked up or de-duplicated on the host; the
         batch holds the Pfam number of every kept domain row and the device does the feature extraction
-        (``GCRF_FLAG_ACCESSIONS``; for models whose attributes are all ``PF`` + digits, ``attrs`` is not needed)."""
+        (``GCRF_FLAG_ACCESSIONS``; for models whose attributes are all ``PF`` + ``digits`` digits — only domain names
+        of exactly that form count, the reference compares names — ``attrs`` is not needed)."""
         if feature_type not in ("protein", "domain"):
             raise ValueError(f"invalid feature type: {feature_type!r}")
         cp, rp, ai = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         rows, nnz = ctypes.c_int64(), ctypes.c_int64()
         if accessions:
-            rc = self._lib.gcrf_table_pack_accessions(self._h, 0 if feature_type == "protein" else 1, ctypes.byref(cp),
+            rc = self._lib.gcrf_table_pack_accessions(self._h, 0 if feature_type == "protein" else 1, int(digits), ctypes.byref(cp),
                                                       ctypes.byref(rp), ctypes.byref(ai), ctypes.byref(rows), ctypes.byref(nnz))
         else:
             names = (ctypes.c_char_p * max(1, len(attrs)))(*[a.encode() for a in attrs])
@@ -194,8 +196,10 @@ class FeatureTables:
         """Pack with the model's vocabulary and feature type, run the marginal kernels: one value per packed row."""
         # Pfam-only vocabularies (the shipped model): the table hands over raw accession numbers and the feature
         # extraction runs on the device; GECCO_B200_HOST_FEATURES=1 keeps the host packer (A/B, other vocabularies)
-        on_device = os.environ.get("GECCO_B200_HOST_FEATURES", "0") != "1" and crf._get_engine().has_vocabulary
-        packed = self.pack(crf._weights.attrs, crf.feature_type, accessions=on_device)
+        engine = crf._get_engine()
+        on_device = os.environ.get("GECCO_B200_HOST_FEATURES", "0") != "1" and engine.has_vocabulary
+        packed = self.pack(crf._weights.attrs, crf.feature_type, accessions=on_device,
+                           digits=getattr(engine, "vocabulary_digits", 0))
         return crf.marginals(packed, pad=pad) if packed.G else numpy.zeros(0)
 
     # ------------------------------------------------------------------ results

@@ -259,10 +259,11 @@ int gcrf_table_pack(gcrf_table *table, const char *const *attr_names, int32_t A,
  * per kept domain row — the number behind a "PF" prefix (PF00394 -> 394), -1 for any other name — in the table's
  * domain order, nothing looked up or de-duplicated on the host (gecco/crf/features.py:13-35 then runs in
  * gcrf::features_kernel).  Same feature types, ownership and row layout as gcrf_table_pack; for models whose
- * attributes are all "PF" + digits (gcrf_model_set_vocabulary).
+ * attributes are all "PF" + `digits` ASCII digits (gcrf_model_set_vocabulary): the reference compares NAMES, so a
+ * domain called PF394 is not PF00394 — only names with exactly `digits` digits count (0 = any number of digits).
  */
-int gcrf_table_pack_accessions(gcrf_table *table, int32_t feature_type, const int32_t **contig_ptr, const int32_t **row_ptr,
-                               const int32_t **accession, int64_t *rows, int64_t *nnz);
+int gcrf_table_pack_accessions(gcrf_table *table, int32_t feature_type, int32_t digits, const int32_t **contig_ptr,
+                               const int32_t **row_ptr, const int32_t **accession, int64_t *rows, int64_t *nnz);
 const int32_t *gcrf_table_row_gene(const gcrf_table *table); /* [rows] gene of every packed row */
 
 /*

@@ -275,7 +275,8 @@ def test_accession_pack_is_the_id_pack_before_feature_extraction(weights, featur
     """gcrf_table_pack_accessions hands the device every kept domain row as a Pfam number; mapping those through the
     vocabulary and keeping the first of equal names per row (features.py:13-35, what gcrf::features_kernel does) must
     give the batch gcrf_table_pack builds on the host — same rows, same contigs, same row -> gene map."""
-    names = list(weights.attrs[:40]) + ["PF99999", "TIGR00001", "PFAM1", "PF", "PF12x"]
+    names = list(weights.attrs[:40]) + ["PF99999", "TIGR00001", "PFAM1", "PF", "PF12x", "PF" + weights.attrs[0][2:].lstrip("0"),
+                                        "PF0" + weights.attrs[1][2:]]  # the last two: right number, wrong NAME
     gtext, ftexts = synthetic_tables(23, 40, 30, names)
     with native(gtext, ftexts) as tables:
         ids = tables.pack(weights.attrs, feature_type)
