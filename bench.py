@@ -366,7 +366,7 @@ def run_ours(args) -> None:
     # ---- the stage in front of the marginals: accession -> attribute id on device, same batch.
     # Outside the headline's timed region; reported so that "accessions in, marginals out" has a measured number.
     features_stage = None
-    if rank == 0 and engine.has_vocabulary:
+    if rank == 0 and world == 1 and engine.has_vocabulary:  # like cpu_baseline: on the N=1 line only
         nums = numpy.array([int(a[2:]) for a in weights.attrs], dtype=numpy.int32)
         acc_host = numpy.where(batch.attr_idx >= 0, nums[numpy.clip(batch.attr_idx, 0, len(nums) - 1)], 99_999).astype(numpy.int32)
         d_acc = torch.from_numpy(acc_host).to(dev)
