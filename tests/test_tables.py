@@ -409,3 +409,31 @@ def test_predict_tables_on_device(bgc, tmp_path):
     assert (int(crows[0]["start"]), int(crows[0]["end"])) == (want["start"], want["end"])
     assert abs(float(crows[0]["average_p"]) - float(want["average_p"])) <= 1e-5
     tables.close()
+
+
+def test_the_abi_from_plain_c(bgc, tmp_path):
+    """examples/tables_roundtrip.c, compiled as C99 against include/gecco_crf_b200.h and linked with the shared library
+    (no Python, no torch in that process): loads the reference fixture's tables, packs the accession batch and writes
+    the genes table — the header is valid C and the table half of the ABI needs no GPU."""
+    import shutil
+    import subprocess
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "tables_roundtrip"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{root / 'include'}", str(root / "examples" / "tables_roundtrip.c"),
+                    f"-L{root / 'gecco_b200'}", "-lgecco_crf_b200", f"-Wl,-rpath,{root / 'gecco_b200'}", "-lm", "-o", str(exe)],
+                   check=True, capture_output=True)
+    gtext, ftext = bgc_tables(bgc)
+    (tmp_path / "x.genes.tsv").write_text(gtext)
+    (tmp_path / "x.features.tsv").write_text(ftext)
+    run = subprocess.run([str(exe), str(tmp_path / "x.genes.tsv"), str(tmp_path / "x.features.tsv"), str(tmp_path / "o.genes.tsv")],
+                         check=True, capture_output=True, text=True)
+    fields = dict(kv.split("=") for kv in run.stdout.split())
+    with native(gtext, [ftext]) as tables:
+        assert (int(fields["contigs"]), int(fields["genes"]), int(fields["domains"])) == (tables.contigs, tables.genes, tables.domains)
+        assert int(fields["rows"]) == tables.genes and int(fields["nnz"]) == tables.domains == int(fields["last_row_end"])
+        assert fields["first_contig"] == tables.contig_ids[0]
+        tables.write_genes(tmp_path / "p.genes.tsv")
+    assert (tmp_path / "o.genes.tsv").read_bytes() == (tmp_path / "p.genes.tsv").read_bytes()
