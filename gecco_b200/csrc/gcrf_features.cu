@@ -168,7 +168,7 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
             p_lo1 = (int64_t)__ldg(gene_ptr + min(next + stride + lane, G));
             p_end1 = (int64_t)__ldg(gene_ptr + min(next + stride + 32, G));
         }
-        if (block_rows > 0x7fffffff) {  // offsets would not fit 32 bits: gene by gene
+        if (block_rows > 0x7fffffff - 32 * U) {  // offsets (plus one batch) would not fit 32 bits: gene by gene
             for (int g = 0; g < ng; ++g)
                 gene_rows_simple(accession, (int64_t)__ldg(gene_ptr + base + g), (int64_t)__ldg(gene_ptr + base + g + 1),
                                  lut, lut_size, out, lane);
@@ -219,7 +219,7 @@ features_kernel(const int32_t *__restrict__ accession, const PtrT *__restrict__ 
                     const int64_t P0n = __shfl_sync(kFull, p_lo, 0);
                     const int ngn = (int)min((int64_t)32, G - next);
                     const int64_t r1n = (GG >= ngn ? p_end : __shfl_sync(kFull, p_lo, GG & 31)) - P0n;
-                    if (p_end - P0n <= 0x7fffffff) {
+                    if (p_end - P0n <= 0x7fffffff - 32 * U) {
                         pend_off = 0;
                         pend_r1 = uniform((int)r1n);
 #pragma unroll
