@@ -17,6 +17,7 @@ pack to the CSR batch of the marginal kernels, write the result tables from the 
 from __future__ import annotations
 
 import bz2
+import collections.abc
 import ctypes
 import gzip
 import lzma
@@ -50,6 +51,40 @@ def _nan_if_none(x: Optional[float]) -> float:
     return math.nan if x is None else float(x)
 
 
+class _LazyNames(collections.abc.Sequence):
+    """Names held by the native table, fetched when somebody looks: a metagenome table has a million contig ids, and
+    ``pack`` hands them along with every batch without anybody reading them on the bulk path."""
+
+    def __init__(self, n: int, fetch):
+        self._n, self._fetch, self._all = n, fetch, None
+
+    def __len__(self) -> int:
+        return self._n
+
+    def _list(self) -> List[str]:
+        if self._all is None:
+            self._all = [self._fetch(i).decode() for i in range(self._n)]
+        return self._all
+
+    def __getitem__(self, i):
+        if isinstance(i, slice) or self._all is not None:
+            return self._list()[i]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._fetch(i).decode()
+
+    def __iter__(self):
+        return iter(self._list())
+
+    def __eq__(self, other):
+        return self._list() == list(other) if isinstance(other, (list, tuple, _LazyNames)) else NotImplemented
+
+    def __repr__(self) -> str:
+        return repr(self._list())
+
+
 class FeatureTables:
     """A genes table plus its feature tables, annotated, sorted and filtered like ``gecco predict`` does."""
 
@@ -58,6 +93,8 @@ class FeatureTables:
         self._h = handle
         self._packed: Optional[PackedGenes] = None
         self.feature_type: Optional[str] = None
+        self._contig_ids: Optional[_LazyNames] = None
+        self._gene_ids: Optional[_LazyNames] = None
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -125,12 +162,16 @@ class FeatureTables:
         return int(self._lib.gcrf_table_domains(self._h))
 
     @property
-    def contig_ids(self) -> List[str]:
-        return [self._lib.gcrf_table_contig_id(self._h, c).decode() for c in range(self.contigs)]
+    def contig_ids(self) -> Sequence[str]:
+        if self._contig_ids is None:
+            self._contig_ids = _LazyNames(self.contigs, lambda c: self._lib.gcrf_table_contig_id(self._h, c))
+        return self._contig_ids
 
     @property
-    def gene_ids(self) -> List[str]:
-        return [self._lib.gcrf_table_gene_id(self._h, g).decode() for g in range(self.genes)]
+    def gene_ids(self) -> Sequence[str]:
+        if self._gene_ids is None:
+            self._gene_ids = _LazyNames(self.genes, lambda g: self._lib.gcrf_table_gene_id(self._h, g))
+        return self._gene_ids
 
     def _view(self, ptr: Optional[int], n: int, dtype) -> numpy.ndarray:
         if not ptr or n == 0:
