@@ -551,7 +551,35 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
     const size_t C = ids.size();
     std::vector<int32_t> by_id(C), rank_of(C);
     std::iota(by_id.begin(), by_id.end(), 0);
-    std::sort(by_id.begin(), by_id.end(), [&](int32_t a, int32_t b) { return ids[(size_t)a] < ids[(size_t)b]; });
+    {
+        // a metagenome table has a million distinct ids: nothing to do when they already come in order, else sorted
+        // slices on all threads, merged pairwise
+        auto less = [&](int32_t a, int32_t b) { return ids[(size_t)a] < ids[(size_t)b]; };
+        bool in_order = true;
+        for (size_t r = 1; r < C && in_order; ++r) in_order = !(ids[r] < ids[r - 1]);
+        int nt = (int)std::min<size_t>((size_t)threads, C / 20000);
+        if (in_order) {
+            // ids are distinct: the order of first appearance is the sorted order
+        } else if (nt <= 1) {
+            std::sort(by_id.begin(), by_id.end(), less);
+        } else {
+            int pow2 = 1;
+            while (pow2 * 2 <= nt) pow2 *= 2;
+            nt = pow2;
+            auto cut = [&](int k) { return by_id.begin() + (std::ptrdiff_t)(C * (size_t)k / (size_t)nt); };
+            {
+                std::vector<std::thread> pool;
+                for (int k = 0; k < nt; ++k) pool.emplace_back([&, k] { std::sort(cut(k), cut(k + 1), less); });
+                for (auto &th : pool) th.join();
+            }
+            for (int width = 1; width < nt; width *= 2) {
+                std::vector<std::thread> pool;
+                for (int k = 0; k + width < nt; k += 2 * width)
+                    pool.emplace_back([&, k, width] { std::inplace_merge(cut(k), cut(k + width), cut(std::min(nt, k + 2 * width)), less); });
+                for (auto &th : pool) th.join();
+            }
+        }
+    }
     for (size_t r = 0; r < C; ++r) rank_of[(size_t)by_id[r]] = (int32_t)r;
     t->contig_ptr.assign(C + 1, 0);
     for (size_t i = 0; i < G; ++i) ++t->contig_ptr[(size_t)rank_of[(size_t)contig_of[i]] + 1];

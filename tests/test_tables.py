@@ -343,6 +343,26 @@ def test_concurrent_name_index_finds_duplicates_and_every_gene(monkeypatch):
         native(head + "".join(dup), [])
 
 
+@pytest.mark.parametrize("threads", ["8", "3", "1"])
+def test_many_contigs_are_ranked_by_id_on_all_threads(threads, monkeypatch):
+    """170k contigs whose ids arrive in no particular order: the distinct ids are sorted in slices by all threads and
+    merged pairwise; contigs come out in id order (predict.py:81), genes inside a contig by start."""
+    monkeypatch.setenv("GCRF_TABLE_THREADS", threads)
+    n = 170_000
+    head = "sequence_id\tprotein_id\tstart\tend\tstrand\n"
+    order = [(i * 7919) % n for i in range(n)]  # a permutation: 7919 is prime and does not divide n
+    lines = [f"k{c:06d}\tk{c:06d}_1\t10\t400\t+\n" for c in order]
+    lines += [f"k{c:06d}\tk{c:06d}_0\t5\t9\t-\n" for c in order[:1000]]  # a second, earlier gene for some
+    with native(head + "".join(lines), []) as tables:
+        assert (tables.contigs, tables.genes) == (n, n + 1000)
+        ids = tables.contig_ids
+        assert ids[0] == "k000000" and ids[n - 1] == f"k{n - 1:06d}" and list(ids) == sorted(ids)
+        first = sorted(order[:1000])[0]
+        cp = tables.contig_ptr
+        assert cp[first + 1] - cp[first] == 2
+        assert tables.gene_ids[int(cp[first])] == f"k{first:06d}_0" and tables.gene_ids[int(cp[first]) + 1] == f"k{first:06d}_1"
+
+
 def test_writers_are_independent_of_threads_and_chunks(weights, tmp_path, monkeypatch):
     """~30k genes / ~60k domain rows: the writers cut the genes into chunks that threads format and place with pwrite at
     chained offsets; one thread or eight, the files are the same bytes, and every row is the restatement's row."""
