@@ -693,10 +693,6 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
     timer.mark("parse + annotate features");
     // group by gene keeping the row order (counting sort), then order every gene's rows by (start, end), stable
     t->dom_ptr.assign(G + 1, 0);
-    for (const DomainRow &d : drows)
-        if (d.gene >= 0) ++t->dom_ptr[(size_t)d.gene + 1];
-    for (size_t g = 0; g < G; ++g) t->dom_ptr[g + 1] += t->dom_ptr[g];
-    t->domains.resize((size_t)t->dom_ptr[G]);
     {
         // Rows that already arrive in gene order (sorted tables: the usual case) only need compaction, which every
         // thread can do for its own slice; otherwise a sequential, order-preserving scatter.
@@ -737,12 +733,32 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             kept[k + 1] += kept[k];
         }
         if (in_order) {
+            // compaction per slice; the row pointers follow from where the gene changes in the compacted rows:
+            // dom_ptr[g] = first kept row of a gene >= g, filled slice by slice (a slice owns the genes from the one
+            // after the previous kept row's up to its own last row's)
+            t->domains.resize(kept[nt]);
             in_threads([&](int k) {
                 DomainRow *out = t->domains.data() + kept[k];
-                for (size_t i = R * k / nt; i < R * (k + 1) / nt; ++i)
-                    if (drows[i].gene >= 0) *out++ = drows[i];
+                int32_t prev_gene = -1;  // gene of the last kept row in front of this slice
+                for (int j = k - 1; j >= 0 && prev_gene < 0; --j) prev_gene = last[j];
+                size_t pos = kept[k];
+                for (size_t i = R * k / nt; i < R * (k + 1) / nt; ++i) {
+                    const int32_t g = drows[i].gene;
+                    if (g < 0) continue;
+                    *out++ = drows[i];
+                    for (int32_t q = prev_gene + 1; q <= g; ++q) t->dom_ptr[(size_t)q] = (int64_t)pos;
+                    prev_gene = g;
+                    ++pos;
+                }
             });
+            int32_t last_gene = -1;
+            for (int j = nt - 1; j >= 0 && last_gene < 0; --j) last_gene = last[j];
+            for (size_t q = (size_t)(last_gene + 1); q <= G; ++q) t->dom_ptr[q] = (int64_t)kept[nt];
         } else {
+            for (const DomainRow &d : drows)
+                if (d.gene >= 0) ++t->dom_ptr[(size_t)d.gene + 1];
+            for (size_t g = 0; g < G; ++g) t->dom_ptr[g + 1] += t->dom_ptr[g];
+            t->domains.resize((size_t)t->dom_ptr[G]);
             std::vector<int64_t> cursor(t->dom_ptr.begin(), t->dom_ptr.end() - 1);
             for (const DomainRow &d : drows)
                 if (d.gene >= 0) t->domains[(size_t)cursor[(size_t)d.gene]++] = d;
@@ -1241,10 +1257,15 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
     if (row_prob && t->packed_mode < 0) return tfail(GCRF_EINVAL, "gcrf_table_pack has not been called");
     const size_t G = t->genes.size();
     PhaseTimer timer;
-    // per-domain probability: the gene's value in protein mode, the row's own in domain mode
-    std::vector<double> dp(t->domains.size(), std::numeric_limits<double>::quiet_NaN());
+    // per-domain probability: the gene's value in protein mode (row g of row_prob: read in place), the row's own in
+    // domain mode (a per-domain array, since domain-less genes own a row too)
+    const bool protein_rows = row_prob && t->packed_mode == 0;
+    std::vector<double> dp;
     bool any = false;
-    if (row_prob) {
+    if (protein_rows) {
+        for (size_t g = 0; g < G && !any; ++g) any = t->dom_ptr[g] != t->dom_ptr[g + 1] && !std::isnan(row_prob[g]);
+    } else if (row_prob) {
+        dp.assign(t->domains.size(), std::numeric_limits<double>::quiet_NaN());
         int64_t cursor = 0;
         for (size_t g = 0; g < G; ++g) {
             const int64_t b = t->dom_ptr[g], e = t->dom_ptr[g + 1];
@@ -1262,7 +1283,7 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
     if (any) header += "\tcluster_probability";
     header += '\n';
     const size_t per_gene = G ? 160 * (t->domains.size() / G + 1) : 160;
-    const bool per_gene_prob = t->packed_mode == 0;  // protein mode: every domain row of a gene carries the gene's value
+    const bool per_gene_prob = protein_rows;  // protein mode: every domain row of a gene carries the gene's value
     return write_by_genes(path, header, G, per_gene, [&](std::string &out, size_t g) {
         const GeneRow &r = t->genes[g];
         const int64_t b = t->dom_ptr[g], e = t->dom_ptr[g + 1];
@@ -1283,8 +1304,8 @@ int gcrf_table_write_features(const gcrf_table *t, const double *row_prob, const
         char prob[40];
         size_t prob_len = 0;
         std::string tmp;
-        if (any && per_gene_prob && !std::isnan(dp[(size_t)b])) {
-            append_repr(tmp, dp[(size_t)b]);
+        if (any && per_gene_prob && !std::isnan(row_prob[g])) {
+            append_repr(tmp, row_prob[g]);
             prob_len = std::min(tmp.size(), sizeof(prob));
             memcpy(prob, tmp.data(), prob_len);
         }
