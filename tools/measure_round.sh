@@ -7,6 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r1_gpu_tests.txt 2>
 python bench.py > gpurun_out/r1_bench_1gpu.json 2> gpurun_out/r1_bench_1gpu.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 timeout 120 python tools/features_time.py > gpurun_out/r1_features_time.txt 2>&1
+timeout 200 python tools/predict_tables_time.py 300000 3.0 > gpurun_out/r1_predict_tables_time.txt 2>&1
 if [ "$mode" = full ]; then
   python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/r1_bench_reference.json 2>> gpurun_out/r1_bench_1gpu.err
   timeout 300 python tools/bench_configs.py > gpurun_out/r1_configs_kernel_only.jsonl 2>&1
