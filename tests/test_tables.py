@@ -457,3 +457,78 @@ def test_the_abi_from_plain_c(bgc, tmp_path):
         assert fields["first_contig"] == tables.contig_ids[0]
         tables.write_genes(tmp_path / "p.genes.tsv")
     assert (tmp_path / "o.genes.tsv").read_bytes() == (tmp_path / "p.genes.tsv").read_bytes()
+
+
+class StandInEngine:
+    """What FeatureTables / predict_tables ask of CRFEngine, answered on the CPU: marginals from the oracle (after the
+    device's feature extraction restated on arrays when the batch holds accessions), segments from the refine oracle."""
+
+    has_vocabulary = True
+    vocabulary_digits = 5
+
+    def __init__(self, weights):
+        self.weights = weights
+        self.accession_batches = 0
+
+    def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window, step, pad, accessions=False):
+        from oracle import crf_oracle
+
+        gene_ptr, attr_idx = numpy.asarray(gene_ptr), numpy.asarray(attr_idx)
+        if accessions:
+            self.accession_batches += 1
+            number = {int(a[2:]): i for i, a in enumerate(self.weights.attrs)}
+            ids, ptr = [], [0]
+            for r in range(len(gene_ptr) - 1):
+                seen = []
+                for a in attr_idx[gene_ptr[r]:gene_ptr[r + 1]].tolist():
+                    if a in number and number[a] not in seen:
+                        seen.append(number[a])
+                ids.extend(seen)
+                ptr.append(len(ids))
+            gene_ptr, attr_idx = numpy.array(ptr, dtype=numpy.int32), numpy.array(ids, dtype=numpy.int32)
+        p, _ = crf_oracle.marginals_windowed(self.weights.state_w, self.weights.trans_w, self.weights.label_id("1"),
+                                             numpy.asarray(contig_ptr), gene_ptr, attr_idx, window, step, pad)
+        return p
+
+    def segments(self, contig_ptr, prob, annotated, *, threshold, n_cds, edge_distance, trim, reset_per_contig):
+        from gecco_b200._lib import Segments
+        from oracle import refine_oracle
+
+        found = refine_oracle.extract_clusters(contig_ptr, prob, annotated, threshold, n_cds, edge_distance, trim, reset_per_contig)
+        seg = Segments(len(found)).truncated(len(found))
+        for k, (c, b, e, o, a, m) in enumerate(found):
+            seg.contig[k], seg.begin[k], seg.end[k], seg.ordinal[k], seg.average_p[k], seg.max_p[k] = c, b, e, o, a, m
+        return seg
+
+
+@pytest.mark.parametrize("host_features", ["0", "1"])
+def test_predict_tables_plumbing_on_the_cpu(bgc, weights, tmp_path, monkeypatch, host_features):
+    """predict_tables end to end with the device replaced by the oracles: tables in, the reference's golden genes /
+    features / clusters tables out — through the accession batch (feature extraction left to the engine) and through
+    the host packer."""
+    from gecco_b200.crf import ClusterCRF
+    from gecco_b200.tables import predict_tables
+
+    monkeypatch.setenv("GECCO_B200_HOST_FEATURES", host_features)
+    gtext, ftext = bgc_tables(bgc, shuffle=5)
+    (tmp_path / "BGC0001866.genes.tsv").write_text(gtext)
+    (tmp_path / "BGC0001866.features.tsv").write_text(ftext)
+    crf = ClusterCRF.trained()
+    crf._engine = StandInEngine(weights)
+    tables, prob = predict_tables(tmp_path / "BGC0001866.genes.tsv", tmp_path / "BGC0001866.features.tsv", tmp_path / "out", model=crf)
+    assert crf._engine.accession_batches == (1 if host_features == "0" else 0)
+    golden = numpy.array([g["average_p"] for g in bgc["genes"]])
+    assert numpy.abs(prob - golden).max() <= 1e-12
+    rows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.genes.tsv").read_text())
+    assert [r["protein_id"] for r in rows] == [g["protein_id"] for g in bgc["genes"]]
+    frows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.features.tsv").read_text())
+    assert len(frows) == 37 and all(abs(float(r["cluster_probability"]) - d["cluster_probability"]) <= 1e-12
+                                    for r, d in zip(frows, bgc["domains"]))
+    clusters = tables.segments(crf, prob, threshold=0.8, n_cds=3)
+    assert len(clusters) == 1 and clusters[0][0] == "BGC0001866.1"  # tests/test_cli/test_run.py:68-70
+    crows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.clusters.tsv").read_text())
+    want = bgc["clusters"][0]
+    assert len(crows) == 1 and all(crows[0][k] == want[k] for k in ("sequence_id", "cluster_id"))
+    assert (int(crows[0]["start"]), int(crows[0]["end"])) == (want["start"], want["end"])
+    assert abs(float(crows[0]["average_p"]) - float(want["average_p"])) <= 1e-12
+    tables.close()
