@@ -522,31 +522,65 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
     std::vector<int32_t> contig_of(G);
     std::vector<sv> ids;  // distinct sequence ids in order of first appearance
     {
-        auto id_of = [&](int32_t c) { return ids[(size_t)c]; };
-        NameIndex seen;
-        seen.reserve(1024);
-        sv last;
-        int32_t last_id = -1;
-        for (size_t i = 0; i < G; ++i) {
-            if (last_id >= 0 && rows[i].seq == last) {  // tables are usually grouped by contig
-                contig_of[i] = last_id;
-                continue;
+        // Runs of equal ids (tables are usually grouped by contig) are found by all threads; the first row of every run
+        // is a candidate, candidates are de-duplicated through a concurrently filled name index, and the smallest
+        // candidate of a name stands for it — the ids come out in order of first appearance whatever the thread timing.
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, G / 50000));
+        auto in_threads = [&](auto &&fn) {
+            if (nt <= 1) {
+                fn(0);
+                return;
             }
-            int32_t c = seen.find(rows[i].seq, id_of);
-            if (c < 0) {
-                c = (int32_t)ids.size();
-                ids.push_back(rows[i].seq);
-                if (2 * ids.size() + 2 > seen.capacity()) {  // grow and re-insert
-                    seen.reserve(4 * ids.size());
-                    for (size_t k = 0; k < ids.size(); ++k) seen.insert(ids[k], (int32_t)k, id_of);
-                } else {
-                    seen.insert(rows[i].seq, c, id_of);
+            std::vector<std::thread> pool;
+            for (int k = 0; k < nt; ++k) pool.emplace_back(fn, k);
+            for (auto &th : pool) th.join();
+        };
+        std::vector<std::vector<int32_t>> starts((size_t)nt);
+        in_threads([&](int k) {
+            const size_t i0 = G * (size_t)k / (size_t)nt, i1 = G * (size_t)(k + 1) / (size_t)nt;
+            for (size_t i = i0; i < i1; ++i)
+                if (i == i0 || rows[i].seq != rows[i - 1].seq) starts[(size_t)k].push_back((int32_t)i);
+        });
+        std::vector<size_t> first_cand((size_t)nt + 1, 0);
+        for (int k = 0; k < nt; ++k) first_cand[(size_t)k + 1] = first_cand[(size_t)k] + starts[(size_t)k].size();
+        const size_t ncand = first_cand[(size_t)nt];
+        std::vector<int32_t> cand(ncand), canon(ncand);
+        for (int k = 0; k < nt; ++k) std::copy(starts[(size_t)k].begin(), starts[(size_t)k].end(), cand.begin() + (std::ptrdiff_t)first_cand[(size_t)k]);
+        auto name_of = [&](int32_t c) { return rows[(size_t)cand[(size_t)c]].seq; };
+        NameIndex seen;
+        seen.reserve(ncand);
+        std::vector<char> fresh(ncand, 0);
+        in_threads([&](int k) {
+            for (size_t c = first_cand[(size_t)k]; c < first_cand[(size_t)k + 1]; ++c)
+                fresh[c] = seen.insert(name_of((int32_t)c), (int32_t)c, name_of) ? 1 : 0;
+        });
+        // every candidate learns which one holds its name in the index; the smallest of a name becomes its canonical one
+        std::vector<int32_t> smallest(ncand);
+        std::iota(smallest.begin(), smallest.end(), 0);
+        in_threads([&](int k) {
+            for (size_t c = first_cand[(size_t)k]; c < first_cand[(size_t)k + 1]; ++c) {
+                const int32_t holder = fresh[c] ? (int32_t)c : seen.find(name_of((int32_t)c), name_of);
+                canon[c] = holder;
+                int32_t cur = __atomic_load_n(&smallest[(size_t)holder], __ATOMIC_RELAXED);
+                while ((int32_t)c < cur &&
+                       !__atomic_compare_exchange_n(&smallest[(size_t)holder], &cur, (int32_t)c, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
                 }
             }
-            contig_of[i] = c;
-            last = rows[i].seq;
-            last_id = c;
-        }
+        });
+        std::vector<int32_t> id_of_cand(ncand, -1);
+        for (size_t c = 0; c < ncand; ++c)
+            if (smallest[(size_t)canon[c]] == (int32_t)c) {
+                id_of_cand[c] = (int32_t)ids.size();
+                ids.push_back(name_of((int32_t)c));
+            }
+        in_threads([&](int k) {
+            const size_t i1 = G * (size_t)(k + 1) / (size_t)nt;
+            for (size_t c = first_cand[(size_t)k]; c < first_cand[(size_t)k + 1]; ++c) {
+                const int32_t id = id_of_cand[(size_t)smallest[(size_t)canon[c]]];
+                const size_t e = c + 1 < first_cand[(size_t)k + 1] ? (size_t)cand[c + 1] : i1;
+                for (size_t i = (size_t)cand[c]; i < e; ++i) contig_of[i] = id;
+            }
+        });
     }
     const size_t C = ids.size();
     std::vector<int32_t> by_id(C), rank_of(C);
