@@ -390,7 +390,11 @@ struct gcrf_table {
     // genes, in the reference's order (sequence_id, start, end)
     RowVector<GeneRow> genes;
     std::vector<int32_t> contig_ptr;           // [C+1] into genes
-    std::vector<std::string> contig_ids;       // [C]
+    // contig c is called genes[contig_ptr[c]].seq; NUL-terminated copies are made when gcrf_table_contig_id first asks
+    // (a metagenome table has a million of them)
+    mutable std::vector<std::string> contig_ids;
+    size_t contigs() const { return genes.empty() ? 0 : contig_ptr.size() - 1; }
+    sv contig_name(size_t c) const { return genes[(size_t)contig_ptr[c]].seq; }
     std::vector<std::string> gene_ids;         // [G] NUL-terminated copies, built lazily for the accessor
     // domain rows kept by the filters, grouped by gene, ordered by (domain_start, domain_end)
     RowVector<DomainRow> domains;
@@ -582,6 +586,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             }
         });
     }
+    timer.mark("  distinct contig ids");
     const size_t C = ids.size();
     std::vector<int32_t> by_id(C), rank_of(C);
     std::iota(by_id.begin(), by_id.end(), 0);
@@ -615,6 +620,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
         }
     }
     for (size_t r = 0; r < C; ++r) rank_of[(size_t)by_id[r]] = (int32_t)r;
+    timer.mark("  rank contig ids");
     t->contig_ptr.assign(C + 1, 0);
     for (size_t i = 0; i < G; ++i) ++t->contig_ptr[(size_t)rank_of[(size_t)contig_of[i]] + 1];
     for (size_t r = 0; r < C; ++r) t->contig_ptr[r + 1] += t->contig_ptr[r];
@@ -649,6 +655,7 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             for (auto &th : pool) th.join();
         }
     }
+    timer.mark("  bucket + sort inside contigs");
     std::vector<int32_t> rank(G);
     t->genes.resize(G);
     {
@@ -667,8 +674,6 @@ void build(gcrf_table *t, sv genes_buf, const std::vector<sv> &feature_bufs, dou
             for (auto &th : pool) th.join();
         }
     }
-    t->contig_ids.reserve(C);
-    for (size_t r = 0; r < C; ++r) t->contig_ids.emplace_back(ids[(size_t)by_id[r]]);
     if (G == 0) t->contig_ptr.assign(1, 0);
     timer.mark("sort genes, contigs");
 
@@ -995,12 +1000,16 @@ int gcrf_table_parse(const char *genes, uint64_t genes_len, const char *const *f
 
 void gcrf_table_destroy(gcrf_table *t) { delete t; }
 
-int64_t gcrf_table_contigs(const gcrf_table *t) { return t ? (int64_t)t->contig_ids.size() : 0; }
+int64_t gcrf_table_contigs(const gcrf_table *t) { return t ? (int64_t)t->contigs() : 0; }
 int64_t gcrf_table_genes(const gcrf_table *t) { return t ? (int64_t)t->genes.size() : 0; }
 int64_t gcrf_table_domains(const gcrf_table *t) { return t ? (int64_t)t->domains.size() : 0; }
 
 const char *gcrf_table_contig_id(const gcrf_table *t, int64_t c) {
-    if (!t || c < 0 || c >= (int64_t)t->contig_ids.size()) return nullptr;
+    if (!t || c < 0 || c >= (int64_t)t->contigs()) return nullptr;
+    if (t->contig_ids.empty()) {
+        t->contig_ids.reserve(t->contigs());
+        for (size_t k = 0; k < t->contigs(); ++k) t->contig_ids.emplace_back(t->contig_name(k));
+    }
     return t->contig_ids[(size_t)c].c_str();
 }
 
@@ -1038,7 +1047,7 @@ int gcrf_table_pack(gcrf_table *t, const char *const *attr_names, int32_t A, int
             if (!attr_names[a]) return tfail(GCRF_EINVAL, "attribute name %d is NULL", a);
             if (!vocab.emplace(sv(attr_names[a]), a).second) return tfail(GCRF_EINVAL, "attribute %s appears twice", attr_names[a]);
         }
-        const size_t G = t->genes.size(), C = t->contig_ids.size();
+        const size_t G = t->genes.size(), C = t->contigs();
         t->row_ptr.assign(1, 0);
         t->attr_idx.clear();
         t->row_gene.clear();
@@ -1094,7 +1103,7 @@ int gcrf_table_pack_accessions(gcrf_table *t, int32_t feature_type, int32_t digi
     if (digits < 0 || digits > 9) return tfail(GCRF_EINVAL, "digits must be 0..9");
     if (feature_type != 0 && feature_type != 1) return tfail(GCRF_EINVAL, "invalid feature type: %d", feature_type);
     try {
-        const size_t G = t->genes.size(), C = t->contig_ids.size(), D = t->domains.size();
+        const size_t G = t->genes.size(), C = t->contigs(), D = t->domains.size();
         if (D > 0x7fffff00u || G + D > 0x7fffff00u) return tfail(GCRF_EINVAL, "table too large for int32 row pointers; shard it");
         // "PF" + digits -> the number; anything else is not in a Pfam-only vocabulary
         t->attr_idx.resize(D);
@@ -1235,9 +1244,9 @@ int gcrf_table_write_clusters(const gcrf_table *t, const double *row_prob, const
     std::vector<sv> names;
     for (int64_t k = 0; k < n_segments; ++k) {
         const int64_t c = seg_contig[k], b = seg_begin[k], e = seg_end[k];
-        if (c < 0 || c >= (int64_t)t->contig_ids.size() || b < 0 || e > (int64_t)G || b >= e)
+        if (c < 0 || c >= (int64_t)t->contigs() || b < 0 || e > (int64_t)G || b >= e)
             return tfail(GCRF_EINVAL, "segment %lld is out of range", (long long)k);
-        const std::string &seq = t->contig_ids[(size_t)c];
+        const sv seq = t->contig_name((size_t)c);
         int64_t start = t->genes[(size_t)b].start, end = t->genes[(size_t)b].end;
         long double sum = 0;
         double best = std::numeric_limits<double>::quiet_NaN();
