@@ -1,0 +1,71 @@
+"""The shipped library's machine code holds what DESIGN.md says it does (cuobjdump on the in-tree .so; no GPU needed)."""
+import pathlib
+import re
+import shutil
+import subprocess
+
+import pytest
+
+LIB = pathlib.Path(__file__).resolve().parent.parent / "gecco_b200" / "libgecco_crf_b200.so"
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if shutil.which("cuobjdump") is None or not LIB.exists():
+        pytest.skip("cuobjdump or the built library is missing")
+    text = subprocess.run(["cuobjdump", "-sass", str(LIB)], check=True, capture_output=True, text=True).stdout
+    functions, name = {}, None
+    for line in text.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            functions[name] = []
+        elif name is not None and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            functions[name].append(line.split("*/", 1)[1].strip())
+    archs = set(re.findall(r"arch = (\S+)", text))
+    return functions, archs
+
+
+def find(functions, *parts):
+    hits = [body for name, body in functions.items() if all(p in name for p in parts)]
+    assert hits, parts
+    return hits
+
+
+def count(body, mnemonic):
+    return sum(1 for ins in body if re.search(rf"(^|\s){re.escape(mnemonic)}", ins))
+
+
+def test_built_for_sm_100a_only(sass):
+    _, archs = sass
+    assert archs == {"sm_100a"}
+
+
+def test_streaming_kernel_uses_bulk_copies_mbarriers_and_packed_math(sass):
+    """ids and the delta table arrive by cp.async.bulk (UBLKCP) on mbarriers (SYNCS), the DP runs on packed
+    f32x2 instructions with MUFU reciprocals / exponentials, outputs leave as 64-bit stores."""
+    functions, _ = sass
+    for body in find(functions, "stream_kernel", "ILi20E"):
+        assert count(body, "UBLKCP") >= 2 and count(body, "SYNCS.PHASECHK") >= 1
+        assert count(body, "FFMA2") >= 40 and count(body, "FMUL2") >= 40
+        assert count(body, "MUFU.RCP") >= 40 and count(body, "MUFU.EX2") >= 1
+        assert count(body, "STG.E.64") >= 1
+        assert not any("LDL" in ins or "STL" in ins for ins in body), "no register spills in the hot kernel"
+
+
+def test_feature_kernel_is_branch_light_and_works_in_shared_memory(sass):
+    """uniform loop bounds through REDUX (no BRA.DIV in front of the shuffles), shared-memory atomics for
+    the bitmaps, the staged uint16 table, streaming loads / stores, 16-byte bitmap wipes."""
+    functions, _ = sass
+    staged = find(functions, "features_kernel", "Li8ELi8ELi512ELb1E")
+    for body in staged:
+        assert count(body, "BRA.DIV") == 0
+        assert count(body, "CREDUX") + count(body, "REDUX") >= 3
+        assert count(body, "ATOMS.OR") >= 8
+        assert count(body, "LDS.U16") >= 8
+        assert count(body, "STS.128") >= 1
+        assert any(ins.startswith("@") and "STG.E.EF" in ins for ins in body), "predicated streaming stores"
+        assert any("LDG.E.EF" in ins for ins in body)
+        assert not any("LDL" in ins or "STL" in ins for ins in body)
+    for body in find(functions, "features_kernel", "Li32ELi2ELi256ELb0E"):  # sparse tables: hashed bitmaps
+        assert count(body, "BRA.DIV") == 0 and count(body, "ATOMS.OR") >= 2
