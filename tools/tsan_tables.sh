@@ -1,4 +1,4 @@
-# ThreadSanitizer over the native table path (gcrf_tables.cpp is host-only C++: built here without the CUDA part).
+# ThreadSanitizer (SANITIZE=address,undefined for ASan + UBSan) over the native table path (gcrf_tables.cpp is host-only C++: built here without the CUDA part).
 # Usage: bash tools/tsan_tables.sh genes.tsv features.tsv      (e.g. the tables tools/tables_time.py generates)
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
@@ -29,11 +29,12 @@ int main(int argc, char **argv) {
     printf("ok contigs=%lld genes=%lld domains=%lld rows(domain mode)=%lld id0=%s\n", (long long)gcrf_table_contigs(t),
            (long long)gcrf_table_genes(t), (long long)gcrf_table_domains(t), (long long)rows, gcrf_table_contig_id(t, 0));
     gcrf_table_destroy(t);
+    free(prob);
     return 0;
 }
 MAIN
-g++ -std=c++17 -O1 -g -fsanitize=thread -fPIC -pthread -c $ROOT/gecco_b200/csrc/gcrf_tables.cpp -o $TMP/tables.o
-gcc -std=c99 -O1 -g -fsanitize=thread -I$ROOT/include -c $TMP/main.c -o $TMP/main.o
+g++ -std=c++17 -O1 -g -fsanitize=${SANITIZE:-thread} -fPIC -pthread -c $ROOT/gecco_b200/csrc/gcrf_tables.cpp -o $TMP/tables.o
+gcc -std=c99 -O1 -g -fsanitize=${SANITIZE:-thread} -I$ROOT/include -c $TMP/main.c -o $TMP/main.o
 gcc -c $TMP/stubs.c -o $TMP/stubs.o
-g++ -fsanitize=thread -pthread $TMP/tables.o $TMP/main.o $TMP/stubs.o -o $TMP/tsan_tables -lm
+g++ -fsanitize=${SANITIZE:-thread} -pthread $TMP/tables.o $TMP/main.o $TMP/stubs.o -o $TMP/tsan_tables -lm
 GCRF_TABLE_THREADS=${GCRF_TABLE_THREADS:-8} $TMP/tsan_tables "$@"
