@@ -24,6 +24,7 @@ GCRF_FLAG_PROB_F32 = 0x8
 GCRF_FLAG_RESET_PER_CONTIG = 0x10
 GCRF_FLAG_IDX_U16 = 0x20
 GCRF_FLAG_ACCESSIONS = 0x40
+GCRF_FLAG_F64 = 0x80
 
 # every symbol include/gecco_crf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTED_SYMBOLS = (
@@ -41,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "gcrf_segments",
     "gcrf_host_alloc",
     "gcrf_host_free",
+    "gcrf_max_window",
     "gcrf_model_launch_count",
     "gcrf_model_set_timing",
     "gcrf_model_last_kernel_ms",
@@ -127,6 +129,8 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_host_alloc.argtypes = [ctypes.POINTER(vp), u64]
     lib.gcrf_host_free.restype = ctypes.c_int
     lib.gcrf_host_free.argtypes = [vp]
+    lib.gcrf_max_window.restype = i32
+    lib.gcrf_max_window.argtypes = [vp, i32]
     lib.gcrf_model_launch_count.restype = i64
     lib.gcrf_model_launch_count.argtypes = [vp]
     lib.gcrf_model_set_timing.restype = ctypes.c_int
@@ -304,11 +308,14 @@ class CRFEngine:
     # ------------------------------------------------------------------ host-pointer calls
     def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window: Optional[int] = None,
                            step: Optional[int] = None, pad: bool = True, out: Optional[numpy.ndarray] = None,
-                           f32: bool = False, accessions: bool = False) -> numpy.ndarray:
+                           f32: bool = False, accessions: bool = False, f64_arith: bool = False) -> numpy.ndarray:
         """Per-gene cluster probability (``gcrf_marginals_windowed``, host buffers, blocking).  ``accessions``:
         ``attr_idx`` holds integer domain accessions, one row per domain in domain-start order; they are mapped to
-        attribute ids and de-duplicated per gene on the device (``GCRF_FLAG_ACCESSIONS``)."""
+        attribute ids and de-duplicated per gene on the device (``GCRF_FLAG_ACCESSIONS``).  ``f64_arith``: compute in
+        the reference's own f64 arithmetic (``GCRF_FLAG_F64``) instead of FP32."""
         contig_ptr, gene_ptr, attr_idx, flags = self._host_csr(contig_ptr, gene_ptr, attr_idx)
+        if f64_arith:
+            flags |= GCRF_FLAG_F64
         if accessions:
             if not self.has_vocabulary:
                 raise ValueError("the model's attributes are not Pfam-style accessions; pack attribute ids on the host")
@@ -426,6 +433,10 @@ class CRFEngine:
 
     def synchronize(self) -> None:
         _check(self._lib, self._lib.gcrf_model_synchronize(self._handle))
+
+    def max_window(self, f64_arith: bool = False) -> int:
+        """Largest ``window`` the device path accepts for this model (``gcrf_max_window``)."""
+        return int(self._lib.gcrf_max_window(self._handle, int(bool(f64_arith))))
 
     @property
     def launch_count(self) -> int:

@@ -20,6 +20,12 @@ Differences from the reference, all deliberate:
 * ``feature_type="domain"`` sizes the probability vector by the number of feature rows.  The reference sizes it
   by genes and fails with a shape error as soon as a gene has two domains (``:251`` vs ``:254``).
 * ``progress`` is called with ``(0, total)`` and ``(total, total)`` — the windows are not evaluated one by one.
+* arithmetic: the drop-in computes in f64 like the reference's tagger (``GCRF_FLAG_F64``; results within 1e-12 of
+  python-crfsuite's, so thresholded cluster calls cannot flip) — the Python object handling around the call costs
+  orders of magnitude more than the wider arithmetic.  ``GECCO_B200_ARITHMETIC=f32`` (or ``crf.arithmetic = "f32"``)
+  selects the FP32 streaming kernels of the bulk array API (within 1e-5).
+* any ``window_size`` works, like in the reference (``:134-137``): sizes beyond what the FP32 kernels hold in shared
+  memory (``CRFEngine.max_window``: 128 for Pfam-sized models) run the f64 path.
 * training (``fit`` / ``save``) is delegated to the reference class when GECCO and sklearn-crfsuite are
   installed; it is out of scope here.
 """
@@ -89,6 +95,7 @@ class ClusterCRF(object):
         weights = model_io.load_model(model_path)
         self = cls(weights.feature_type, window_size=weights.window_size, window_step=weights.window_step)
         self._set_weights(weights)
+
         extra = weights.extra or {}
         self.algorithm = extra.get("algorithm") or self.algorithm
         self.significance = extra.get("significance")
@@ -115,6 +122,9 @@ class ClusterCRF(object):
         self._weights: Optional[CRFWeights] = None
         self._engine = None
         self.device = int(os.environ.get("GECCO_B200_DEVICE", "0"))
+        self.arithmetic = os.environ.get("GECCO_B200_ARITHMETIC", "f64")
+        if self.arithmetic not in ("f32", "f64"):
+            raise ValueError(f"invalid arithmetic: {self.arithmetic!r} (expected 'f32' or 'f64')")
 
     def _set_weights(self, weights: CRFWeights) -> None:
         self._weights = weights
@@ -128,14 +138,26 @@ class ClusterCRF(object):
 
             assert self._weights is not None
             self._engine = CRFEngine(self._weights, device=self.device)
+            self._check_window(self._engine)
         return self._engine
+
+    def _check_window(self, engine) -> None:
+        # the reference accepts any window_size >= 1 (gecco/crf/__init__.py:134-137) and so does the f64 path; the
+        # FP32 kernels keep a window's state in shared memory and stop at engine.max_window() (128 for Pfam-sized models)
+        if self.arithmetic == "f32" and self.window_size > engine.max_window(False):
+            warnings.warn(f"window_size {self.window_size} exceeds the FP32 kernels' limit ({engine.max_window(False)}); "
+                          "using the f64 path")
+            self.arithmetic = "f64"
 
     def marginals(self, packed: PackedGenes, *, pad: bool = True) -> numpy.ndarray:
         """Bulk entry point: per-row cluster probability of an already packed batch (NaN = skipped contig)."""
         if self.model is None:
             raise NotFittedError("This ClusterCRF instance is not fitted yet.")
         extra = {"accessions": True} if getattr(packed, "accessions", False) else {}
-        return self._get_engine().marginals_windowed(packed.contig_ptr, packed.gene_ptr, packed.attr_idx,
+        engine = self._get_engine()
+        if self.arithmetic == "f64":
+            extra["f64_arith"] = True
+        return engine.marginals_windowed(packed.contig_ptr, packed.gene_ptr, packed.attr_idx,
                                                      window=self.window_size, step=self.window_step, pad=pad, **extra)
 
     # ------------------------------------------------------------------ the hot path

@@ -72,6 +72,9 @@ struct gcrf_model {
     int32_t lut_size = 0;
     double *d_table64 = nullptr;
     double m01 = 0, m10 = 0, m11 = 0;
+    double *d_state_w = nullptr;  // [A][2] raw state weights (GCRF_FLAG_F64)
+    double exp_trans[4] = {0, 0, 0, 0};
+    int32_t pos_label = 1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -85,6 +88,7 @@ struct gcrf_model {
     int64_t launches = 0;
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
+    DeviceBuffer b_unary, b_pool, b_work;  // GCRF_FLAG_F64: exp of the state scores, max-pool (float output), work area
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
     DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
 };
@@ -103,7 +107,17 @@ struct DeviceGuard {
     }
 };
 
-// Host-side sanity checks of a CSR batch given as host pointers (cheap, O(C)).
+// gene_ptr non-decreasing: branch-free OR-reduction of the sign of every difference (a pass at memory speed:
+// ~1 ms for the 8 MB of config 2, against a PCIe-bound call of several ms)
+template <typename T>
+bool non_decreasing(const T *p, int64_t n) {
+    T bad = 0;
+    for (int64_t i = 0; i < n; ++i) bad |= (T)(p[i + 1] - p[i]);
+    return bad >= 0;
+}
+
+// Host-side sanity checks of a CSR batch given as host pointers: O(C + G), so that no malformed pointer array can
+// send the kernels out of bounds.
 int check_host_csr(const int32_t *contig_ptr, const void *gene_ptr, bool ptr64, int64_t C, int64_t G, int64_t nnz) {
     if (contig_ptr[0] != 0 || contig_ptr[C] != G) return fail(GCRF_EINVAL, "contig_ptr must start at 0 and end at G");
     for (int64_t c = 0; c < C; ++c)
@@ -111,6 +125,14 @@ int check_host_csr(const int32_t *contig_ptr, const void *gene_ptr, bool ptr64, 
     const int64_t first = ptr64 ? static_cast<const int64_t *>(gene_ptr)[0] : static_cast<const int32_t *>(gene_ptr)[0];
     const int64_t last = ptr64 ? static_cast<const int64_t *>(gene_ptr)[G] : static_cast<const int32_t *>(gene_ptr)[G];
     if (first != 0 || last != nnz) return fail(GCRF_EINVAL, "gene_ptr must start at 0 and end at nnz");
+    const bool mono = ptr64 ? non_decreasing(static_cast<const int64_t *>(gene_ptr), G) : non_decreasing(static_cast<const int32_t *>(gene_ptr), G);
+    if (!mono) {
+        for (int64_t g = 0; g < G; ++g) {
+            const int64_t a = ptr64 ? static_cast<const int64_t *>(gene_ptr)[g] : static_cast<const int32_t *>(gene_ptr)[g];
+            const int64_t b = ptr64 ? static_cast<const int64_t *>(gene_ptr)[g + 1] : static_cast<const int32_t *>(gene_ptr)[g + 1];
+            if (b < a) return fail(GCRF_EINVAL, "gene_ptr must be non-decreasing (gene %lld: %lld > %lld)", (long long)g, (long long)a, (long long)b);
+        }
+    }
     return GCRF_OK;
 }
 
@@ -317,6 +339,14 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
     m->m01 = m01;
     m->m10 = m10;
     m->m11 = m11;
+    if (A > 0) {
+        if ((err = cudaMalloc(reinterpret_cast<void **>(&m->d_state_w), (size_t)A * 2 * sizeof(double))) != cudaSuccess)
+            return cleanup(fail_cuda(err, "cudaMalloc(state_w)"));
+        if ((err = cudaMemcpy(m->d_state_w, state_w, (size_t)A * 2 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return cleanup(fail_cuda(err, "cudaMemcpy(state_w)"));
+    }
+    for (int k = 0; k < 4; ++k) m->exp_trans[k] = std::exp(trans_w[k]);  // CRFsuite exponentiates the raw transition scores
+    m->pos_label = pos_label;
     if ((err = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return cleanup(fail_cuda(err, "cudaStreamCreate"));
     m->stream = m->own_stream;
@@ -353,6 +383,10 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_seg.release();
     m->b_idx16.release();
     m->b_acc.release();
+    m->b_unary.release();
+    m->b_pool.release();
+    m->b_work.release();
+    if (m->d_state_w) cudaFree(m->d_state_w);
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_table64) cudaFree(m->d_table64);
     if (m->d_table_fx) cudaFree(m->d_table_fx);
@@ -396,7 +430,8 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
     cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {
         cudaGetLastError();
-        return fail(GCRF_EUNSUPPORTED, "window size %d / %d attributes do not fit the fused kernel's shared memory", args.window, m->A);
+        return fail(GCRF_EUNSUPPORTED, "window size %d with %d attributes does not fit the FP32 kernels' shared memory (largest window: %d); "
+                    "GCRF_FLAG_F64 accepts any window", args.window, m->A, gcrf::windowed_max_window(m->A));
     }
     if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
     if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
@@ -497,7 +532,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     const bool prof = prof_env && prof_env[0] == '1';
     // host buffers, PCIe-bound size: overlap the two copy directions over contig-aligned slices
     int slices = 1;
-    if (!(flags & (GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_IDX_U16 | GCRF_FLAG_ACCESSIONS)) && !m->timing && !prof && C >= 2) {
+    if (!(flags & (GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_IDX_U16 | GCRF_FLAG_ACCESSIONS | GCRF_FLAG_F64)) && !m->timing && !prof && C >= 2) {
         const double bytes = 4.0 * (double)nnz + 12.0 * (double)G;
         const char *env = getenv("GCRF_HOST_SLICES");  // tuning / A-B: 1 turns the overlap off
         // Off unless asked for: on the PCIe Gen5 hosts measured (config 2, 207 MB in / 16 MB out) the D2H overlap
@@ -511,6 +546,36 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     Batch b;
     int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b, slices > 1);
     if (rc != GCRF_OK || G == 0) return rc;
+
+    if (flags & GCRF_FLAG_F64) {
+        // the reference's own arithmetic (gcrf_exact.cu)
+        gcrf::ExactArgs ex{};
+        ex.csr = b.csr;
+        ex.csr.gene_base = 0;
+        ex.A = m->A;
+        ex.state_w = m->d_state_w;
+        for (int k = 0; k < 4; ++k) ex.M[k] = m->exp_trans[k];
+        ex.pos_label = m->pos_label;
+        ex.window = window;
+        ex.step = step;
+        ex.pad = pad ? 1 : 0;
+        ex.out = b.d_out;
+        ex.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
+        GCRF_CUDA(m->b_unary.reserve((size_t)G * 2 * sizeof(double)));
+        ex.unary = static_cast<double *>(m->b_unary.ptr);
+        if (ex.out_f32) {
+            GCRF_CUDA(m->b_pool.reserve((size_t)G * sizeof(double)));
+            ex.pool = static_cast<double *>(m->b_pool.ptr);
+        }
+        const size_t work_bytes = gcrf::exact_work_bytes(G, window, m->num_sms);
+        if (work_bytes) GCRF_CUDA(m->b_work.reserve(work_bytes));
+        if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+        cudaError_t err = gcrf::launch_exact(ex, static_cast<double *>(m->b_work.ptr), m->num_sms, m->stream, &m->launches);
+        if (err != cudaSuccess) return fail_cuda(err, "launch_exact");
+        if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
+        m->timed = m->timing;
+        return finish_batch(m, b, out);
+    }
 
     gcrf::WindowedArgs args{};
     args.model = m->dev;
@@ -737,6 +802,11 @@ int gcrf_host_free(void *ptr) {
 }
 
 int64_t gcrf_model_launch_count(const gcrf_model *m) { return m ? m->launches : 0; }
+
+int32_t gcrf_max_window(const gcrf_model *m, int32_t f64) {
+    if (!m) return 0;
+    return f64 ? 0x7fffffff : gcrf::windowed_max_window(m->A);
+}
 
 int gcrf_model_set_timing(gcrf_model *m, int32_t enable) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");

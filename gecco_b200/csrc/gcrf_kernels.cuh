@@ -64,6 +64,25 @@ cudaError_t plan_windowed(const WindowedArgs &args, int num_sms, WindowedPlan *p
 // Enqueue the fused gather + windowed forward-backward + max-pool kernel.  *launches += kernels launched.
 cudaError_t launch_windowed(const WindowedArgs &args, const WindowedPlan &plan, cudaStream_t stream,
                             int64_t *launches);
+// Largest window the generic kernel's shared-memory layout holds for a model of A attributes.
+int windowed_max_window(int A);
+
+// GCRF_FLAG_F64 — the windowed marginals in the reference's own arithmetic (gcrf_exact.cu): CRFsuite's scaled
+// forward-backward in f64, operation by operation (restated on the CPU by the test oracle).
+struct ExactArgs {
+    CsrDev csr;
+    int32_t A;
+    const double *state_w;   // [A][2] state weights as given to gcrf_model_create (label-major pairs)
+    double M[4];             // exp(trans_w), from -> to
+    int32_t pos_label;
+    int32_t window, step, pad;
+    void *out;               // double[G] or float[G]
+    int32_t out_f32;
+    double *unary;           // [2*G] scratch: exp of the two state scores of every gene
+    double *pool;            // [G] scratch for the max-pool when out is float, else nullptr (pool straight into out)
+};
+size_t exact_work_bytes(int64_t G, int32_t window, int num_sms);  // global work area of runtime window sizes
+cudaError_t launch_exact(const ExactArgs &args, double *work, int num_sms, cudaStream_t stream, int64_t *launches);
 
 // Fast fused kernel for the compile-time window sizes (gcrf_stream.cu); same arguments and results.
 bool stream_supported(const WindowedArgs &args);

@@ -205,8 +205,10 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
         // c1 may exceed ngt: the contig continues outside the staged range)
         int c0 = 0, c1 = 0;
         if (tid < ngt) {
+            // sCp[ngt+1] > tid for a valid batch (contig_ptr strictly increasing); the bound also ends the search on
+            // a malformed device-pointer batch instead of spinning
             int hi = 1;
-            while (sCp[hi] <= tid) hi <<= 1, hi = hi > ngt + 1 ? ngt + 1 : hi;  // sCp[ngt+1] > tid always
+            while (hi < ngt + 1 && sCp[hi] <= tid) hi <<= 1, hi = hi > ngt + 1 ? ngt + 1 : hi;
             int lo_k = hi >> 1;
             if (sCp[lo_k] > tid) lo_k = 0;  // only when hi was clamped to a non power of two
             while (hi - lo_k > 1) {
@@ -352,6 +354,12 @@ cudaError_t configure(const Tiling &tl, int *ctas_per_sm) {
 }
 
 }  // namespace
+
+int windowed_max_window(int A) {
+    int w = kMaxWindow;
+    while (w > 1 && Tiling(A, w).bytes() > 227 * 1024) --w;
+    return w;
+}
 
 cudaError_t plan_windowed(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
     if (args.window <= 0 || args.window > kMaxWindow) return cudaErrorInvalidValue;

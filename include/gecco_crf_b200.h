@@ -65,6 +65,12 @@ typedef enum gcrf_status {
                                       through the vocabulary (gcrf_model_set_vocabulary) and de-duplicated per gene on
                                       the device first — gcrf_features_from_accessions and the marginals in one call
                                       (gecco/crf/features.py:13-35 + crf/__init__.py:253).  Not with GCRF_FLAG_IDX_U16 */
+#define GCRF_FLAG_F64         0x80u /* gcrf_marginals_windowed: the reference's own arithmetic — CRFsuite's scaled
+                                      forward-backward in f64 (floatval_t is double), operation by operation and without
+                                      fused multiply-adds, exp() correctly rounded: bit-identical to python-crfsuite's
+                                      output on the reference's golden fixture, within a few ulps of it elsewhere (the
+                                      residue is the host libm's rounding of exp).  Any window size.  Several times
+                                      slower than the default FP32 odds-ratio kernels, whose results stay within 1e-5 */
 #define GCRF_FLAG_PROB_F32    0x8u /* gcrf_segments: prob is float[G] instead of double[G] */
 #define GCRF_FLAG_RESET_PER_CONTIG 0x10u /* gcrf_segments: the in-cluster state starts at "out" in every
                                       contig, i.e. one ClusterRefiner.iter_clusters call per contig as
@@ -126,7 +132,11 @@ int gcrf_model_synchronize(gcrf_model *model);
  * Host-pointer mode (default): the call copies the inputs to the device, runs, copies `out` back
  * and returns when `out` is complete.  Device-pointer mode: see GCRF_FLAG_DEVICE_PTRS.
  * Result tolerance vs the f64 reference arithmetic: |dp| <= 1e-5 (FP32 device arithmetic;
- * measured <= 2e-6, tests/test_gpu_parity.py).
+ * measured <= 2e-6, tests/test_gpu_parity.py); with GCRF_FLAG_F64 <= 1e-12.
+ * Window sizes (the reference takes any window_size >= 1, gecco/crf/__init__.py:134-137): the FP32 kernels hold a
+ * window's state in shared memory — 5, 10 and 20 run the streaming kernel, other sizes up to gcrf_max_window(model, 0)
+ * (128, fewer for very large vocabularies) the generic one, larger ones fail with GCRF_EUNSUPPORTED; with
+ * GCRF_FLAG_F64 any window size works.
  */
 int gcrf_marginals_windowed(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
                             const void *attr_idx, int64_t C, int64_t G, int64_t nnz,
@@ -195,6 +205,9 @@ int gcrf_segments(gcrf_model *model, const int32_t *contig_ptr, const void *prob
  */
 int gcrf_host_alloc(void **ptr, uint64_t bytes);
 int gcrf_host_free(void *ptr);
+
+/* Largest `window` gcrf_marginals_windowed accepts for this model (f64 != 0: with GCRF_FLAG_F64 — INT32_MAX). */
+int32_t gcrf_max_window(const gcrf_model *model, int32_t f64);
 
 /* Number of kernel launches the handle has issued so far (for bench.py's gpu_launches). */
 int64_t gcrf_model_launch_count(const gcrf_model *model);

@@ -15,10 +15,14 @@ class OracleEngine:
         self.weights = weights
         self.calls = 0
 
-    def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window, step, pad):
+    def max_window(self, f64_arith=False):
+        return 2**31 - 1 if f64_arith else 128
+
+    def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window, step, pad, f64_arith=False):
         from oracle import crf_oracle
 
         self.calls += 1
+        self.f64_arith = f64_arith
         p, _ = crf_oracle.marginals_windowed(self.weights.state_w, self.weights.trans_w, self.weights.label_id("1"),
                                              contig_ptr, gene_ptr, attr_idx, window, step, pad)
         return p
@@ -134,10 +138,65 @@ def test_training_is_delegated_or_refused(weights, tmp_path):
             ClusterCRF().fit([])
 
 
+def test_arithmetic_switch(weights, ref_cases, monkeypatch):
+    """The drop-in asks for the reference's f64 arithmetic unless told otherwise (GECCO_B200_ARITHMETIC / .arithmetic)."""
+    crf = make_crf(weights, ref_cases[0])
+    assert crf.arithmetic == "f64"
+    crf.predict_probabilities(genes_of_case(ref_cases[0]), pad=True)
+    assert crf._engine.f64_arith is True
+    monkeypatch.setenv("GECCO_B200_ARITHMETIC", "f32")
+    crf = make_crf(weights, ref_cases[0])
+    crf.predict_probabilities(genes_of_case(ref_cases[0]), pad=True)
+    assert crf.arithmetic == "f32" and crf._engine.f64_arith is False
+    monkeypatch.setenv("GECCO_B200_ARITHMETIC", "f16")
+    with pytest.raises(ValueError, match="invalid arithmetic"):
+        ClusterCRF()
+
+
 @pytest.mark.gpu
-def test_reference_cases_on_device(ref_cases, weights):
+@pytest.mark.parametrize("arithmetic,tol", [("f32", 1e-5), ("f64", 1e-12)])
+def test_reference_cases_on_device(ref_cases, weights, arithmetic, tol):
     for case in ref_cases:
-        check_case(make_crf(weights, case, oracle=False), case, tol=1e-5)
+        crf = make_crf(weights, case, oracle=False)
+        crf.arithmetic = arithmetic
+        check_case(crf, case, tol=tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arithmetic,tol", [("f32", 1e-5), ("f64", 1e-12)])
+def test_domain_feature_type_on_device_vs_oracle(weights, arithmetic, tol):
+    """feature_type="domain" (gecco/crf/features.py:38-48, 99-120) through the CUDA path against the CPU oracle: one
+    row per domain, one empty row per domain-less gene, several contigs incl. one shorter than the window."""
+    from oracle import crf_oracle
+
+    rng = numpy.random.default_rng(11)
+    names = weights.attrs
+    genes, rows, contig_rows = [], [], []
+    for c, n_genes in enumerate([40, 3, 75, 1, 12]):
+        src = Source(f"ctg{c}")
+        before = len(rows)
+        for i in range(n_genes):
+            nd = int(rng.choice([0, 1, 1, 2, 4]))
+            doms = [Domain(str(rng.choice(names)) if rng.random() < 0.9 else "PF99999", 10 * j + 1, 10 * j + 9) for j in range(nd)]
+            genes.append(Gene(src, 100 * i, 100 * i + 90, 1, Protein(f"c{c}g{i}", None, doms)))
+            rows += [[weights.attr_index.get(d.name, -1)] for d in doms] or [[]]
+        contig_rows.append(len(rows) - before)
+    crf = ClusterCRF.trained()
+    crf.feature_type, crf.window_size, crf.arithmetic = "domain", 5, arithmetic
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = crf.predict_probabilities(genes)
+    ptr = numpy.cumsum([0] + [len(r) for r in rows])
+    idx = numpy.array([a for r in rows for a in r], dtype=numpy.int32)
+    cptr = numpy.cumsum([0] + contig_rows)
+    want, _ = crf_oracle.marginals_windowed(weights.state_w, weights.trans_w, 1, cptr, ptr, idx, 5, 1, True)
+    got = []
+    for g in out:
+        got += [d.probability for d in g.protein.domains] or [g.average_probability]
+    assert len(got) == len(want) and numpy.abs(numpy.array(got) - want).max() <= tol
+    # bulk cluster-weight annotation (gecco/crf/__init__.py:261-269)
+    sf = crf.model.state_features_
+    assert all(d.cluster_weight == sf.get((d.name, "1")) for g in out for d in g.protein.domains)
 
 
 @pytest.mark.gpu
@@ -149,6 +208,12 @@ def test_golden_bgc0001866_through_the_dropin(bgc, weights):
     src = Source("BGC0001866.1")
     genes = [Gene(src, g["start"], g["end"], 1, Protein(g["protein_id"], None, doms.get(g["protein_id"], [])))
              for g in bgc["genes"]]
-    out = ClusterCRF.trained().predict_probabilities(genes)
     golden = {g["protein_id"]: g["average_p"] for g in bgc["genes"]}
+    crf = ClusterCRF.trained()
+    assert crf.arithmetic == "f64"
+    out = crf.predict_probabilities(genes)
+    # the reference's own arithmetic on the device: python-crfsuite's numbers to the last bit
+    assert [g.average_probability for g in out] == [golden[g.id] for g in out]
+    crf.arithmetic = "f32"
+    out = crf.predict_probabilities(genes)
     assert max(abs(g.average_probability - golden[g.id]) for g in out) <= 1e-5

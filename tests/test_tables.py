@@ -431,6 +431,30 @@ def test_predict_tables_on_device(bgc, tmp_path):
     tables.close()
 
 
+@pytest.mark.gpu
+def test_predict_tables_reproduces_the_reference_tables_byte_for_byte(bgc, tmp_path):
+    """Tables in -> CRF on the B200 in the reference's own arithmetic (GCRF_FLAG_F64, the drop-in's default) -> result
+    tables whose SHA-256 equals that of the reference's committed BGC0001866.genes.tsv / .features.tsv (python-crfsuite
+    output, 16-17 digits per probability), from the DEVICE'S OWN numbers; the clusters row's average_p / max_p strings
+    equal the reference's as well."""
+    from gecco_b200.crf import ClusterCRF
+    from gecco_b200.tables import predict_tables
+
+    gtext, ftext = bgc_tables(bgc, shuffle=3)
+    (tmp_path / "BGC0001866.genes.tsv").write_text(gtext)
+    (tmp_path / "BGC0001866.features.tsv").write_text(ftext)
+    crf = ClusterCRF.trained()
+    assert crf.arithmetic == "f64"
+    tables, prob = predict_tables(tmp_path / "BGC0001866.genes.tsv", tmp_path / "BGC0001866.features.tsv", tmp_path / "out", model=crf)
+    tables.close()
+    assert prob.tolist() == [g["average_p"] for g in bgc["genes"]]
+    for name, key in (("genes.tsv", "genes_tsv"), ("features.tsv", "features_tsv")):
+        data = (tmp_path / "out" / f"BGC0001866.{name}").read_bytes()
+        assert hashlib.sha256(data).hexdigest() == bgc["sha256_lf"][key], name
+    crows = tables_oracle.read_table((tmp_path / "out" / "BGC0001866.clusters.tsv").read_text())
+    assert len(crows) == 1 and all(crows[0][k] == bgc["clusters"][0][k] for k in ("average_p", "max_p", "cluster_id"))
+
+
 def test_the_abi_from_plain_c(bgc, tmp_path):
     """examples/tables_roundtrip.c, compiled as C99 against include/gecco_crf_b200.h and linked with the shared library
     (no Python, no torch in that process): loads the reference fixture's tables, packs the accession batch and writes
