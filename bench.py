@@ -50,6 +50,7 @@ import numpy  # noqa: E402
 METRIC = "genes/sec CRF marginal inference"
 UNIT = "genes/s"
 WINDOW, STEP, PAD = 20, 1, True
+KERNEL_NAME = "gcrf::stream_kernel<20,128,4,int>"
 
 
 def load_weights():
@@ -209,12 +210,68 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def gpu_cpu_affinity(gpu_index: int):
+    """Host cores NVML reports as local to the GPU (its NUMA node), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        return [c for c in cpus if c in os.sched_getaffinity(0)] or None
+    except Exception:
+        return None
+
+
+class bound_to_gpu:
+    """Run the enclosed host work (pinned allocations are first-touched here, copies are driven from here) on this
+    rank's slice of the cores local to its GPU; restores the previous affinity on exit."""
+
+    def __init__(self, gpu_index: int, rank_slot: int, slots: int):
+        self.gpu, self.slot, self.slots, self.prev, self.cpus = gpu_index, rank_slot, slots, None, None
+
+    def __enter__(self):
+        local = gpu_cpu_affinity(self.gpu)
+        if local:
+            # ranks whose GPUs share a node split its cores so that their copy threads do not stack on one core
+            per = max(1, len(local) // max(1, self.slots))
+            mine = local[self.slot * per:(self.slot + 1) * per] or local
+            try:
+                self.prev = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, mine)
+                self.cpus = mine
+            except OSError:
+                self.prev = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+
+
+def oracle_full(weights, batch, window=WINDOW, step=STEP, pad=PAD):
+    from oracle import crf_oracle
+
+    p, _ = crf_oracle.marginals_windowed(weights.state_w, weights.trans_w, weights.label_id("1"), batch.contig_ptr,
+                                         batch.gene_ptr, batch.attr_idx, window, step, pad, nthreads=host_cores())
+    return p
+
+
+def max_abs_err(got, want) -> float:
+    ok = ~numpy.isnan(want)
+    if not numpy.array_equal(numpy.isnan(got), ~ok):
+        return float("inf")
+    return float(numpy.abs(got[ok] - want[ok]).max()) if ok.any() else 0.0
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from gecco_b200 import synth
-    from gecco_b200._lib import CRFEngine, PinnedArray
+    from gecco_b200 import sharding, synth
+    from gecco_b200._lib import GCRF_FLAG_F64, CRFEngine, PinnedArray
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,16 +290,8 @@ def run_ours(args) -> None:
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     engine.set_stream(stream.cuda_stream)
-
-    # ---- device-resident inputs
-    cp = torch.from_numpy(batch.contig_ptr).to(dev)
-    gp = torch.from_numpy(batch.gene_ptr).to(dev)
-    ai = torch.from_numpy(batch.attr_idx).to(dev)
-    out = torch.empty(batch.G, dtype=torch.float64, device=dev)
-
-    def step_device():
-        engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), batch.C, batch.G, batch.nnz,
-                                         out.data_ptr(), window=WINDOW, step=STEP, pad=PAD)
+    peak, peak_src = measured_peak_gbs()
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > the 126 MB L2
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -250,19 +299,47 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op) -> float:
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x: float) -> float:
+        return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+
     def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x
+
+    def upload(b):
+        cp = torch.from_numpy(b.contig_ptr).to(dev)
+        gp = torch.from_numpy(b.gene_ptr).to(dev)
+        ai = torch.full((b.nnz + 16,), -1, dtype=torch.int32, device=dev)  # readable slack behind the last id
+        ai[: b.nnz] = torch.from_numpy(b.attr_idx).to(dev)
+        return cp, gp, ai
+
+    def kernel_times(launch, n: int, flush: bool):
+        """Average device time of the kernels of one call (events inside the ABI around the kernels only)."""
+        engine.set_timing(True)
+        ms = []
+        for it in range(2 + n):
+            if flush:
+                flush_buf.zero_()
+            launch()
+            t = engine.last_kernel_ms()
+            if it >= 2:
+                ms.append(t)
+        engine.set_timing(False)
+        return sum(ms) / len(ms), min(ms)
+
+    # ---- device-resident inputs: the headline loop (BASELINE config 2, FP32 arithmetic)
+    cp, gp, ai = upload(batch)
+    out = torch.empty(batch.G, dtype=torch.float64, device=dev)
+
+    def step_device(flags: int = 0):
+        engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), batch.C, batch.G, batch.nnz,
+                                         out.data_ptr(), window=WINDOW, step=STEP, pad=PAD, flags=flags)
 
     for _ in range(args.warmup):
         step_device()
@@ -285,86 +362,100 @@ def run_ours(args) -> None:
     total_genes = sum_over_ranks(float(batch.G))
     value = total_genes * args.steps / (dev_ms * 1e-3)
 
-    # ---- per-launch kernel time (events inside the ABI around the kernel only), separate pass
-    kernel_ms = []
-    engine.set_timing(True)
-    for _ in range(min(args.steps, 10)):
-        step_device()
-        kernel_ms.append(engine.last_kernel_ms())
-    kernel_ms_avg = sum(kernel_ms) / len(kernel_ms)
-    engine.set_timing(False)
+    # ---- per-launch kernel time, separate pass (inputs + outputs exceed L2: no flush needed for config 2)
+    algo_bytes = synth.algorithmic_bytes(batch.C, batch.G, batch.nnz)
+    kernel_ms_avg, kernel_ms_min = kernel_times(step_device, min(args.steps, 10), flush=algo_bytes < 130e6)
     if rank == 0:
         time.sleep(0.2)
         sampler.stop()
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+    out_f32_arith = out.cpu().numpy()
 
-    # ---- parity spot check of what was timed (oracle on the first contigs; rank 0 only)
-    parity = None
+    # ---- CPU baseline beside it (rank 0, N=1 only) — its output is the whole-batch parity reference
+    cpu, want = None, None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        times = time_cpu_port(weights, batch, cores, 3)
+        few = batch.slice_contigs(0, max(1, batch.C // 20))
+        one = time_cpu_port(weights, few, 1, 1)[0]
+        cpu = {"value": batch.G / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"the whole batch ({batch.C} contigs / {batch.G} genes), best of 3 passes, {cores} threads over contigs",
+               "single_thread_value": few.G / one}
     if rank == 0:
-        from oracle import crf_oracle
+        want = oracle_full(weights, batch)  # every gene of the timed batch, not a sample
+    parity = max_abs_err(out_f32_arith, want) if rank == 0 else None
 
-        sub = batch.slice_contigs(0, min(batch.C, 64))
-        want, _ = crf_oracle.marginals_windowed(weights.state_w, weights.trans_w, weights.label_id("1"), sub.contig_ptr,
-                                                sub.gene_ptr, sub.attr_idx, WINDOW, STEP, PAD, nthreads=4)
-        got = out[:sub.G].cpu().numpy()
-        parity = float(numpy.abs(got - want).max())
-
-    # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H per step)
-    engine.set_stream(None)
-    pins = [PinnedArray(a.shape, a.dtype) for a in (batch.contig_ptr, batch.gene_ptr, batch.attr_idx)]
-    for pin, a in zip(pins, (batch.contig_ptr, batch.gene_ptr, batch.attr_idx)):
-        pin.array[...] = a
-    pout = PinnedArray((batch.G,), numpy.float64)
-
-    def step_host():
-        engine.marginals_windowed(pins[0].array, pins[1].array, pins[2].array, window=WINDOW, step=STEP, pad=PAD,
-                                  out=pout.array)
-
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
+    # ---- the same batch in the reference's own arithmetic (GCRF_FLAG_F64): CRFsuite's f64 recursion, op by op
+    f64_ms_avg, f64_ms_min = kernel_times(lambda: step_device(GCRF_FLAG_F64), 5, flush=False)
+    f64_line = None
+    if rank == 0:
+        got64 = out.cpu().numpy()
+        f64_line = {"dtype": "f64", "value": batch.G / (f64_ms_avg * 1e-3), "unit": UNIT, "kernel_ms_avg": f64_ms_avg,
+                    "kernels": "gcrf::exact_unary_kernel + gcrf::exact_window_kernel<20>",
+                    "roofline": {"bound": "hbm", "achieved": algo_bytes / (f64_ms_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": algo_bytes / (f64_ms_avg * 1e-3) / 1e9 / peak},
+                    "parity_max_abs_err_vs_oracle": max_abs_err(got64, want),
+                    "bit_identical_to_oracle_frac": float((got64 == want).mean()),
+                    "note": "n_gpus=1 figure of rank 0; CRFsuite's scaled forward-backward in f64, no FMA contraction, "
+                            "correctly rounded exp (gcrf_exact.cu)"}
+    step_device()  # leave the FP32 result in `out` for the bit-identity checks below
     torch.cuda.synchronize(dev)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = total_genes * e2e_steps / e2e_s
-    h2d = int(batch.contig_ptr.nbytes + batch.gene_ptr.nbytes + batch.attr_idx.nbytes)
-    d2h = int(batch.G * 8)
-    e2e_equal = bool(numpy.array_equal(pout.array, out.cpu().numpy()))
 
-    # ---- the same call with compact buffers: uint16 ids (GCRF_FLAG_IDX_U16, widened on the device) and float32
-    #      marginals — a separate variant with its own byte counts, not the headline
+    # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H per step), three wire layouts
     from gecco_b200.packer import compact_ids
 
-    small = compact_ids(batch.attr_idx, len(weights.attrs))
-    pin16 = PinnedArray(small.shape, small.dtype)
-    pin16.array[...] = small
-    pout32 = PinnedArray((batch.G,), numpy.float32)
+    engine.set_stream(None)
+    slots = max(1, world)
+    with bound_to_gpu(local_rank, rank_slot=local_rank, slots=slots) as binding:
+        small = compact_ids(batch.attr_idx, len(weights.attrs))
+        pins = [PinnedArray(a.shape, a.dtype) for a in (batch.contig_ptr, batch.gene_ptr, batch.attr_idx, small)]
+        for pin, a in zip(pins, (batch.contig_ptr, batch.gene_ptr, batch.attr_idx, small)):
+            pin.array[...] = a
+        pout = PinnedArray((batch.G,), numpy.float64)
+        pout32 = PinnedArray((batch.G,), numpy.float32)
+        e2e_steps = max(3, min(args.steps, 10))
 
-    def step_host_compact():
-        engine.marginals_windowed(pins[0].array, pins[1].array, pin16.array, window=WINDOW, step=STEP, pad=PAD,
-                                  out=pout32.array, f32=True)
+        def e2e_leg(ids_pin, out_pin, f32: bool, **kw):
+            def one():
+                engine.marginals_windowed(pins[0].array, pins[1].array, ids_pin.array, window=WINDOW, step=STEP, pad=PAD,
+                                          out=out_pin.array, f32=f32, **kw)
+            for _ in range(2):
+                one()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                one()
+            torch.cuda.synchronize(dev)
+            mine = time.perf_counter() - t0
+            secs = max_over_ranks(mine)
+            barrier()
+            h2d = int(pins[0].array.nbytes + pins[1].array.nbytes + ids_pin.array.nbytes)
+            d2h = int(out_pin.array.nbytes)
+            return {"value": total_genes * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * secs / e2e_steps,
+                    "this_rank_pcie_gbs": (h2d + d2h) * e2e_steps / mine / 1e9}
 
-    for _ in range(2):
-        step_host_compact()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host_compact()
-    torch.cuda.synchronize(dev)
-    compact_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    compact = {"value": total_genes * e2e_steps / compact_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(batch.contig_ptr.nbytes + batch.gene_ptr.nbytes + small.nbytes),
-               "d2h_bytes_per_step": int(batch.G * 4), "ms_per_step": 1e3 * compact_s / e2e_steps,
-               "layout": "uint16 attribute ids, float32 marginals",
-               "identical_to_float32_of_device_path": bool(numpy.array_equal(pout32.array, out.cpu().numpy().astype(numpy.float32)))}
+        # headline: uint16 ids in (GCRF_FLAG_IDX_U16; the packers emit them natively for vocabularies < 65,535), f64 out
+        e2e = e2e_leg(pins[3], pout, False)
+        e2e["layout"] = "int32 row pointers, uint16 attribute ids, float64 marginals"
+        e2e["bit_identical_to_device_path"] = bool(numpy.array_equal(pout.array, out_f32_arith))
+        e2e_i32 = e2e_leg(pins[2], pout, False)
+        e2e_i32["layout"] = "int32 row pointers, int32 attribute ids, float64 marginals"
+        e2e_i32["bit_identical_to_device_path"] = bool(numpy.array_equal(pout.array, out_f32_arith))
+        compact = e2e_leg(pins[3], pout32, True)
+        compact["layout"] = "int32 row pointers, uint16 attribute ids, float32 marginals (the FP32 results un-widened)"
+        compact["identical_to_float32_of_device_path"] = bool(numpy.array_equal(pout32.array, out_f32_arith.astype(numpy.float32)))
+        per_rank_gbs = [e2e["this_rank_pcie_gbs"]]
+        if world > 1:
+            t = torch.tensor([e2e["this_rank_pcie_gbs"]], dtype=torch.float64, device=dev)
+            allv = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allv, t)
+            per_rank_gbs = [float(v.item()) for v in allv]
+        e2e["per_rank_pcie_gbs"] = per_rank_gbs
+        e2e["host_binding"] = {"cpus_of_rank0": binding.cpus, "policy": "each rank on its slice of the cores NVML reports local to its GPU; "
+                               "pinned staging first-touched there"}
 
     # ---- the stage in front of the marginals: accession -> attribute id on device, same batch.
-    # Outside the headline's timed region; reported so that "accessions in, marginals out" has a measured number.
     features_stage = None
     if rank == 0 and world == 1 and engine.has_vocabulary:  # like cpu_baseline: on the N=1 line only
         nums = numpy.array([int(a[2:]) for a in weights.attrs], dtype=numpy.int32)
@@ -372,7 +463,7 @@ def run_ours(args) -> None:
         d_acc = torch.from_numpy(acc_host).to(dev)
         d_ids = torch.empty(batch.nnz, dtype=torch.int32, device=dev)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        engine.set_stream(stream.cuda_stream)  # the host-buffer legs above run on the engine's own stream
+        engine.set_stream(stream.cuda_stream)
         f_ms = []
         for it in range(3 + 8):
             f0.record(stream)
@@ -383,50 +474,167 @@ def run_ours(args) -> None:
                 f_ms.append(f0.elapsed_time(f1))
         f_ms_avg = sum(f_ms) / len(f_ms)
         f_bytes = 8 * batch.nnz + 4 * (batch.G + 1)  # accession in, id out, row pointers
-        features_stage = {"kernel": "gcrf::features_kernel<int,8,8,512,true>", "kernel_ms_avg": f_ms_avg,
-                          "rows": int(batch.nnz), "algorithmic_bytes_per_launch": int(f_bytes),
-                          "achieved_gbs": f_bytes / (f_ms_avg * 1e-3) / 1e9,
-                          "ids_equal_packer": bool(torch.equal(d_ids, ai)),
-                          "genes_per_s_features_plus_marginals": batch.G / ((f_ms_avg + kernel_ms_avg) * 1e-3)}
+        ids_equal = bool(torch.equal(d_ids, ai[: batch.nnz]))
+        # accessions in -> marginals out in ONE call on device-resident arrays (GCRF_FLAG_ACCESSIONS)
+        from gecco_b200._lib import GCRF_FLAG_ACCESSIONS
+
+        def step_acc():
+            engine.marginals_windowed_device(cp.data_ptr(), gp.data_ptr(), d_acc.data_ptr(), batch.C, batch.G, batch.nnz,
+                                             out.data_ptr(), window=WINDOW, step=STEP, pad=PAD, flags=GCRF_FLAG_ACCESSIONS)
+        acc_ms_avg, _ = kernel_times(step_acc, 8, flush=False)
+        acc_equal = bool(numpy.array_equal(out.cpu().numpy(), out_f32_arith))
+        features_stage = {"kernel_ms_avg": f_ms_avg, "rows": int(batch.nnz), "algorithmic_bytes_per_launch": int(f_bytes),
+                          "achieved_gbs": f_bytes / (f_ms_avg * 1e-3) / 1e9, "ids_equal_packer": ids_equal,
+                          "accessions_to_marginals": {"kernel_ms_avg": acc_ms_avg, "genes_per_s": batch.G / (acc_ms_avg * 1e-3),
+                                                      "roofline_frac": algo_bytes / (acc_ms_avg * 1e-3) / 1e9 / peak,
+                                                      "bit_identical_to_ids_path": acc_equal}}
         engine.set_stream(None)
         del d_acc, d_ids
-        # ... and end to end from raw accessions (GCRF_FLAG_ACCESSIONS): H2D + features + marginals + D2H per step
-        pin_acc = PinnedArray(acc_host.shape, acc_host.dtype)
-        pin_acc.array[...] = acc_host
 
-        def step_host_accessions():
-            engine.marginals_windowed(pins[0].array, pins[1].array, pin_acc.array, window=WINDOW, step=STEP, pad=PAD,
-                                      out=pout.array, accessions=True)
+    # ---- the other BASELINE configs on the same line (rank 0, N=1): kernel time, roofline fraction, whole-batch parity
+    configs = None
+    big = None  # config 4 at its full size, kept for the sharded leg
+    engine.set_stream(stream.cuda_stream)
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = []
+        A = len(weights.attrs)
 
-        for _ in range(2):
-            step_host_accessions()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_host_accessions()
-        torch.cuda.synchronize(dev)
-        acc_s = time.perf_counter() - t0
-        features_stage["e2e_from_accessions"] = {
-            "value": batch.G * e2e_steps / acc_s, "unit": UNIT, "ms_per_step": 1e3 * acc_s / e2e_steps,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "n_gpus": 1,
-            "bit_identical_to_device_path": bool(numpy.array_equal(pout.array, out.cpu().numpy()))}
-        pin_acc.free()
+        def config_entry(name, b, *, chain=False, note=None):
+            dcp, dgp, dai = upload(b)
+            dout = torch.empty(b.G, dtype=torch.float64, device=dev)
+            if chain:
+                def go():
+                    engine.marginals_chain_device(dcp.data_ptr(), dgp.data_ptr(), dai.data_ptr(), b.C, b.G, b.nnz, dout.data_ptr(),
+                                                  ptr64=b.gene_ptr.dtype == numpy.int64)
+            else:
+                def go():
+                    engine.marginals_windowed_device(dcp.data_ptr(), dgp.data_ptr(), dai.data_ptr(), b.C, b.G, b.nnz, dout.data_ptr(),
+                                                     window=WINDOW, step=STEP, pad=PAD, ptr64=b.gene_ptr.dtype == numpy.int64)
+            ab = synth.algorithmic_bytes(b.C, b.G, b.nnz)
+            ms_avg, ms_min = kernel_times(go, 6, flush=ab < 400e6)
+            got = dout.cpu().numpy()
+            if chain:
+                from oracle import crf_oracle
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cores = host_cores()
-        sample = batch if batch.C <= 10_000 else batch.slice_contigs(0, 10_000)
-        times = time_cpu_port(weights, sample, cores, 3)
-        one = time_cpu_port(weights, sample.slice_contigs(0, max(1, sample.C // 20)), 1, 1)[0]
-        cpu = {"value": sample.G / min(times), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{sample.C} contigs / {sample.G} genes of the same batch, best of 3 passes, {cores} threads over contigs",
-               "single_thread_value": (sample.slice_contigs(0, max(1, sample.C // 20)).G) / one}
+                err = 0.0
+                for c in range(b.C):
+                    g0, g1 = int(b.contig_ptr[c]), int(b.contig_ptr[c + 1])
+                    ref = crf_oracle.chain_marginals(weights.state_w, weights.trans_w, b.gene_ptr, b.attr_idx, g0, g1)[:, 1]
+                    err = max(err, float(numpy.abs(got[g0:g1] - ref).max()))
+            else:
+                err = max_abs_err(got, oracle_full(weights, b))
+            entry = {"config": name, "contigs": b.C, "genes": b.G, "nnz": b.nnz, "kernel_ms_avg": ms_avg, "kernel_ms_min": ms_min,
+                     "value": b.G / (ms_avg * 1e-3), "unit": UNIT, "algorithmic_bytes": ab,
+                     "roofline_frac": ab / (ms_avg * 1e-3) / 1e9 / peak, "parity_max_abs_err_vs_oracle": err,
+                     "parity_genes_checked": b.G, "l2_flushed_between_launches": ab < 400e6}
+            if note:
+                entry["note"] = note
+            configs.append(entry)
+            del dcp, dgp, dai, dout
+
+        config_entry("2 at real annotation density (10k contigs x Poisson(200) genes x Poisson(1.4) domains)",
+                     synth.config2(A, seed=2, mean_domains=1.4, unknown_fraction=0.0))
+        config_entry("3 E. coli-like stand-in (1 contig x 4,300 genes x Poisson(1.4) domains; the real table is not in the reference)",
+                     synth.config3_ecoli_like(A))
+        big = synth.config4_chunked(A, seed=4)
+        config_entry("4 metagenome, full size (1M contigs, lognormal lengths, ~31% shorter than the window, Poisson(25) domains)", big)
+        config_entry("4 metagenome, full size, real annotation density (Poisson(1.4) domains)", synth.config4_chunked(A, seed=4, mean_domains=1.4))
+        five = synth.config5(A)
+        config_entry("5 long contigs (100 x 5,000 genes x Poisson(25) domains), GECCO semantics W=20", five)
+        config_entry("5 long contigs, deep-chain primitive (one 5,000-item chain per contig, gcrf_marginals_chain, f64)", five, chain=True,
+                     note="tolerance 1e-9 (f64 2x2 scan vs the oracle's sequential scaled recursion)")
+
+    # ---- ONE batch sharded by contig over the ranks (BASELINE config 4 at full size): each rank ingests its own
+    #      shard from pinned host memory, runs the kernel, and an NCCL all-gather of the padded f64 shards puts every
+    #      gene's marginal on every rank — kernel + collective inside the timed region (strong scaling)
+    sharded = None
+    if not args.no_sharded:
+        A = len(weights.attrs)
+        lens = synth.config4_lengths(4)
+        cptr = numpy.concatenate([[0], numpy.cumsum(lens)])
+        parts = sharding.partition_contigs(cptr, None, world, WINDOW, contig_nnz=25.0 * lens)  # expected ids per contig
+        c0, c1 = parts[rank]
+        if big is not None and world == 1:
+            shard = big
+        else:
+            shard = synth.config4_chunked(A, seed=4, contig_range=(c0, c1), threads=max(1, host_cores() // max(1, world)))
+        big = None
+        sizes = [int(cptr[b] - cptr[a]) for a, b in parts]
+        gmax = max(sizes)
+        ds = sharding.DeviceShard(shard, dev)
+        local = torch.zeros(gmax, dtype=torch.float64, device=dev)
+        gathered = torch.empty(world * gmax, dtype=torch.float64, device=dev) if world > 1 else local
+        ptr64 = shard.gene_ptr.dtype == numpy.int64
+
+        def shard_kernel():
+            engine.marginals_windowed_device(ds.contig_ptr.data_ptr(), ds.gene_ptr.data_ptr(), ds.attr_idx.data_ptr(), ds.C, ds.G,
+                                             ds.nnz, local.data_ptr(), window=WINDOW, step=STEP, pad=PAD, ptr64=ptr64)
+
+        def shard_gather():
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, local)
+
+        sh_steps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            shard_kernel()
+            shard_gather()
+        barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * sh_steps + 1)]
+        e[0].record(stream)
+        for k in range(sh_steps):
+            shard_kernel()
+            e[2 * k + 1].record(stream)
+            shard_gather()
+            e[2 * k + 2].record(stream)
+        barrier()
+        ms_total = max_over_ranks(e[0].elapsed_time(e[-1])) / sh_steps
+        ms_kernel = max_over_ranks(sum(e[2 * k].elapsed_time(e[2 * k + 1]) for k in range(sh_steps)) / sh_steps)
+        ms_gather = max_over_ranks(sum(e[2 * k + 1].elapsed_time(e[2 * k + 2]) for k in range(sh_steps)) / sh_steps)
+        # parity: every rank checks ITS contigs' slice of the gathered array against the oracle on its shard
+        got = gathered[rank * gmax: rank * gmax + shard.G].cpu().numpy() if world > 1 else local[: shard.G].cpu().numpy()
+        err = max_over_ranks(max_abs_err(got, oracle_full(weights, shard)))
+        # the same pass with the shard coming from (pinned) host memory every step: per-rank H2D inside the timed region
+        with bound_to_gpu(local_rank, rank_slot=local_rank, slots=slots):
+            hp = [PinnedArray(a.shape, a.dtype) for a in (shard.contig_ptr, shard.gene_ptr, shard.attr_idx)]
+            for pin, a in zip(hp, (shard.contig_ptr, shard.gene_ptr, shard.attr_idx)):
+                pin.array[...] = a
+            srcs = [torch.from_numpy(pin.array) for pin in hp]
+            dsts = [ds.contig_ptr, ds.gene_ptr, ds.attr_idx[: shard.nnz]]
+
+            def ingest():
+                for d, h in zip(dsts, srcs):
+                    d.copy_(h, non_blocking=True)
+
+            for _ in range(2):
+                ingest()
+                shard_kernel()
+                shard_gather()
+            barrier()
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record(stream)
+            for _ in range(sh_steps):
+                ingest()
+                shard_kernel()
+                shard_gather()
+            i1.record(stream)
+            barrier()
+            ms_ingest_total = max_over_ranks(i0.elapsed_time(i1)) / sh_steps
+            for pin in hp:
+                pin.free()
+        G_all = int(cptr[-1])
+        sharded = {"workload": "BASELINE config 4 at full size: 1,000,000 contigs / %d genes, Poisson(25) domains, one batch "
+                               "cost-partitioned by contig over the ranks" % G_all,
+                   "scaling": "strong", "n_gpus": world, "genes": G_all, "genes_per_rank": sizes,
+                   "value": G_all / (ms_total * 1e-3), "unit": UNIT, "ms_per_step": ms_total, "ms_kernel": ms_kernel,
+                   "ms_gather": ms_gather, "gather_bytes": int(8 * gmax * world) if world > 1 else 0,
+                   "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) on the kernel's stream" if world > 1 else None,
+                   "steps": sh_steps, "parity_max_abs_err_vs_oracle": err, "parity_genes_checked": G_all,
+                   "with_host_ingest": {"value": G_all / (ms_ingest_total * 1e-3), "ms_per_step": ms_ingest_total,
+                                        "h2d_bytes_this_rank": int(shard.contig_ptr.nbytes + shard.gene_ptr.nbytes + shard.attr_idx.nbytes),
+                                        "note": "every rank copies its own shard from pinned host memory each step, then kernel + all-gather"}}
+        del ds, local, gathered
 
     if rank == 0:
-        algo_bytes = synth.algorithmic_bytes(batch.C, batch.G, batch.nnz)
-        peak, peak_src = measured_peak_gbs()
-        achieved = algo_bytes / (kernel_ms_avg * 1e-3) / 1e9
         traffic = None
         tpath = ROOT / "profiles" / "traffic_bytes_per_launch.json"
         if tpath.exists():
@@ -436,25 +644,33 @@ def run_ours(args) -> None:
                     traffic = t.get("dram_bytes_per_launch")
             except ValueError:
                 pass
+        achieved = algo_bytes / (kernel_ms_avg * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(batch, world, args.contigs),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "gcrf::stream_kernel<20,128,4,int>",
-                         "kernel_ms_avg": kernel_ms_avg, "algorithmic_bytes_per_launch": algo_bytes},
+                         "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel on this workload, committed under profiles/",
+                         "peak_source": peak_src, "kernel": KERNEL_NAME,
+                         "kernel_ms_avg": kernel_ms_avg, "kernel_ms_min": kernel_ms_min, "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "kernel_ms_avg brackets single launches with events; back-to-back launches (ms_per_step) overlap "
+                                 "their prologues through programmatic dependent launch and are slightly faster"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "bit_identical_to_device_path": e2e_equal},
+            "e2e": e2e,
+            "e2e_int32_ids": e2e_i32,
             "e2e_compact": compact,
+            "f64": f64_line,
+            "configs": configs,
+            "sharded": sharded,
             "features_stage": features_stage,
             "gpu_launches": launches,
             "clocks": clocks,
             "parity_max_abs_err_vs_oracle": parity,
+            "parity_genes_checked": batch.G,
         }
         emit(line)
-    for p in pins + [pout, pin16, pout32]:
-        p.free()
+    for p_ in pins + [pout, pout32]:
+        p_.free()
     engine.close()
     if world > 1:
         dist.destroy_process_group()
@@ -468,6 +684,8 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--contigs", type=int, default=10_000, help="contigs per GPU (config 2 = 10000)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (N=1 line)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the strong-scaling leg (config 4 sharded by contig)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

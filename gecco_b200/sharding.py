@@ -15,26 +15,30 @@ import numpy
 
 from .synth import CsrBatch
 
-__all__ = ["partition_contigs", "scatter_batch", "gather_marginals", "predict_sharded"]
+__all__ = ["partition_contigs", "scatter_batch", "gather_marginals", "predict_sharded", "DeviceShard"]
 
 
-def partition_contigs(contig_ptr: numpy.ndarray, gene_ptr: numpy.ndarray, n_shards: int, window: int,
-                      kappa: float = 2.0) -> List[Tuple[int, int]]:
+def partition_contigs(contig_ptr: numpy.ndarray, gene_ptr: Optional[numpy.ndarray], n_shards: int, window: int,
+                      kappa: float = 2.0, contig_nnz: Optional[numpy.ndarray] = None) -> List[Tuple[int, int]]:
     """Split contigs into ``n_shards`` contiguous ranges of roughly equal cost.
 
     Cost of a contig = its attribute ids (the bytes streamed from HBM) + ``kappa * windows * window`` (the
     dynamic-programming steps it triggers).  Contiguous ranges keep every shard a plain slice of the CSR arrays.
     Returns ``[(c_begin, c_end), ...]``; trailing shards may be empty when there are fewer contigs than shards.
+    ``contig_nnz`` (ids per contig, exact or expected) replaces ``gene_ptr`` when the row pointers are not at hand.
     """
     contig_ptr = numpy.asarray(contig_ptr, dtype=numpy.int64)
-    gene_ptr = numpy.asarray(gene_ptr, dtype=numpy.int64)
     C = len(contig_ptr) - 1
     if n_shards <= 0:
         raise ValueError("n_shards must be positive")
     if C == 0:
         return [(0, 0)] * n_shards
     n = numpy.diff(contig_ptr)
-    nnz = gene_ptr[contig_ptr[1:]] - gene_ptr[contig_ptr[:-1]]
+    if contig_nnz is not None:
+        nnz = numpy.asarray(contig_nnz, dtype=numpy.float64)
+    else:
+        gene_ptr = numpy.asarray(gene_ptr, dtype=numpy.int64)
+        nnz = gene_ptr[contig_ptr[1:]] - gene_ptr[contig_ptr[:-1]]
     windows = numpy.maximum(n, window) - window + 1
     cost = nnz + kappa * windows * window
     cum = numpy.concatenate([[0.0], numpy.cumsum(cost, dtype=numpy.float64)])
@@ -95,31 +99,84 @@ def scatter_batch(batch: Optional[CsrBatch], window: int, src: int = 0, device=N
 
 def gather_marginals(local, genes_per_rank: Sequence[int]):
     """All-gather the per-gene marginals of every rank (shards padded to the largest one); returns the
-    concatenation in rank order as a tensor on ``local``'s device."""
+    concatenation in rank order as a tensor on ``local``'s device.  One collective on the caller's stream
+    (``all_gather_into_tensor``: NCCL on GPUs, gloo on CPU tensors); nothing touches the host."""
     import torch
 
     dist = _dist()
     world = dist.get_world_size()
     gmax = max(int(g) for g in genes_per_rank) if len(genes_per_rank) else 0
-    padded = torch.zeros(max(gmax, 1), dtype=local.dtype, device=local.device)
-    padded[: local.numel()] = local
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded)
-    return torch.cat([p[: int(g)] for p, g in zip(parts, genes_per_rank)])
+    gmax = max(gmax, 1)
+    if local.numel() == gmax:
+        padded = local
+    else:
+        padded = torch.zeros(gmax, dtype=local.dtype, device=local.device)
+        padded[: local.numel()] = local
+    gathered = torch.empty(world * gmax, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, padded)
+    if all(int(g) == gmax for g in genes_per_rank):
+        return gathered
+    return torch.cat([gathered[r * gmax: r * gmax + int(g)] for r, g in enumerate(genes_per_rank)])
 
 
-def predict_sharded(engine, shard: CsrBatch, *, window: int, step: int = 1, pad: bool = True, device=None):
+class DeviceShard:
+    """This rank's CSR shard resident in HBM (uploaded once; ``predict_sharded`` then runs kernel + gather only)."""
+
+    def __init__(self, shard: CsrBatch, device):
+        import torch
+
+        self.C, self.G, self.nnz = shard.C, shard.G, shard.nnz
+        self.ptr64 = shard.gene_ptr.dtype == numpy.int64
+        self.contig_ptr = torch.from_numpy(numpy.ascontiguousarray(shard.contig_ptr)).to(device)
+        self.gene_ptr = torch.from_numpy(numpy.ascontiguousarray(shard.gene_ptr)).to(device)
+        # the streaming kernel's bulk copies read whole 16-byte units: keep slack behind the last id
+        self.attr_idx = torch.full((shard.nnz + 16,), -1, dtype=torch.int32, device=device)
+        self.attr_idx[: shard.nnz] = torch.from_numpy(numpy.ascontiguousarray(shard.attr_idx)).to(device)
+
+
+def predict_sharded(engine, shard, *, window: int, step: int = 1, pad: bool = True, device=None,
+                    genes_per_rank: Optional[Sequence[int]] = None, to_host: bool = True):
     """Run this rank's shard through ``engine`` and gather everybody's marginals (rank order = contig order).
 
-    ``engine`` is a ``CRFEngine`` (or anything with its ``marginals_windowed``).  Returns a float64 numpy array
-    with the marginals of ALL shards on every rank.
+    CUDA device (``device.type == "cuda"``, NCCL process group): ``shard`` is a ``CsrBatch`` (uploaded here) or a
+    ``DeviceShard`` (already resident); the kernel writes straight into the padded send buffer of ONE
+    ``all_gather_into_tensor`` on the same stream — no host round trip between kernel and collective.  Returns the
+    float64 marginals of ALL shards on every rank: a device tensor when ``to_host`` is false, else a numpy array.
+    CPU (gloo, the test-suite): ``engine.marginals_windowed`` on host arrays, gather on CPU tensors.
     """
     import torch
 
     dist = _dist()
-    dev = device if device is not None else torch.device("cpu")
+    world = dist.get_world_size()
+    if genes_per_rank is None:
+        genes_per_rank = [None] * world
+        dist.all_gather_object(genes_per_rank, int(shard.G))
+    genes_per_rank = [int(g) for g in genes_per_rank]
+    gmax = max(max(genes_per_rank), 1)
+    if device is not None and torch.device(device).type == "cuda":
+        dev = torch.device(device)
+        ds = shard if isinstance(shard, DeviceShard) else DeviceShard(shard, dev)
+        current = torch.cuda.current_stream(dev)
+        # the engine runs on the stream torch's collectives order themselves against; stream handle 0 (the legacy
+        # default stream) would mean "the engine's own stream", so work moves to a side stream in that case
+        side = torch.cuda.Stream(dev) if current.cuda_stream == 0 else current
+        side.wait_stream(current)
+        with torch.cuda.stream(side):
+            engine.set_stream(side.cuda_stream)
+            local = torch.empty(gmax, dtype=torch.float64, device=dev)
+            if ds.G < gmax:
+                local[ds.G:].zero_()
+            if ds.G:
+                engine.marginals_windowed_device(ds.contig_ptr.data_ptr(), ds.gene_ptr.data_ptr(), ds.attr_idx.data_ptr(),
+                                                 ds.C, ds.G, ds.nnz, local.data_ptr(), window=window, step=step, pad=pad,
+                                                 ptr64=ds.ptr64)
+            out = gather_marginals(local, genes_per_rank)
+            engine.set_stream(None)
+        current.wait_stream(side)
+        if not to_host:
+            return out
+        return out.cpu().numpy()
     local = engine.marginals_windowed(shard.contig_ptr, shard.gene_ptr, shard.attr_idx, window=window, step=step, pad=pad)
-    sizes = [None] * dist.get_world_size()
-    dist.all_gather_object(sizes, int(shard.G))
-    out = gather_marginals(torch.from_numpy(numpy.ascontiguousarray(local)).to(dev), sizes)
-    return out.cpu().numpy()
+    dev = device if device is not None else torch.device("cpu")
+    out = gather_marginals(torch.from_numpy(numpy.ascontiguousarray(local)).to(dev), genes_per_rank)
+    return out.cpu().numpy() if to_host else out

@@ -12,7 +12,8 @@ from typing import Optional
 
 import numpy
 
-__all__ = ["CsrBatch", "make_batch", "config2", "config3_ecoli_like", "config4", "config5", "algorithmic_bytes"]
+__all__ = ["CsrBatch", "make_batch", "config2", "config3_ecoli_like", "config4", "config4_lengths", "config4_chunked",
+           "config5", "algorithmic_bytes", "concat_batches"]
 
 
 @dataclass
@@ -108,6 +109,52 @@ def config4(num_attrs: int = 2659, seed: int = 4, contigs: int = 1_000_000, mean
     rng = numpy.random.default_rng(seed)
     n = numpy.maximum(1, numpy.rint(rng.lognormal(mean=numpy.log(40.0) - 0.32, sigma=0.8, size=contigs))).astype(numpy.int64)
     return make_batch(rng, n, mean_domains, num_attrs, unknown_fraction, name=f"config4(seed={seed})")
+
+
+def config4_lengths(seed: int = 4, contigs: int = 1_000_000) -> numpy.ndarray:
+    """Genes per contig of config 4 — the first draw of ``config4``'s generator, so G is the same (39,973,222 for seed 4)."""
+    rng = numpy.random.default_rng(seed)
+    return numpy.maximum(1, numpy.rint(rng.lognormal(mean=numpy.log(40.0) - 0.32, sigma=0.8, size=contigs))).astype(numpy.int64)
+
+
+def concat_batches(parts) -> CsrBatch:
+    """Concatenate independent batches (pointers rebased) — the inverse of ``slice_contigs``."""
+    parts = list(parts)
+    g = numpy.cumsum([0] + [p.G for p in parts])
+    z = numpy.cumsum([0] + [p.nnz for p in parts])
+    ptr_dtype = numpy.int32 if int(z[-1]) <= 0x7FFFFFFF else numpy.int64
+    contig_ptr = numpy.concatenate([parts[0].contig_ptr[:1]] + [p.contig_ptr[1:] + g[i] for i, p in enumerate(parts)]).astype(numpy.int32)
+    gene_ptr = numpy.concatenate([numpy.zeros(1, dtype=ptr_dtype)] + [p.gene_ptr[1:].astype(ptr_dtype) + ptr_dtype(z[i]) for i, p in enumerate(parts)])
+    return CsrBatch(contig_ptr, gene_ptr, numpy.concatenate([p.attr_idx for p in parts]), name="+".join(p.name for p in parts[:2]) + "...")
+
+
+def config4_chunked(num_attrs: int = 2659, seed: int = 4, contigs: int = 1_000_000, mean_domains: float = 25.0,
+                    unknown_fraction: float = 0.05, contig_range=None, chunk: int = 8192, threads: int = 0) -> CsrBatch:
+    """Config 4 at sizes where one global sort of a billion (gene, id) keys would take minutes: the same contig lengths
+    as ``config4`` (so the same G), the attribute ids drawn per chunk of ``chunk`` contigs from ``default_rng([seed, j])``
+    — chunks are independent, run on ``threads`` host threads (0 = all), and a rank that owns contigs
+    ``contig_range = (c0, c1)`` generates only the chunks it needs.  Not the same ids as ``config4`` (same distribution)."""
+    import concurrent.futures
+    import os
+
+    lens = config4_lengths(seed, contigs)
+    c0, c1 = (0, contigs) if contig_range is None else contig_range
+    if c1 <= c0:
+        return CsrBatch(numpy.zeros(1, dtype=numpy.int32), numpy.zeros(1, dtype=numpy.int32), numpy.zeros(0, dtype=numpy.int32))
+    first, last = c0 // chunk, (c1 - 1) // chunk
+
+    def one(j: int) -> CsrBatch:
+        a, b = max(c0, j * chunk), min(c1, (j + 1) * chunk)
+        rng = numpy.random.default_rng([seed, j])
+        whole = make_batch(rng, lens[j * chunk:min(contigs, (j + 1) * chunk)], mean_domains, num_attrs, unknown_fraction)
+        return whole if (a, b) == (j * chunk, min(contigs, (j + 1) * chunk)) else whole.slice_contigs(a - j * chunk, b - j * chunk)
+
+    n = threads or len(os.sched_getaffinity(0))
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, n)) as pool:
+        parts = list(pool.map(one, range(first, last + 1)))
+    out = concat_batches(parts)
+    out.name = f"config4_chunked(seed={seed})[{c0}:{c1}]"
+    return out
 
 
 def config5(num_attrs: int = 2659, seed: int = 5, contigs: int = 100, genes: int = 5000, mean_domains: float = 25.0) -> CsrBatch:

@@ -494,7 +494,7 @@ class StandInEngine:
         self.weights = weights
         self.accession_batches = 0
 
-    def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window, step, pad, accessions=False):
+    def marginals_windowed(self, contig_ptr, gene_ptr, attr_idx, *, window, step, pad, accessions=False, f64_arith=False):
         from oracle import crf_oracle
 
         gene_ptr, attr_idx = numpy.asarray(gene_ptr), numpy.asarray(attr_idx)
