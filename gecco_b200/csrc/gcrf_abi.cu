@@ -12,6 +12,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 namespace {
 
 thread_local char g_error[512] = "";
@@ -34,6 +36,14 @@ int fail_cuda(cudaError_t err, const char *what) {
         cudaError_t err__ = (call);                            \
         if (err__ != cudaSuccess) return fail_cuda(err__, #call); \
     } while (0)
+
+// NVTX range over a scope: stage (validation + H2D), launch (kernels), finish (D2H + sync) of every ABI call
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct DeviceBuffer {
     void *ptr = nullptr;
@@ -146,6 +156,7 @@ struct Batch {
 // Validates the common arguments and, in host-pointer mode, stages the inputs on the device.
 int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const void *attr_idx_any,
                 int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags, Batch *b, bool defer_copies = false) {
+    NvtxRange range("gcrf:stage");
     const int32_t *attr_idx = static_cast<const int32_t *>(attr_idx_any);
     const bool idx16 = (flags & GCRF_FLAG_IDX_U16) != 0;
     const bool accessions = (flags & GCRF_FLAG_ACCESSIONS) != 0;
@@ -236,6 +247,7 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
 
 int finish_batch(gcrf_model *m, const Batch &b, void *out) {
     if (b.device_ptrs || b.csr.G == 0) return GCRF_OK;
+    NvtxRange range("gcrf:finish");
     GCRF_CUDA(cudaMemcpyAsync(out, b.d_out, b.out_bytes, cudaMemcpyDeviceToHost, m->stream));
     GCRF_CUDA(cudaStreamSynchronize(m->stream));
     return GCRF_OK;
@@ -422,6 +434,7 @@ namespace {
 
 // Plans and enqueues the windowed kernel for one (sub-)batch on the handle's stream.
 int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
+    NvtxRange range("gcrf:launch windowed");
     gcrf::WindowedPlan plan{};
     // GCRF_FORCE_GENERIC=1 routes W=20 through the generic kernel too (A/B testing of the two device paths)
     const char *force = getenv("GCRF_FORCE_GENERIC");
@@ -569,6 +582,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         }
         const size_t work_bytes = gcrf::exact_work_bytes(G, window, m->num_sms);
         if (work_bytes) GCRF_CUDA(m->b_work.reserve(work_bytes));
+        NvtxRange range("gcrf:launch exact f64");
         if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
         cudaError_t err = gcrf::launch_exact(ex, static_cast<double *>(m->b_work.ptr), m->num_sms, m->stream, &m->launches);
         if (err != cudaSuccess) return fail_cuda(err, "launch_exact");
@@ -624,6 +638,7 @@ int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *g
     args.m10 = m->m10;
     args.m11 = m->m11;
     args.scratch = static_cast<double *>(m->b_scratch.ptr);
+    NvtxRange range("gcrf:launch chain");
     if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
     cudaError_t err = gcrf::launch_chain(args, m->num_sms, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_chain");
@@ -764,6 +779,7 @@ int gcrf_segments(gcrf_model *m, const int32_t *contig_ptr, const void *prob, co
         a.seg_ordinal = reinterpret_cast<int32_t *>(q);
     }
     GCRF_CUDA(m->b_scratch.reserve(gcrf::segments_scratch_bytes(G, m->num_sms)));
+    NvtxRange range("gcrf:launch segments");
     if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
     cudaError_t err = gcrf::launch_segments(a, m->b_scratch.ptr, m->num_sms, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_segments");

@@ -115,15 +115,6 @@ __device__ __forceinline__ int find_slice_contig(const int *sCp, int j, int kmax
 
 // Unary odds of one gene straight from global memory (prologue halo, oversized tiles, very long rows).
 template <typename PtrT>
-__device__ __forceinline__ float direct_unary_inl(const PtrT *gene_ptr, const int32_t *attr_idx, const float *table, uint32_t A,
-                                                  int g, float clampv) {
-    const int64_t rb = (int64_t)__ldg(gene_ptr + g), re = (int64_t)__ldg(gene_ptr + g + 1);
-    float delta = 0.f;
-    for (int64_t p = rb; p < re; ++p) delta += __ldg(table + min((uint32_t)__ldg(attr_idx + p), A));
-    return exp_fast(fminf(fmaxf(delta, -clampv), clampv));
-}
-
-template <typename PtrT>
 __device__ __noinline__ float direct_unary(const PtrT *gene_ptr, const int32_t *attr_idx, const float *table, uint32_t A,
                                            int g, float clampv) {
     const int64_t rb = (int64_t)__ldg(gene_ptr + g), re = (int64_t)__ldg(gene_ptr + g + 1);
@@ -134,32 +125,6 @@ __device__ __noinline__ float direct_unary(const PtrT *gene_ptr, const int32_t *
 
 // Window of a padded short contig (gecco/crf/__init__.py:216-227): n < W genes starting at local gene j,
 // (W-n)/2 empty items in front and the rest behind; writes the odds of its n genes to sQ.
-// (inlined twin for kernels whose register budget is set by setmaxnreg: ABI calls are not possible there)
-template <int W>
-__device__ __forceinline__ void padded_window_inl(const float *sU0, float *sQ, int j, int n, float m01, float m10, float m11) {
-    const int front = (W - n) >> 1;
-    float ra[W];
-    float rr = 0.f;
-#pragma unroll
-    for (int q = 0; q < W; ++q) {
-        const int p = q - front;
-        const float u = (p >= 0 && p < n) ? sU0[j + p] : 1.0f;
-        rr = q == 0 ? u : (fmaf(rr, m11, m01) * u) * rcp_fast(fmaf(rr, m10, 1.0f));
-        ra[q] = rr;
-    }
-    float ss = 1.0f;
-#pragma unroll
-    for (int q = W - 1; q >= 0; --q) {
-        const int p = q - front;
-        const bool real = p >= 0 && p < n;
-        if (real) sQ[j + p] = ra[q] * ss;
-        if (q > 0) {
-            const float w = (real ? sU0[j + p] : 1.0f) * ss;
-            ss = fmaf(w, m11, m10) * rcp_fast(fmaf(w, m01, 1.0f));
-        }
-    }
-}
-
 template <int W>
 __device__ __noinline__ void padded_window(const float *sU0, float *sQ, int j, int n, float m01, float m10, float m11) {
     const int front = (W - n) >> 1;

@@ -39,6 +39,7 @@ namespace gcrf {
 
 namespace {
 
+constexpr int kStreamSmemCap = 100 * 1024;  // largest dynamic shared memory a streaming CTA may ask for
 constexpr int kFewPerLane = 16;  // ids per lane of the one-warp walk used for tiles with <= 512 staged ids
 
 template <int W, int NT>
@@ -568,7 +569,9 @@ cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
     const StreamTiling<W, NT> tl(A);
     *bytes = tl.bytes();
     auto kernel = stream_kernel<W, NT, MINB, PtrT>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.bytes());
+    // The attribute is per kernel and device, not per launch: always raise it to the cap stream_supported() enforces, so
+    // that host threads with models of different sizes cannot lower it under each other's cached plans.
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemCap);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, NT, tl.bytes());
 }
@@ -601,7 +604,7 @@ bool stream_supported(const WindowedArgs &args) {
 #undef X
     if (!known) return false;
     const StreamTiling<20, 128> tl(args.model.A);  // the largest of the compiled windows
-    if (tl.bytes() > 100 * 1024) return false;
+    if (tl.bytes() > (size_t)kStreamSmemCap) return false;
     // tile arithmetic is 32-bit: G + one tile of slack must fit
     return args.csr.G < 0x7fff0000;
 }

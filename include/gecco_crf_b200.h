@@ -55,7 +55,12 @@ typedef enum gcrf_status {
 /* flags of the marginal calls */
 #define GCRF_FLAG_DEVICE_PTRS 0x1u /* contig_ptr/gene_ptr/attr_idx/out are device pointers on the
                                       handle's device; the call only enqueues work on the handle's
-                                      stream (gcrf_model_set_stream) and does not synchronise */
+                                      stream (gcrf_model_set_stream) and does not synchronise.
+                                      The arrays are trusted (no validation pass): contig_ptr strictly
+                                      increasing from 0 to G, gene_ptr non-decreasing from 0 to nnz.
+                                      attr_idx must be 16-byte aligned and READABLE up to the next
+                                      multiple of 4 elements past nnz (the streaming kernel moves ids
+                                      with 16-byte bulk copies; the over-read values are ignored) */
 #define GCRF_FLAG_OUT_F32     0x2u /* out is float[G] instead of double[G] */
 #define GCRF_FLAG_PTR64       0x4u /* gene_ptr is int64_t[G+1] (nnz >= 2^31); contig_ptr stays int32 */
 #define GCRF_FLAG_IDX_U16     0x20u /* attr_idx is uint16_t[nnz] (0xFFFF = unknown attribute; models with fewer than
