@@ -95,6 +95,7 @@ struct gcrf_model {
     cudaEvent_t ev_slice[kMaxSlices] = {};
     bool timed = false;
     bool timing = false;  // record events around the kernels (gcrf_model_set_timing)
+    bool ev_open = false; // ev_start already recorded by this call (in front of a widening / feature-extraction kernel)
     int64_t launches = 0;
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
@@ -124,6 +125,20 @@ bool non_decreasing(const T *p, int64_t n) {
     T bad = 0;
     for (int64_t i = 0; i < n; ++i) bad |= (T)(p[i + 1] - p[i]);
     return bad >= 0;
+}
+
+// Start of the timed region of a call (gcrf_model_set_timing): in front of the FIRST kernel it launches, which may be
+// the uint16 widening or the feature extraction inside stage_batch.
+cudaError_t timing_begin(gcrf_model *m) {
+    if (!m->timing || m->ev_open) return cudaSuccess;
+    m->ev_open = true;
+    return cudaEventRecord(m->ev_start, m->stream);
+}
+cudaError_t timing_end(gcrf_model *m) {
+    m->timed = m->timing;
+    if (!m->timing) return cudaSuccess;
+    m->ev_open = false;
+    return cudaEventRecord(m->ev_stop, m->stream);
 }
 
 // Host-side sanity checks of a CSR batch given as host pointers: O(C + G), so that no malformed pointer array can
@@ -185,6 +200,7 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
             return fail(GCRF_EINVAL, "device attr_idx must be 16-byte aligned");
         if (idx16) {  // widen into the library's own buffer
             GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
+            GCRF_CUDA(timing_begin(m));
             cudaError_t werr = gcrf::launch_widen_u16(static_cast<const uint16_t *>(attr_idx_any), static_cast<int32_t *>(m->b_attr.ptr),
                                                       nnz, m->num_sms, m->stream, &m->launches);
             if (werr != cudaSuccess) return fail_cuda(werr, "launch_widen_u16");
@@ -192,6 +208,7 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
         }
         if (accessions && nnz > 0) {  // accession -> attribute id, repeats inside a gene dropped, into the library's buffer
             GCRF_CUDA(m->b_attr.reserve((size_t)nnz * 4 + 64));
+            GCRF_CUDA(timing_begin(m));
             cudaError_t ferr = gcrf::launch_features(attr_idx, ptr64 ? nullptr : static_cast<const int32_t *>(gene_ptr),
                                                      ptr64 ? static_cast<const int64_t *>(gene_ptr) : nullptr, G, nnz, m->d_lut,
                                                      m->lut_size, m->A, static_cast<int32_t *>(m->b_attr.ptr), m->num_sms,
@@ -221,12 +238,14 @@ int stage_batch(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, 
             // half the PCIe bytes: the ids cross as uint16 and are widened on the device
             GCRF_CUDA(m->b_idx16.reserve((size_t)nnz * 2 + 16));
             GCRF_CUDA(cudaMemcpyAsync(m->b_idx16.ptr, attr_idx_any, (size_t)nnz * 2, cudaMemcpyHostToDevice, m->stream));
+            GCRF_CUDA(timing_begin(m));
             cudaError_t werr = gcrf::launch_widen_u16(static_cast<const uint16_t *>(m->b_idx16.ptr), static_cast<int32_t *>(m->b_attr.ptr),
                                                       nnz, m->num_sms, m->stream, &m->launches);
             if (werr != cudaSuccess) return fail_cuda(werr, "launch_widen_u16");
         } else if (nnz > 0 && accessions) {
             GCRF_CUDA(m->b_acc.reserve((size_t)nnz * 4 + 16));
             GCRF_CUDA(cudaMemcpyAsync(m->b_acc.ptr, attr_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, m->stream));
+            GCRF_CUDA(timing_begin(m));
             cudaError_t ferr = gcrf::launch_features(static_cast<const int32_t *>(m->b_acc.ptr),
                                                      ptr64 ? nullptr : static_cast<const int32_t *>(m->b_gene.ptr),
                                                      ptr64 ? static_cast<const int64_t *>(m->b_gene.ptr) : nullptr, G, nnz, m->d_lut,
@@ -447,12 +466,11 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
                     "GCRF_FLAG_F64 accepts any window", args.window, m->A, gcrf::windowed_max_window(m->A));
     }
     if (err != cudaSuccess) return fail_cuda(err, "plan_windowed");
-    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    GCRF_CUDA(timing_begin(m));
     err = fast ? gcrf::launch_stream(args, plan, m->stream, &m->launches)
                : gcrf::launch_windowed(args, plan, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_windowed");
-    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-    m->timed = m->timing;
+    GCRF_CUDA(timing_end(m));
     if (prof) {
         unsigned long long h[16];
         GCRF_CUDA(cudaMemcpyAsync(h, args.prof, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
@@ -536,6 +554,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
                             int64_t C, int64_t G, int64_t nnz, int32_t window, int32_t step, int32_t pad, void *out,
                             uint32_t flags) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    m->ev_open = false;
     // gecco/_meta.py:127-130
     if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
     if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
@@ -583,11 +602,10 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         const size_t work_bytes = gcrf::exact_work_bytes(G, window, m->num_sms);
         if (work_bytes) GCRF_CUDA(m->b_work.reserve(work_bytes));
         NvtxRange range("gcrf:launch exact f64");
-        if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+        GCRF_CUDA(timing_begin(m));
         cudaError_t err = gcrf::launch_exact(ex, static_cast<double *>(m->b_work.ptr), m->num_sms, m->stream, &m->launches);
         if (err != cudaSuccess) return fail_cuda(err, "launch_exact");
-        if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-        m->timed = m->timing;
+        GCRF_CUDA(timing_end(m));
         return finish_batch(m, b, out);
     }
 
@@ -623,6 +641,7 @@ extern "C" {
 int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const void *attr_idx,
                          int64_t C, int64_t G, int64_t nnz, void *out, uint32_t flags) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    m->ev_open = false;
     DeviceGuard guard(m->device);
     Batch b;
     int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b);
@@ -639,11 +658,10 @@ int gcrf_marginals_chain(gcrf_model *m, const int32_t *contig_ptr, const void *g
     args.m11 = m->m11;
     args.scratch = static_cast<double *>(m->b_scratch.ptr);
     NvtxRange range("gcrf:launch chain");
-    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    GCRF_CUDA(timing_begin(m));
     cudaError_t err = gcrf::launch_chain(args, m->num_sms, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_chain");
-    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-    m->timed = m->timing;
+    GCRF_CUDA(timing_end(m));
     return finish_batch(m, b, out);
 }
 
@@ -780,11 +798,10 @@ int gcrf_segments(gcrf_model *m, const int32_t *contig_ptr, const void *prob, co
     }
     GCRF_CUDA(m->b_scratch.reserve(gcrf::segments_scratch_bytes(G, m->num_sms)));
     NvtxRange range("gcrf:launch segments");
-    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_start, m->stream));
+    GCRF_CUDA(timing_begin(m));
     cudaError_t err = gcrf::launch_segments(a, m->b_scratch.ptr, m->num_sms, m->stream, &m->launches);
     if (err != cudaSuccess) return fail_cuda(err, "launch_segments");
-    if (m->timing) GCRF_CUDA(cudaEventRecord(m->ev_stop, m->stream));
-    m->timed = m->timing;
+    GCRF_CUDA(timing_end(m));
     int64_t count = 0;
     GCRF_CUDA(cudaMemcpyAsync(&count, a.count, sizeof(count), cudaMemcpyDeviceToHost, m->stream));
     GCRF_CUDA(cudaStreamSynchronize(m->stream));

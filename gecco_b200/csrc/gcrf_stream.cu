@@ -39,6 +39,14 @@ namespace gcrf {
 
 namespace {
 
+// CTA geometry of the production kernel; -DGCRF_STREAM_NT / -DGCRF_STREAM_MINB build A/B variants (tools/build_variant.sh)
+#ifndef GCRF_STREAM_NT
+#define GCRF_STREAM_NT 128
+#endif
+#ifndef GCRF_STREAM_MINB
+#define GCRF_STREAM_MINB 4
+#endif
+constexpr int kNT = GCRF_STREAM_NT, kMinB = GCRF_STREAM_MINB;
 constexpr int kStreamSmemCap = 100 * 1024;  // largest dynamic shared memory a streaming CTA may ask for
 constexpr int kFewPerLane = 16;  // ids per lane of the one-warp walk used for tiles with <= 512 staged ids
 
@@ -53,7 +61,7 @@ struct StreamTiling {
     static constexpr int keep = ng - tile_out;     // genes carried over from the previous tile
     static_assert(tile_out + 1 <= 2 * NT, "two row pointers per thread must cover a tile's new genes");
     static_assert(keep <= NT, "the ring carry is one gene per thread");
-    static_assert(keep + 1 <= NT - 32, "the last warp holds no halo row pointer (it runs the contig search instead)");
+    static_assert(keep + 1 <= NT, "one halo row pointer per thread (with NT >= keep + 33 the last warp holds none and only runs the contig search)");
     int off_idx, off_pool, off_u0, off_q, off_sp, off_cp, off_stat, words;
     __host__ __device__ explicit StreamTiling(int A) {
         int o = round_up4s(A + 1);
@@ -583,16 +591,16 @@ cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
 
 template <int W>
 cudaError_t configure_window(const WindowedArgs &args, int *per_sm, size_t *bytes, int *tile_out) {
-    *tile_out = StreamTiling<W, 128>::tile_out;
-    return args.csr.gene_ptr64 ? configure_stream<W, 128, 4, int64_t>(args.model.A, per_sm, bytes)
-                               : configure_stream<W, 128, 4, int32_t>(args.model.A, per_sm, bytes);
+    *tile_out = StreamTiling<W, kNT>::tile_out;
+    return args.csr.gene_ptr64 ? configure_stream<W, kNT, kMinB, int64_t>(args.model.A, per_sm, bytes)
+                               : configure_stream<W, kNT, kMinB, int32_t>(args.model.A, per_sm, bytes);
 }
 
 template <int W>
 cudaError_t launch_window(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int num_tiles, int tiles_per_cta) {
     return args.csr.gene_ptr64
-               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, 128, 4, int64_t>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
-               : cudaLaunchKernelEx(&cfg, stream_kernel<W, 128, 4, int32_t>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
+               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int64_t>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
+               : cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int32_t>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
 }
 
 }  // namespace
@@ -603,7 +611,7 @@ bool stream_supported(const WindowedArgs &args) {
     GCRF_STREAM_WINDOWS(X)
 #undef X
     if (!known) return false;
-    const StreamTiling<20, 128> tl(args.model.A);  // the largest of the compiled windows
+    const StreamTiling<20, kNT> tl(args.model.A);  // the largest of the compiled windows
     if (tl.bytes() > (size_t)kStreamSmemCap) return false;
     // tile arithmetic is 32-bit: G + one tile of slack must fit
     return args.csr.G < 0x7fff0000;
@@ -629,12 +637,18 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
         cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.window = args.window;
         cache.per_sm = q; cache.bytes = b; cache.tile_out = tile_out;
     }
-    const int per_sm = cache.per_sm;
+    int per_sm = cache.per_sm;
     const size_t bytes = cache.bytes;
+#ifdef GCRF_TUNING
+    if (const char *cap = getenv("GCRF_CTAS_PER_SM")) {  // occupancy experiments: fewer resident CTAs than fit
+        const int want = atoi(cap);
+        if (want >= 1 && want < per_sm) per_sm = want;
+    }
+#endif
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    plan->threads = 128;
+    plan->threads = kNT;
     plan->tile_out = cache.tile_out;
-    plan->chunk = 128 * kWalk;
+    plan->chunk = kNT * kWalk;
     plan->smem_bytes = bytes;
     plan->num_tiles = (args.csr.G + plan->tile_out - 1) / plan->tile_out;
     plan->ctas_per_sm = per_sm;
@@ -652,7 +666,7 @@ cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cu
     const int nt_ = (int)plan.num_tiles, tpc = plan.tiles_per_cta;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(plan.grid);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(kNT);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

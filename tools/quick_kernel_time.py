@@ -14,7 +14,7 @@ from gecco_b200._lib import CRFEngine
 w = model_io.load_tsv_model(model_io.bundled_model_dir())
 mean_domains = float(os.environ.get("QK_DOMAINS", "25"))
 window = int(os.environ.get("QK_WINDOW", "20"))
-b = synth.config2(len(w.attrs), mean_domains=mean_domains)
+b = synth.config2(len(w.attrs), mean_domains=mean_domains, contigs=int(os.environ.get("QK_CONTIGS", "10000")))
 dev = torch.device("cuda:0")
 eng = CRFEngine(w, 0)
 eng.set_timing(True)
