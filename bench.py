@@ -415,10 +415,7 @@ def run_ours(args) -> None:
         pout32 = PinnedArray((batch.G,), numpy.float32)
         e2e_steps = max(3, min(args.steps, 10))
 
-        def e2e_leg(ids_pin, out_pin, f32: bool, **kw):
-            def one():
-                engine.marginals_windowed(pins[0].array, pins[1].array, ids_pin.array, window=WINDOW, step=STEP, pad=PAD,
-                                          out=out_pin.array, f32=f32, **kw)
+        def e2e_leg(one, h2d: int, out_pin):
             for _ in range(2):
                 one()
             barrier()
@@ -429,22 +426,37 @@ def run_ours(args) -> None:
             mine = time.perf_counter() - t0
             secs = max_over_ranks(mine)
             barrier()
-            h2d = int(pins[0].array.nbytes + pins[1].array.nbytes + ids_pin.array.nbytes)
             d2h = int(out_pin.array.nbytes)
-            return {"value": total_genes * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            return {"value": total_genes * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * secs / e2e_steps,
                     "this_rank_pcie_gbs": (h2d + d2h) * e2e_steps / mine / 1e9}
 
-        # headline: uint16 ids in (GCRF_FLAG_IDX_U16; the packers emit them natively for vocabularies < 65,535), f64 out
-        e2e = e2e_leg(pins[3], pout, False)
-        e2e["layout"] = "int32 row pointers, uint16 attribute ids, float64 marginals"
+        def csr_call(ids_pin, out_pin, f32):
+            return lambda: engine.marginals_windowed(pins[0].array, pins[1].array, ids_pin.array, window=WINDOW, step=STEP,
+                                                     pad=PAD, out=out_pin.array, f32=f32)
+
+        def csr_bytes(ids_pin):
+            return pins[0].array.nbytes + pins[1].array.nbytes + ids_pin.array.nbytes
+
+        # headline: the compact wire format (gcrf_wire_encode: sorted ids as LEB128 deltas, one-byte row lengths, one
+        # page-locked block — what the packers hand to a bulk call), float64 marginals back
+        from gecco_b200._lib import WireBatch
+
+        wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, len(weights.attrs))
+        e2e = e2e_leg(lambda: engine.marginals_windowed_wire(wire, window=WINDOW, step=STEP, pad=PAD, out=pout.array), wire.nbytes, pout)
+        e2e["layout"] = "gcrf_wire block (int32 contig_ptr, uint8 ids/bytes per gene, LEB128 delta stream of the sorted ids), float64 marginals"
         e2e["bit_identical_to_device_path"] = bool(numpy.array_equal(pout.array, out_f32_arith))
-        e2e_i32 = e2e_leg(pins[2], pout, False)
-        e2e_i32["layout"] = "int32 row pointers, int32 attribute ids, float64 marginals"
+        e2e_u16 = e2e_leg(csr_call(pins[3], pout, False), csr_bytes(pins[3]), pout)
+        e2e_u16["layout"] = "int32 row pointers, uint16 attribute ids, float64 marginals"
+        e2e_u16["bit_identical_to_device_path"] = bool(numpy.array_equal(pout.array, out_f32_arith))
+        e2e_i32 = e2e_leg(csr_call(pins[2], pout, False), csr_bytes(pins[2]), pout)
+        e2e_i32["layout"] = "int32 row pointers, int32 attribute ids, float64 marginals (the CSR layout of SURVEY.md 8(b))"
         e2e_i32["bit_identical_to_device_path"] = bool(numpy.array_equal(pout.array, out_f32_arith))
-        compact = e2e_leg(pins[3], pout32, True)
-        compact["layout"] = "int32 row pointers, uint16 attribute ids, float32 marginals (the FP32 results un-widened)"
+        compact = e2e_leg(lambda: engine.marginals_windowed_wire(wire, window=WINDOW, step=STEP, pad=PAD, out=pout32.array, f32=True),
+                          wire.nbytes, pout32)
+        compact["layout"] = "gcrf_wire block, float32 marginals (the FP32 results un-widened)"
         compact["identical_to_float32_of_device_path"] = bool(numpy.array_equal(pout32.array, out_f32_arith.astype(numpy.float32)))
+        wire.close()
         per_rank_gbs = [e2e["this_rank_pcie_gbs"]]
         if world > 1:
             t = torch.tensor([e2e["this_rank_pcie_gbs"]], dtype=torch.float64, device=dev)
@@ -657,6 +669,7 @@ def run_ours(args) -> None:
                                  "their prologues through programmatic dependent launch and are slightly faster"},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "e2e_uint16_ids": e2e_u16,
             "e2e_int32_ids": e2e_i32,
             "e2e_compact": compact,
             "f64": f64_line,

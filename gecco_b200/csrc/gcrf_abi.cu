@@ -14,6 +14,9 @@
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
+// internal: a nested call (wire batch -> regular entry point) keeps the timed region its caller opened
+#define GCRF_FLAG_KEEP_TIMING 0x40000000u
+
 namespace {
 
 thread_local char g_error[512] = "";
@@ -100,6 +103,7 @@ struct gcrf_model {
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
     DeviceBuffer b_unary, b_pool, b_work;  // GCRF_FLAG_F64: exp of the state scores, max-pool (float output), work area
+    DeviceBuffer b_wire, b_wire_sums;      // gcrf_marginals_windowed_wire: the block as it came over PCIe, scan scratch
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
     DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
 };
@@ -414,6 +418,8 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_seg.release();
     m->b_idx16.release();
     m->b_acc.release();
+    m->b_wire.release();
+    m->b_wire_sums.release();
     m->b_unary.release();
     m->b_pool.release();
     m->b_work.release();
@@ -554,7 +560,8 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
                             int64_t C, int64_t G, int64_t nnz, int32_t window, int32_t step, int32_t pad, void *out,
                             uint32_t flags) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
-    m->ev_open = false;
+    if (!(flags & GCRF_FLAG_KEEP_TIMING)) m->ev_open = false;
+    flags &= ~(uint32_t)GCRF_FLAG_KEEP_TIMING;
     // gecco/_meta.py:127-130
     if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
     if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
@@ -632,6 +639,48 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     rc = launch_windowed_path(m, args, prof);
     if (rc != GCRF_OK) return rc;
     return finish_batch(m, b, out);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int gcrf_marginals_windowed_wire(gcrf_model *m, const gcrf_wire *w, int32_t window, int32_t step, int32_t pad, void *out,
+                                 uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (!w) return fail(GCRF_EINVAL, "wire batch is NULL");
+    if (flags & ~(uint32_t)(GCRF_FLAG_OUT_F32 | GCRF_FLAG_F64)) return fail(GCRF_EINVAL, "only GCRF_FLAG_OUT_F32 / GCRF_FLAG_F64 apply to a wire batch");
+    const int64_t C = gcrf_wire_contigs(w), G = gcrf_wire_genes(w), nnz = gcrf_wire_ids(w);
+    if (G == 0) return GCRF_OK;
+    if (!out) return fail(GCRF_EINVAL, "out is NULL");
+    m->ev_open = false;
+    DeviceGuard guard(m->device);
+    const size_t out_bytes = (size_t)G * ((flags & GCRF_FLAG_OUT_F32) ? 4 : 8);
+    {
+        NvtxRange range("gcrf:stage wire");
+        GCRF_CUDA(m->b_wire.reserve(gcrf::wire_total(w)));
+        GCRF_CUDA(m->b_wire_sums.reserve((size_t)gcrf::wire_chunks(G) * 2 * sizeof(int64_t)));
+        GCRF_CUDA(m->b_gene.reserve((size_t)(G + 1) * 4));
+        GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
+        GCRF_CUDA(m->b_out.reserve(out_bytes));
+        // ONE host-to-device copy: contig_ptr, both length arrays and the id stream share a page-locked block
+        GCRF_CUDA(cudaMemcpyAsync(m->b_wire.ptr, gcrf::wire_block(w), gcrf::wire_total(w), cudaMemcpyHostToDevice, m->stream));
+        GCRF_CUDA(timing_begin(m));
+        const char *d = static_cast<const char *>(m->b_wire.ptr);
+        cudaError_t derr = gcrf::launch_wire_decode(d + gcrf::wire_off_len_ids(w), d + gcrf::wire_off_len_bytes(w), gcrf::wire_len_width(w),
+                                                    reinterpret_cast<const uint8_t *>(d + gcrf::wire_off_stream(w)), G,
+                                                    static_cast<int64_t *>(m->b_wire_sums.ptr), static_cast<int32_t *>(m->b_gene.ptr),
+                                                    static_cast<int32_t *>(m->b_attr.ptr), m->stream, &m->launches);
+        if (derr != cudaSuccess) return fail_cuda(derr, "launch_wire_decode");
+    }
+    // the decoded batch is a device-pointer batch of the regular entry point; its result lands in the library's buffer
+    const int rc = gcrf_marginals_windowed(m, static_cast<const int32_t *>(m->b_wire.ptr), m->b_gene.ptr, m->b_attr.ptr, C, G, nnz, window,
+                                           step, pad, m->b_out.ptr, flags | GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_KEEP_TIMING);
+    if (rc != GCRF_OK) return rc;
+    NvtxRange range("gcrf:finish");
+    GCRF_CUDA(cudaMemcpyAsync(out, m->b_out.ptr, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+    GCRF_CUDA(cudaStreamSynchronize(m->stream));
+    return GCRF_OK;
 }
 
 }  // extern "C"

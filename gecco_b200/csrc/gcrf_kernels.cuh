@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct gcrf_wire;  // include/gecco_crf_b200.h
+
 namespace gcrf {
 
 // Two-label model folded for the device ("two-state simplifications"):
@@ -109,6 +111,18 @@ cudaError_t launch_features(const int32_t *accession, const int32_t *gene_ptr32,
 
 // uint16 attribute ids -> int32 (0xFFFF -> -1); out holds at least round_up(n, 8) entries
 cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int num_sms, cudaStream_t stream, int64_t *launches);
+
+// Compact wire format (gcrf_wire.cu): rebuild gene_ptr[G+1] / attr_idx[nnz] from the length arrays and the delta-coded
+// id stream; `sums` is scratch of 2 * wire_chunks(G) int64.
+int64_t wire_chunks(int64_t G);
+cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
+                               int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t stream_, int64_t *launches);
+const char *wire_block(const gcrf_wire *w);
+size_t wire_total(const gcrf_wire *w);
+size_t wire_off_len_ids(const gcrf_wire *w);
+size_t wire_off_len_bytes(const gcrf_wire *w);
+size_t wire_off_stream(const gcrf_wire *w);
+int32_t wire_len_width(const gcrf_wire *w);
 
 // Threshold + segment extraction (gcrf_segments.cu; gecco/refine.py:51-200, criterion "gecco").
 struct SegmentsArgs {

@@ -205,6 +205,35 @@ int gcrf_segments(gcrf_model *model, const int32_t *contig_ptr, const void *prob
                   double *seg_avg_p, double *seg_max_p, int64_t capacity, int64_t *n_segments, uint32_t flags);
 
 /*
+ * A compact wire format for host-buffer batches.  A host-pointer call is one PCIe copy (the kernels are ~2 % of it), so
+ * the bytes that cross are its cost: 4 per attribute id, 4 per gene (row pointer), 8 per gene (float64 marginal) in the
+ * CSR layout above.  gcrf_wire_encode packs the same batch into ONE page-locked block — contig_ptr unchanged, per gene the
+ * number of ids and of stream bytes (uint8 each, uint16 when a gene has more than 255), and per gene its ids SORTED
+ * ascending, unknown ids mapped to A, as LEB128 deltas: ~1.3 bytes per id for 25 ids out of 2,659 — and
+ * gcrf_marginals_windowed_wire copies that block, rebuilds gene_ptr / attr_idx on the device (three small kernels) and
+ * runs the regular kernels.  Results equal gcrf_marginals_windowed's on the unsorted batch bit for bit in the default
+ * FP32 arithmetic (row sums are exact integer sums; only rows long enough to take the float path, >= ~100 ids for the
+ * shipped model, can differ in the last bit).  With GCRF_FLAG_F64 the row sums run in the SORTED order, so the result is
+ * within a few ulps of the first-occurrence order of the reference, not bit-identical to it.  Combine with
+ * GCRF_FLAG_OUT_F32 to halve the bytes coming back (the FP32 results, un-widened).
+ * Replaces nothing in the reference (which never leaves the host); it is the packers' output format for bulk calls.
+ * The encoder is host code (no device needed); nnz must stay below 2^31, a gene below 65,536 ids.
+ */
+typedef struct gcrf_wire gcrf_wire;
+const char *gcrf_wire_last_error(void);
+int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int32_t *attr_idx, int64_t C, int64_t G,
+                     int64_t nnz, int32_t num_attrs, uint32_t flags /* GCRF_FLAG_PTR64 */, gcrf_wire **out);
+void gcrf_wire_destroy(gcrf_wire *wire);
+int64_t gcrf_wire_bytes(const gcrf_wire *wire);   /* size of the block = host-to-device bytes of a call */
+int64_t gcrf_wire_contigs(const gcrf_wire *wire);
+int64_t gcrf_wire_genes(const gcrf_wire *wire);
+int64_t gcrf_wire_ids(const gcrf_wire *wire);
+/* decode on the host (tests, debugging): gene_ptr[G+1], attr_idx[nnz] = the sorted batch the device will see */
+int gcrf_wire_decode_host(const gcrf_wire *wire, int32_t *gene_ptr, int32_t *attr_idx);
+int gcrf_marginals_windowed_wire(gcrf_model *model, const gcrf_wire *wire, int32_t window, int32_t step, int32_t pad,
+                                 void *out, uint32_t flags /* GCRF_FLAG_OUT_F32, GCRF_FLAG_F64 */);
+
+/*
  * Pinned host memory helpers so that host-pointer calls can run their copies at PCIe speed
  * (pageable buffers are accepted everywhere, they are just slower).
  */

@@ -1,0 +1,80 @@
+"""The compact wire format (gcrf_wire_*): host encoder / decoder on the CPU, the device decoder + marginals on the GPU."""
+import numpy
+import pytest
+
+from gecco_b200 import synth
+from gecco_b200._lib import WireBatch
+
+
+def sorted_reference(batch, A):
+    """What the wire holds: every gene's ids ascending, ids outside [0, A) replaced by A."""
+    ids = numpy.where((batch.attr_idx >= 0) & (batch.attr_idx < A), batch.attr_idx, A).astype(numpy.int64)
+    gene_of = numpy.repeat(numpy.arange(batch.G, dtype=numpy.int64), numpy.diff(batch.gene_ptr))
+    order = numpy.lexsort((ids, gene_of))
+    return ids[order].astype(numpy.int32)
+
+
+@pytest.mark.parametrize("make", ["ragged", "dense", "empty_genes", "long_rows", "nothing"])
+def test_encode_decode_round_trip(weights, make):
+    A = len(weights.attrs)
+    rng = numpy.random.default_rng(3)
+    if make == "ragged":
+        batch = synth.ragged_edge_cases(A)
+    elif make == "dense":
+        batch = synth.config2(A, contigs=60)
+    elif make == "empty_genes":
+        batch = synth.make_batch(rng, numpy.array([5, 1, 30]), 0.2, A, 0.3)
+    elif make == "long_rows":  # rows beyond 255 ids: the length arrays switch to uint16
+        batch = synth.make_batch(rng, numpy.array([3, 40]), 400.0, A, 0.05)
+        assert numpy.diff(batch.gene_ptr).max() > 255
+    else:
+        batch = synth.CsrBatch(numpy.zeros(1, dtype=numpy.int32), numpy.zeros(1, dtype=numpy.int32), numpy.zeros(0, dtype=numpy.int32))
+    wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, A)
+    assert (wire.C, wire.G, wire.nnz) == (batch.C, batch.G, batch.nnz)
+    gene_ptr, attr_idx = wire.decode()
+    assert numpy.array_equal(gene_ptr, batch.gene_ptr)
+    assert numpy.array_equal(attr_idx, sorted_reference(batch, A))
+    if make == "dense":
+        plain = batch.contig_ptr.nbytes + batch.gene_ptr.nbytes + batch.attr_idx.nbytes
+        assert wire.nbytes < 0.42 * plain  # ~1.3 bytes per id + 2 per gene against 4 + 4
+    # int64 row pointers encode to the same block
+    again = WireBatch(batch.contig_ptr, batch.gene_ptr.astype(numpy.int64), batch.attr_idx, A)
+    assert again.nbytes == wire.nbytes and numpy.array_equal(again.decode()[1], attr_idx)
+
+
+def test_encoder_rejects_malformed_row_pointers(weights):
+    from gecco_b200._lib import GcrfError
+
+    with pytest.raises(GcrfError, match="non-decreasing"):
+        WireBatch(numpy.array([0, 2]), numpy.array([0, 3, 2]), numpy.array([1, 2], dtype=numpy.int32), 10)
+    with pytest.raises(GcrfError, match="start at 0 and end at nnz"):
+        WireBatch(numpy.array([0, 1]), numpy.array([0, 1]), numpy.array([1, 2], dtype=numpy.int32), 10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", ["ragged", "dense", "sparse", "long_rows"])
+def test_wire_call_equals_the_plain_call(engine, weights, make):
+    """Bit for bit in FP32 arithmetic (exact integer row sums: the order inside a row does not matter); the f64 path
+    sums in the sorted order, i.e. within a few ulps of the first-occurrence order."""
+    A = len(weights.attrs)
+    rng = numpy.random.default_rng(5)
+    batch = {"ragged": lambda: synth.ragged_edge_cases(A), "dense": lambda: synth.config2(A, contigs=300),
+             "sparse": lambda: synth.config2(A, contigs=300, mean_domains=1.4),
+             "long_rows": lambda: synth.make_batch(rng, numpy.array([3, 40, 25]), 300.0, A, 0.05)}[make]()
+    # unsorted rows on the plain side: the wire sorts, the result must not care
+    shuffled = batch.attr_idx.copy()
+    for g in range(0, batch.G, 3):
+        a, b = int(batch.gene_ptr[g]), int(batch.gene_ptr[g + 1])
+        shuffled[a:b] = shuffled[a:b][::-1]
+    wire = WireBatch(batch.contig_ptr, batch.gene_ptr, shuffled, A)
+    for window, step, pad in ((20, 1, True), (5, 2, False)):
+        plain = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, shuffled, window=window, step=step, pad=pad)
+        got = engine.marginals_windowed_wire(wire, window=window, step=step, pad=pad)
+        if make == "long_rows":  # rows past the fixed-point guard take the float path: same value up to summation order
+            assert numpy.allclose(got, plain, rtol=0, atol=1e-6, equal_nan=True)
+        else:
+            assert numpy.array_equal(got, plain, equal_nan=True)
+        got32 = engine.marginals_windowed_wire(wire, window=window, step=step, pad=pad, f32=True)
+        assert got32.dtype == numpy.float32 and numpy.array_equal(got32, got.astype(numpy.float32), equal_nan=True)
+    exact = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, shuffled, f64_arith=True)
+    assert numpy.allclose(engine.marginals_windowed_wire(wire, f64_arith=True), exact, rtol=0, atol=1e-12, equal_nan=True)

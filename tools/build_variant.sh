@@ -6,7 +6,7 @@ name=$1; shift
 cd "$(dirname "$0")/../gecco_b200/csrc"
 mkdir -p _build/var_$name
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in gcrf_abi gcrf_windowed gcrf_stream gcrf_chain gcrf_features gcrf_segments gcrf_exact; do
+for f in gcrf_abi gcrf_windowed gcrf_stream gcrf_chain gcrf_features gcrf_segments gcrf_exact gcrf_wire; do
   extra=""; [ $f = gcrf_exact ] && extra="-fmad=false"
   nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC $extra "$@" -c $f.cu -o _build/var_$name/$f.o &
 done
