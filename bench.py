@@ -605,6 +605,38 @@ def run_ours(args) -> None:
         # parity: every rank checks ITS contigs' slice of the gathered array against the oracle on its shard
         got = gathered[rank * gmax: rank * gmax + shard.G].cpu().numpy() if world > 1 else local[: shard.G].cpu().numpy()
         err = max_over_ranks(max_abs_err(got, oracle_full(weights, shard)))
+        # ---- the gather fused into the kernel: results stored straight into every rank's output array over NVLink
+        #      (peer stores, or one multimem.st per result to the NVLS multicast address), a device-side barrier instead
+        #      of a collective (gcrf_marginals_windowed_peers, gecco_b200/sharding.py FusedGather)
+        fused = {}
+        if world > 1:
+            offs = numpy.concatenate([[0], numpy.cumsum(sizes)])
+            for name, mc in (("peer_stores", False), ("nvls_multicast", True)):
+                try:
+                    fg = sharding.FusedGather(sizes, dev, multicast=mc)
+                    if mc and not fg.multicast:
+                        fused[name] = {"unavailable": "no NVLS multicast support reported by torch symmetric memory"}
+                        continue
+                    for _ in range(3):
+                        res = fg.predict(engine, ds, window=WINDOW, step=STEP, pad=PAD)
+                    barrier()
+                    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    f0.record(stream)
+                    for _ in range(sh_steps):
+                        res = fg.predict(engine, ds, window=WINDOW, step=STEP, pad=PAD)
+                    f1.record(stream)
+                    barrier()
+                    ms_f = max_over_ranks(f0.elapsed_time(f1)) / sh_steps
+                    same = all(bool(torch.equal(res[int(offs[r]):int(offs[r + 1])], gathered[r * gmax: r * gmax + sizes[r]])) for r in range(world))
+                    same = reduce_ranks(1.0 if same else 0.0, dist.ReduceOp.MIN) == 1.0
+                    fused[name] = {"value": int(cptr[-1]) / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f,
+                                   "equal_to_nccl_all_gather_on_every_rank": same,
+                                   "note": "two device-side barriers per step inside the timed region (before: nobody still reads the "
+                                           "previous result; after: every rank's stores have landed)"}
+                    del fg, res
+                except Exception as err:  # symmetric memory is a torch-private API: report, do not fail the bench
+                    fused[name] = {"unavailable": f"{type(err).__name__}: {err}"[:300]}
+            engine.set_stream(stream.cuda_stream)
         # the same pass with the shard coming from (pinned) host memory every step: per-rank H2D inside the timed region
         with bound_to_gpu(local_rank, rank_slot=local_rank, slots=slots):
             hp = [PinnedArray(a.shape, a.dtype) for a in (shard.contig_ptr, shard.gene_ptr, shard.attr_idx)]
@@ -641,6 +673,7 @@ def run_ours(args) -> None:
                    "ms_gather": ms_gather, "gather_bytes": int(8 * gmax * world) if world > 1 else 0,
                    "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) on the kernel's stream" if world > 1 else None,
                    "steps": sh_steps, "parity_max_abs_err_vs_oracle": err, "parity_genes_checked": G_all,
+                   "fused_gather": fused or None,
                    "with_host_ingest": {"value": G_all / (ms_ingest_total * 1e-3), "ms_per_step": ms_ingest_total,
                                         "h2d_bytes_this_rank": int(shard.contig_ptr.nbytes + shard.gene_ptr.nbytes + shard.attr_idx.nbytes),
                                         "note": "every rank copies its own shard from pinned host memory each step, then kernel + all-gather"}}

@@ -25,6 +25,7 @@ GCRF_FLAG_RESET_PER_CONTIG = 0x10
 GCRF_FLAG_IDX_U16 = 0x20
 GCRF_FLAG_ACCESSIONS = 0x40
 GCRF_FLAG_F64 = 0x80
+GCRF_FLAG_MULTICAST = 0x100
 
 # every symbol include/gecco_crf_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTED_SYMBOLS = (
@@ -36,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "gcrf_model_set_stream",
     "gcrf_model_synchronize",
     "gcrf_marginals_windowed",
+    "gcrf_marginals_windowed_peers",
     "gcrf_marginals_chain",
     "gcrf_model_set_vocabulary",
     "gcrf_features_from_accessions",
@@ -125,6 +127,8 @@ def load_library() -> ctypes.CDLL:
     lib.gcrf_model_synchronize.argtypes = [vp]
     lib.gcrf_marginals_windowed.restype = ctypes.c_int
     lib.gcrf_marginals_windowed.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, u32]
+    lib.gcrf_marginals_windowed_peers.restype = ctypes.c_int
+    lib.gcrf_marginals_windowed_peers.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, vp, i32, i64, u32]
     lib.gcrf_marginals_chain.restype = ctypes.c_int
     lib.gcrf_marginals_chain.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp, u32]
     lib.gcrf_model_set_vocabulary.restype = ctypes.c_int
@@ -520,6 +524,22 @@ class CRFEngine:
         step = self.weights.window_step if step is None else step
         _check(self._lib, self._lib.gcrf_marginals_windowed(
             self._handle, contig_ptr, gene_ptr, attr_idx, C, G, nnz, int(window), int(step), int(bool(pad)), out, flags))
+
+    def marginals_windowed_peers(self, contig_ptr: int, gene_ptr: int, attr_idx: int, C: int, G: int, nnz: int, out: Optional[int],
+                                 peer_out: List[int], out_offset: int, *, window: Optional[int] = None,
+                                 step: Optional[int] = None, pad: bool = True, f32: bool = False, ptr64: bool = False,
+                                 multicast: bool = False) -> None:
+        """``gcrf_marginals_windowed_peers``: the windowed kernel on this GPU's shard, every result stored straight into the
+        output arrays of the peer GPUs (raw device addresses mapped into this process; with ``multicast`` one NVLS multicast
+        address) at ``out_offset + gene`` — the gather of a contig-sharded batch fused into the kernel.  Enqueues only."""
+        flags = GCRF_FLAG_DEVICE_PTRS | (GCRF_FLAG_OUT_F32 if f32 else 0) | (GCRF_FLAG_PTR64 if ptr64 else 0) | \
+            (GCRF_FLAG_MULTICAST if multicast else 0)
+        window = self.weights.window_size if window is None else window
+        step = self.weights.window_step if step is None else step
+        arr = (ctypes.c_void_p * max(1, len(peer_out)))(*[ctypes.c_void_p(int(p)) for p in peer_out])
+        _check(self._lib, self._lib.gcrf_marginals_windowed_peers(
+            self._handle, contig_ptr, gene_ptr, attr_idx, C, G, nnz, int(window), int(step), int(bool(pad)),
+            ctypes.c_void_p(out or 0), arr, len(peer_out), int(out_offset), flags))
 
     def features_from_accessions_device(self, accession: int, gene_ptr: int, G: int, nnz: int, out: int, *,
                                         ptr64: bool = False) -> None:

@@ -16,6 +16,10 @@
 
 // internal: a nested call (wire batch -> regular entry point) keeps the timed region its caller opened
 #define GCRF_FLAG_KEEP_TIMING 0x40000000u
+// internal: the call carries peer output arrays (gcrf_marginals_windowed_peers)
+#define GCRF_FLAG_HAS_PEERS 0x20000000u
+// internal: no local output array (results go to the peer arrays only)
+#define GCRF_FLAG_NO_LOCAL_OUT 0x10000000u
 
 namespace {
 
@@ -103,6 +107,8 @@ struct gcrf_model {
     DeviceBuffer b_contig, b_gene, b_attr, b_out, b_scratch;
     DeviceBuffer b_ann, b_seg;  // gcrf_segments: annotation marks, outputs + count
     DeviceBuffer b_unary, b_pool, b_work;  // GCRF_FLAG_F64: exp of the state scores, max-pool (float output), work area
+    void *peer_out[gcrf::WindowedArgs::kMaxPeers] = {};  // gcrf_marginals_windowed_peers: valid during that call only
+    int32_t n_peer_out = 0, peer_multicast = 0;
     DeviceBuffer b_wire, b_wire_sums;      // gcrf_marginals_windowed_wire: the block as it came over PCIe, scan scratch
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
     DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
@@ -465,6 +471,8 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
     const char *force = getenv("GCRF_FORCE_GENERIC");
     const bool want_generic = force && force[0] == '1';
     const bool fast = gcrf::stream_supported(args) && !want_generic;
+    if (!fast && args.n_peer_out > 0)
+        return fail(GCRF_EUNSUPPORTED, "peer output arrays need the streaming kernel (window 5, 10 or 20, FP32 arithmetic)");
     cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {
         cudaGetLastError();
@@ -561,7 +569,8 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
                             uint32_t flags) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
     if (!(flags & GCRF_FLAG_KEEP_TIMING)) m->ev_open = false;
-    flags &= ~(uint32_t)GCRF_FLAG_KEEP_TIMING;
+    const bool has_peers = (flags & GCRF_FLAG_HAS_PEERS) != 0, no_local_out = (flags & GCRF_FLAG_NO_LOCAL_OUT) != 0;
+    flags &= ~(uint32_t)(GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_HAS_PEERS | GCRF_FLAG_NO_LOCAL_OUT);
     // gecco/_meta.py:127-130
     if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
     if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
@@ -586,6 +595,8 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     int rc = stage_batch(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, out, flags, &b, slices > 1);
     if (rc != GCRF_OK || G == 0) return rc;
 
+    if ((flags & GCRF_FLAG_F64) && has_peers)
+        return fail(GCRF_EUNSUPPORTED, "peer output arrays need the streaming kernel (window 5, 10 or 20, FP32 arithmetic)");
     if (flags & GCRF_FLAG_F64) {
         // the reference's own arithmetic (gcrf_exact.cu)
         gcrf::ExactArgs ex{};
@@ -620,12 +631,17 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     args.model = m->dev;
     args.csr = b.csr;
     args.csr.gene_base = 0;
-    args.out = b.d_out;
+    args.out = no_local_out ? nullptr : b.d_out;
     args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
     args.window = window;
     args.step = step;
     args.pad = pad ? 1 : 0;
     args.prof = nullptr;
+    if (has_peers) {
+        for (int k = 0; k < m->n_peer_out; ++k) args.peer_out[k] = m->peer_out[k];
+        args.n_peer_out = m->n_peer_out;
+        args.peer_multicast = m->peer_multicast;
+    }
     {
         const char *skip = getenv("GCRF_DEBUG_SKIP");  // results are WRONG when set: timing experiments only
         args.debug_skip = skip ? atoi(skip) : 0;
@@ -639,6 +655,36 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     rc = launch_windowed_path(m, args, prof);
     if (rc != GCRF_OK) return rc;
     return finish_batch(m, b, out);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int gcrf_marginals_windowed_peers(gcrf_model *m, const int32_t *contig_ptr, const void *gene_ptr, const void *attr_idx, int64_t C,
+                                  int64_t G, int64_t nnz, int32_t window, int32_t step, int32_t pad, void *out,
+                                  void *const *peer_out, int32_t n_peer_out, int64_t out_offset, uint32_t flags) {
+    if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
+    if (n_peer_out < 0 || n_peer_out > gcrf::WindowedArgs::kMaxPeers)
+        return fail(GCRF_EINVAL, "between 0 and %d peer output arrays", gcrf::WindowedArgs::kMaxPeers);
+    if (n_peer_out > 0 && !peer_out) return fail(GCRF_EINVAL, "peer_out is NULL");
+    if (out_offset < 0) return fail(GCRF_EINVAL, "negative out_offset");
+    if (!(flags & GCRF_FLAG_DEVICE_PTRS)) return fail(GCRF_EINVAL, "peer output arrays are device memory: GCRF_FLAG_DEVICE_PTRS is required");
+    const bool multicast = (flags & GCRF_FLAG_MULTICAST) != 0;
+    if (multicast && n_peer_out != 1) return fail(GCRF_EINVAL, "GCRF_FLAG_MULTICAST takes exactly one (multicast) address");
+    const size_t item = (flags & GCRF_FLAG_OUT_F32) ? 4 : 8;
+    for (int k = 0; k < n_peer_out; ++k) {
+        if (!peer_out[k]) return fail(GCRF_EINVAL, "peer_out[%d] is NULL", k);
+        m->peer_out[k] = static_cast<char *>(peer_out[k]) + (size_t)out_offset * item;
+    }
+    m->n_peer_out = n_peer_out;
+    m->peer_multicast = multicast ? 1 : 0;
+    // `out` may be NULL here (results only go to the peer arrays); the regular entry point insists on an array
+    static char dummy;
+    const int rc = gcrf_marginals_windowed(m, contig_ptr, gene_ptr, attr_idx, C, G, nnz, window, step, pad, out ? out : &dummy,
+                                           (flags & ~(uint32_t)GCRF_FLAG_MULTICAST) | GCRF_FLAG_HAS_PEERS | (out ? 0u : GCRF_FLAG_NO_LOCAL_OUT));
+    m->n_peer_out = 0;
+    return rc;
 }
 
 }  // extern "C"

@@ -87,6 +87,32 @@ __device__ __forceinline__ void stage_ids(int32_t *sIdx, const int32_t *attr_idx
     }
 }
 
+// One result of the streaming kernel -> the local output array and, for a contig-sharded batch, straight into the
+// output arrays of the peer GPUs (plain stores through the NVLink peer mapping, or one multimem.st to an NVLS multicast
+// address that the switch replicates): the "gather" of the marginals happens while the kernel computes.
+__device__ __forceinline__ void store_result(const WindowedArgs &args, int gg, float p) {
+    if (args.out_f32) {
+        if (args.out) static_cast<float *>(args.out)[gg] = p;
+        if (args.n_peer_out) {
+            if (args.peer_multicast) {
+                asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(static_cast<float *>(args.peer_out[0]) + gg), "f"(p) : "memory");
+            } else {
+                for (int k = 0; k < args.n_peer_out; ++k) static_cast<float *>(args.peer_out[k])[gg] = p;
+            }
+        }
+    } else {
+        const double pd = (double)p;
+        if (args.out) static_cast<double *>(args.out)[gg] = pd;
+        if (args.n_peer_out) {
+            if (args.peer_multicast) {
+                asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(static_cast<double *>(args.peer_out[0]) + gg), "d"(pd) : "memory");
+            } else {
+                for (int k = 0; k < args.n_peer_out; ++k) static_cast<double *>(args.peer_out[k])[gg] = pd;
+            }
+        }
+    }
+}
+
 // Largest c in [0, C) with contig_ptr[c] <= g (g >= 0), one warp, 32 probes per round.
 __device__ int64_t warp_find_contig(const int32_t *contig_ptr, int64_t C, int64_t g, int lane) {
     int64_t lo = 0, hi = C;

@@ -46,6 +46,13 @@ struct WindowedArgs {
     int32_t window, step, pad;
     unsigned long long *prof;  // optional [16] cycle accumulators per kernel phase (nullptr = off); tuning aid
     int32_t debug_skip;        // tuning aid (GCRF_DEBUG_SKIP): 1 = skip the walk, 2 = skip the DP, 4 = skip pool/output
+    // gcrf_marginals_windowed_peers (streaming kernel only): besides `out` (may be nullptr) every result is stored to
+    // peer_out[k][gene], k < n_peer_out — the output arrays of the OTHER GPUs of a contig-sharded batch, mapped into this
+    // process over NVLink (pointers already offset to this shard's first gene).  peer_multicast: peer_out[0] is an NVLS
+    // multicast address — one multimem.st, replicated to every GPU by the switch.
+    static constexpr int kMaxPeers = 8;
+    void *peer_out[kMaxPeers];
+    int32_t n_peer_out, peer_multicast;
 };
 
 // Geometry of the fused windowed kernel, fixed on the host so that tests can query it.

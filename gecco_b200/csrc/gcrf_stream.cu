@@ -551,9 +551,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 // the approximate reciprocal can land one ulp above q/(1+q): a probability must not exceed 1
                 float p = fminf(q * rcp_fast(1.0f + q), 1.0f);
                 if (stat == 2) p = __int_as_float(0x7fc00000);
-                const int gg = Gs + g;
-                if (args.out_f32) static_cast<float *>(args.out)[gg] = p;
-                else static_cast<double *>(args.out)[gg] = (double)p;
+                store_result(args, Gs + g, p);
             }
         }
         GCRF_MARK(7);

@@ -15,7 +15,7 @@ import numpy
 
 from .synth import CsrBatch
 
-__all__ = ["partition_contigs", "scatter_batch", "gather_marginals", "predict_sharded", "DeviceShard"]
+__all__ = ["partition_contigs", "scatter_batch", "gather_marginals", "predict_sharded", "DeviceShard", "FusedGather"]
 
 
 def partition_contigs(contig_ptr: numpy.ndarray, gene_ptr: Optional[numpy.ndarray], n_shards: int, window: int,
@@ -180,3 +180,56 @@ def predict_sharded(engine, shard, *, window: int, step: int = 1, pad: bool = Tr
     dev = device if device is not None else torch.device("cpu")
     out = gather_marginals(torch.from_numpy(numpy.ascontiguousarray(local)).to(dev), genes_per_rank)
     return out.cpu().numpy() if to_host else out
+
+
+class FusedGather:
+    """The gather of a contig-sharded batch fused into the marginal kernel (``gcrf_marginals_windowed_peers``).
+
+    Every rank owns a symmetric buffer of ALL genes' marginals (``torch.distributed._symmetric_memory``: one allocation per
+    GPU, mapped into every process of the node over NVLink / NVSwitch).  ``predict`` runs the windowed kernel on this
+    rank's shard and the kernel itself stores every result into all ranks' buffers at the shard's gene offset — peer
+    stores, or ONE ``multimem.st`` to the NVLS multicast address when the fabric offers it — so the transfer overlaps the
+    computation tile by tile and no collective follows, only a device-side barrier before anybody reads.
+
+    Needs the streaming kernel (window 5 / 10 / 20, FP32 arithmetic); callers fall back to ``predict_sharded`` otherwise.
+    """
+
+    def __init__(self, genes_per_rank: Sequence[int], device, *, f32: bool = False, multicast: Optional[bool] = None, group=None):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dist = _dist()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.sizes = [int(g) for g in genes_per_rank]
+        if len(self.sizes) != self.world:
+            raise ValueError("one gene count per rank")
+        self.offsets = numpy.concatenate([[0], numpy.cumsum(self.sizes)]).astype(numpy.int64)
+        self.total = int(self.offsets[-1])
+        self.dtype = torch.float32 if f32 else torch.float64
+        self.f32 = f32
+        self.buffer = symm_mem.empty(max(self.total, 1), dtype=self.dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group.group_name)
+        can_mc = bool(getattr(self.handle, "has_multicast_support", False)) and int(getattr(self.handle, "multicast_ptr", 0) or 0) != 0
+        self.multicast = can_mc if multicast is None else (bool(multicast) and can_mc)
+        if self.world > 8 and not self.multicast:
+            raise ValueError("at most 8 peer output arrays per call without NVLS multicast")
+
+    def predict(self, engine, shard: "DeviceShard", *, window: int, step: int = 1, pad: bool = True, barrier_before: bool = True):
+        """Enqueue kernel + barrier on the current stream; returns the symmetric buffer (all genes, this rank's copy)."""
+        import torch
+
+        stream = torch.cuda.current_stream(self.buffer.device)
+        if stream.cuda_stream == 0:
+            raise RuntimeError("run FusedGather.predict on a non-default CUDA stream (torch.cuda.stream(...))")
+        engine.set_stream(stream.cuda_stream)
+        if barrier_before:
+            self.handle.barrier(channel=0)  # nobody still reads the previous result while peers overwrite it
+        if shard.G:
+            peers = [int(self.handle.multicast_ptr)] if self.multicast else [int(p) for p in self.handle.buffer_ptrs]
+            engine.marginals_windowed_peers(shard.contig_ptr.data_ptr(), shard.gene_ptr.data_ptr(), shard.attr_idx.data_ptr(),
+                                            shard.C, shard.G, shard.nnz, None, peers, int(self.offsets[self.rank]),
+                                            window=window, step=step, pad=pad, f32=self.f32, ptr64=shard.ptr64,
+                                            multicast=self.multicast)
+        self.handle.barrier(channel=1)  # every rank's kernel has finished storing into this rank's buffer
+        return self.buffer[: self.total]

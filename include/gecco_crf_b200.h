@@ -76,6 +76,7 @@ typedef enum gcrf_status {
                                       output on the reference's golden fixture, within a few ulps of it elsewhere (the
                                       residue is the host libm's rounding of exp).  Any window size.  Several times
                                       slower than the default FP32 odds-ratio kernels, whose results stay within 1e-5 */
+#define GCRF_FLAG_MULTICAST   0x100u /* gcrf_marginals_windowed_peers: peer_out[0] is an NVLS multicast address */
 #define GCRF_FLAG_PROB_F32    0x8u /* gcrf_segments: prob is float[G] instead of double[G] */
 #define GCRF_FLAG_RESET_PER_CONTIG 0x10u /* gcrf_segments: the in-cluster state starts at "out" in every
                                       contig, i.e. one ClusterRefiner.iter_clusters call per contig as
@@ -146,6 +147,25 @@ int gcrf_model_synchronize(gcrf_model *model);
 int gcrf_marginals_windowed(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
                             const void *attr_idx, int64_t C, int64_t G, int64_t nnz,
                             int32_t window, int32_t step, int32_t pad, void *out, uint32_t flags);
+
+/*
+ * The multi-GPU form of gcrf_marginals_windowed for ONE batch sharded by contig over the GPUs of a node (contigs are
+ * independent: every GPU runs the kernels on its own contigs, nothing is exchanged inside the math).  What the GPUs do
+ * exchange is the result — every gene's marginal has to end up in one array — and this entry point fuses that gather into
+ * the kernel: besides `out` (this GPU's own array, may be NULL) every result is stored straight into peer_out[k]
+ * [out_offset + g], k < n_peer_out <= 8: the output arrays of the other GPUs (and, if wanted, of this one) mapped into
+ * this process over NVLink / NVSwitch (cudaIpc*, cuMem* fabric handles, or torch symmetric memory —
+ * gecco_b200/sharding.py).  With GCRF_FLAG_MULTICAST peer_out[0] is an NVLS multicast address: one store, replicated to
+ * every GPU by the switch.  The transfer overlaps the computation tile by tile; no collective follows, only a barrier
+ * among the GPUs (theirs to provide) before anybody reads.  out_offset = index of this shard's first gene in the
+ * gathered array.  Device pointers only (GCRF_FLAG_DEVICE_PTRS is required); the streaming kernel only (window 5, 10
+ * or 20, FP32 arithmetic), GCRF_EUNSUPPORTED otherwise — fall back to gcrf_marginals_windowed + a collective.
+ * Replaces: nothing in the reference, which is single-process (gecco/crf/__init__.py:244-258).
+ */
+int gcrf_marginals_windowed_peers(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
+                                  const void *attr_idx, int64_t C, int64_t G, int64_t nnz, int32_t window,
+                                  int32_t step, int32_t pad, void *out, void *const *peer_out, int32_t n_peer_out,
+                                  int64_t out_offset, uint32_t flags);
 
 /*
  * Primitive equal to predict_marginals_single() on whole rows: every contig is ONE chain of

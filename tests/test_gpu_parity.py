@@ -553,3 +553,42 @@ def test_table_path_with_feature_extraction_on_device(weights, mibig, feature_ty
         device = tables.predict(crf)
         assert tables._packed.accessions
     assert numpy.array_equal(host, device, equal_nan=True)
+
+
+def test_peer_output_arrays_single_gpu(engine, weights, device_path):
+    """gcrf_marginals_windowed_peers with the "peer" arrays on this GPU: the local array (optional) and every peer array
+    receive the result at out_offset; paths other than the streaming kernel refuse (callers then gather with a collective)."""
+    import torch
+
+    from gecco_b200 import synth
+    from gecco_b200._lib import GcrfError
+
+    batch = synth.config4(len(weights.attrs), contigs=3000, mean_domains=6.0)
+    want = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    dev = torch.device("cuda", 0)
+    cp, gp = torch.from_numpy(batch.contig_ptr).to(dev), torch.from_numpy(batch.gene_ptr).to(dev)
+    ai = torch.full((batch.nnz + 16,), -1, dtype=torch.int32, device=dev)
+    ai[: batch.nnz] = torch.from_numpy(batch.attr_idx).to(dev)
+    off = 1234
+    for f32 in (False, True):
+        dt = torch.float32 if f32 else torch.float64
+        local = torch.full((batch.G,), -1.0, dtype=dt, device=dev)
+        peers = [torch.full((batch.G + off + 7,), -1.0, dtype=dt, device=dev) for _ in range(3)]
+        call = lambda out, plist: engine.marginals_windowed_peers(cp.data_ptr(), gp.data_ptr(), ai.data_ptr(), batch.C, batch.G, batch.nnz,
+                                                                   out, [p.data_ptr() for p in plist], off, window=20, f32=f32)
+        if device_path == "generic":
+            with pytest.raises(GcrfError, match="streaming kernel"):
+                call(local.data_ptr(), peers)
+            continue
+        call(local.data_ptr(), peers)
+        engine.synchronize()
+        ref = want.astype(numpy.float32) if f32 else want
+        assert numpy.array_equal(local.cpu().numpy(), ref)
+        for p in peers:
+            got = p.cpu().numpy()
+            assert numpy.array_equal(got[off:off + batch.G], ref) and (got[:off] == -1).all() and (got[off + batch.G:] == -1).all()
+        # no local array at all
+        peers[0].fill_(-1.0)
+        call(None, peers[:1])
+        engine.synchronize()
+        assert numpy.array_equal(peers[0].cpu().numpy()[off:off + batch.G], ref)
