@@ -891,7 +891,7 @@ int gcrf_segments(gcrf_model *m, const int32_t *contig_ptr, const void *prob, co
         a.seg_end = reinterpret_cast<int32_t *>(q); q += cap * sizeof(int32_t);
         a.seg_ordinal = reinterpret_cast<int32_t *>(q);
     }
-    GCRF_CUDA(m->b_scratch.reserve(gcrf::segments_scratch_bytes(G, m->num_sms)));
+    GCRF_CUDA(m->b_scratch.reserve(gcrf::segments_scratch_bytes(G, C, m->num_sms)));
     NvtxRange range("gcrf:launch segments");
     GCRF_CUDA(timing_begin(m));
     cudaError_t err = gcrf::launch_segments(a, m->b_scratch.ptr, m->num_sms, m->stream, &m->launches);

@@ -146,14 +146,8 @@ struct SegmentsArgs {
     double *seg_avg_p, *seg_max_p;
     int64_t capacity;
     int64_t *count;             // device: number of valid clusters found (may exceed capacity)
-    // scratch, carved by launch_segments
-    uint8_t *flag, *cmark;
-    int32_t *ann_prefix, *ann_pos;                       // [G+1], [G]
-    int32_t *run_end, *run_start, *run_contig;           // one record per run (at most G)
-    int32_t *contig_first_run;                           // [C] runs that ended before the contig's first gene
-    int32_t *n_runs;                                     // device scalar
 };
-size_t segments_scratch_bytes(int64_t G, int num_sms);
+size_t segments_scratch_bytes(int64_t G, int64_t C, int num_sms);
 cudaError_t launch_segments(SegmentsArgs args, void *scratch, int num_sms, cudaStream_t stream, int64_t *launches);
 
 }  // namespace gcrf
