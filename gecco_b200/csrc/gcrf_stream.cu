@@ -584,8 +584,9 @@ cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
 
 
 // Window sizes with a compiled streaming kernel: GECCO's shipped model (20), the default of `gecco train` (5,
-// gecco/cli/commands/_parser.py:364-372) and one in between; every other size runs the generic kernel.
-#define GCRF_STREAM_WINDOWS(X) X(5) X(10) X(20)
+// gecco/cli/commands/_parser.py:364-372) and a spread of sizes around them (the reference takes any window_size >= 1,
+// gecco/crf/__init__.py:134-137); every other size runs the generic kernel (or, past 128, the f64 path).
+#define GCRF_STREAM_WINDOWS(X) X(5) X(10) X(15) X(20) X(25) X(30) X(40) X(50) X(64)
 
 template <int W>
 cudaError_t configure_window(const WindowedArgs &args, int *per_sm, size_t *bytes, int *tile_out) {
@@ -604,13 +605,14 @@ cudaError_t launch_window(const cudaLaunchConfig_t &cfg, const WindowedArgs &arg
 }  // namespace
 
 bool stream_supported(const WindowedArgs &args) {
-    bool known = false;
-#define X(W) known = known || args.window == W;
-    GCRF_STREAM_WINDOWS(X)
+    size_t bytes = 0;
+    switch (args.window) {
+#define X(W) case W: bytes = StreamTiling<W, kNT>(args.model.A).bytes(); break;
+        GCRF_STREAM_WINDOWS(X)
 #undef X
-    if (!known) return false;
-    const StreamTiling<20, kNT> tl(args.model.A);  // the largest of the compiled windows
-    if (tl.bytes() > (size_t)kStreamSmemCap) return false;
+        default: return false;
+    }
+    if (bytes > (size_t)kStreamSmemCap) return false;
     // tile arithmetic is 32-bit: G + one tile of slack must fit
     return args.csr.G < 0x7fff0000;
 }

@@ -74,7 +74,8 @@ def test_mibig_real_features(engine, mibig, weights):
 
 @pytest.mark.parametrize("window,step,pad", [(20, 1, True), (20, 1, False), (20, 3, True), (5, 1, True), (5, 2, False),
                                              (10, 1, True), (10, 3, False), (7, 7, True), (1, 1, True), (33, 4, True),
-                                             (64, 1, True), (128, 5, True)])
+                                             (64, 1, True), (128, 5, True), (15, 1, True), (25, 2, False), (30, 1, True),
+                                             (40, 1, True), (40, 7, False), (50, 3, True), (64, 9, False)])
 def test_ragged_edge_cases(engine, weights, window, step, pad):
     from gecco_b200 import synth
 
@@ -84,10 +85,10 @@ def test_ragged_edge_cases(engine, weights, window, step, pad):
     assert_close(got, want, what=f"W={window} step={step} pad={pad}")
 
 
-@pytest.mark.parametrize("window", [5, 10])
+@pytest.mark.parametrize("window", [5, 10, 15, 25, 30, 40, 50, 64])
 def test_other_streaming_windows_on_dense_and_short_contigs(engine, weights, window):
-    """The streaming kernel is also compiled for W = 5 (`gecco train`'s default) and W = 10: odd and even meeting
-    points of the two DP chains, on the dense shape and on the metagenome shape (padding and skipping)."""
+    """The streaming kernel is also compiled for W = 5 (`gecco train`'s default) and a spread of other sizes: odd and
+    even meeting points of the two DP chains, on the dense shape and on the metagenome shape (padding and skipping)."""
     from gecco_b200 import synth
 
     batch = synth.config2(len(weights.attrs), contigs=200)
@@ -107,7 +108,7 @@ def test_random_shapes_fuzz(engine, weights):
 
     rng = numpy.random.default_rng(2024)
     for case in range(36):
-        window = int(rng.choice([5, 10, 20, 20, 20, rng.integers(1, 41)]))
+        window = int(rng.choice([5, 10, 20, 20, 20, 15, 25, 30, 40, 50, 64, rng.integers(1, 41)]))
         step = int(rng.integers(1, window + 1)) if rng.random() < 0.4 else 1
         pad = bool(rng.random() < 0.7)
         kind = case % 4
