@@ -20,6 +20,9 @@
 #define GCRF_FLAG_HAS_PEERS 0x20000000u
 // internal: no local output array (results go to the peer arrays only)
 #define GCRF_FLAG_NO_LOCAL_OUT 0x10000000u
+// internal: the arrays are a contig-aligned slice of a larger batch whose first gene is gcrf_model::slice_gene_base
+// (contig_ptr VALUES keep counting from the start of the whole batch, see CsrDev::gene_base)
+#define GCRF_FLAG_SLICE 0x08000000u
 
 namespace {
 
@@ -109,6 +112,7 @@ struct gcrf_model {
     DeviceBuffer b_unary, b_pool, b_work;  // GCRF_FLAG_F64: exp of the state scores, max-pool (float output), work area
     void *peer_out[gcrf::WindowedArgs::kMaxPeers] = {};  // gcrf_marginals_windowed_peers: valid during that call only
     int32_t n_peer_out = 0, peer_multicast = 0;
+    int64_t slice_gene_base = 0;  // GCRF_FLAG_SLICE
     DeviceBuffer b_wire, b_wire_sums;      // gcrf_marginals_windowed_wire: the block as it came over PCIe, scan scratch
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
     DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
@@ -570,7 +574,8 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
     if (!(flags & GCRF_FLAG_KEEP_TIMING)) m->ev_open = false;
     const bool has_peers = (flags & GCRF_FLAG_HAS_PEERS) != 0, no_local_out = (flags & GCRF_FLAG_NO_LOCAL_OUT) != 0;
-    flags &= ~(uint32_t)(GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_HAS_PEERS | GCRF_FLAG_NO_LOCAL_OUT);
+    const int64_t gene_base = (flags & GCRF_FLAG_SLICE) ? m->slice_gene_base : 0;
+    flags &= ~(uint32_t)(GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_HAS_PEERS | GCRF_FLAG_NO_LOCAL_OUT | GCRF_FLAG_SLICE);
     // gecco/_meta.py:127-130
     if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
     if (step <= 0 || step > window) return fail(GCRF_EINVAL, "Window step must be strictly positive and under `window_size`");
@@ -601,7 +606,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
         // the reference's own arithmetic (gcrf_exact.cu)
         gcrf::ExactArgs ex{};
         ex.csr = b.csr;
-        ex.csr.gene_base = 0;
+        ex.csr.gene_base = gene_base;
         ex.A = m->A;
         ex.state_w = m->d_state_w;
         for (int k = 0; k < 4; ++k) ex.M[k] = m->exp_trans[k];
@@ -630,7 +635,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     gcrf::WindowedArgs args{};
     args.model = m->dev;
     args.csr = b.csr;
-    args.csr.gene_base = 0;
+    args.csr.gene_base = gene_base;
     args.out = no_local_out ? nullptr : b.d_out;
     args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
     args.window = window;
@@ -701,30 +706,63 @@ int gcrf_marginals_windowed_wire(gcrf_model *m, const gcrf_wire *w, int32_t wind
     if (!out) return fail(GCRF_EINVAL, "out is NULL");
     m->ev_open = false;
     DeviceGuard guard(m->device);
-    const size_t out_bytes = (size_t)G * ((flags & GCRF_FLAG_OUT_F32) ? 4 : 8);
-    {
-        NvtxRange range("gcrf:stage wire");
-        GCRF_CUDA(m->b_wire.reserve(gcrf::wire_total(w)));
-        GCRF_CUDA(m->b_wire_sums.reserve((size_t)gcrf::wire_chunks(G) * 2 * sizeof(int64_t)));
-        GCRF_CUDA(m->b_gene.reserve((size_t)(G + 1) * 4));
-        GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
-        GCRF_CUDA(m->b_out.reserve(out_bytes));
-        // ONE host-to-device copy: contig_ptr, both length arrays and the id stream share a page-locked block
-        GCRF_CUDA(cudaMemcpyAsync(m->b_wire.ptr, gcrf::wire_block(w), gcrf::wire_total(w), cudaMemcpyHostToDevice, m->stream));
-        GCRF_CUDA(timing_begin(m));
-        const char *d = static_cast<const char *>(m->b_wire.ptr);
-        cudaError_t derr = gcrf::launch_wire_decode(d + gcrf::wire_off_len_ids(w), d + gcrf::wire_off_len_bytes(w), gcrf::wire_len_width(w),
-                                                    reinterpret_cast<const uint8_t *>(d + gcrf::wire_off_stream(w)), G,
-                                                    static_cast<int64_t *>(m->b_wire_sums.ptr), static_cast<int32_t *>(m->b_gene.ptr),
-                                                    static_cast<int32_t *>(m->b_attr.ptr), m->stream, &m->launches);
-        if (derr != cudaSuccess) return fail_cuda(derr, "launch_wire_decode");
+    const size_t osz = (flags & GCRF_FLAG_OUT_F32) ? 4 : 8;
+    const int lw = gcrf::wire_len_width(w);
+    const char *h = gcrf::wire_block(w);
+    GCRF_CUDA(m->b_wire.reserve(gcrf::wire_total(w)));
+    GCRF_CUDA(m->b_wire_sums.reserve((size_t)gcrf::wire_chunks(G) * 2 * sizeof(int64_t) + 64));
+    GCRF_CUDA(m->b_gene.reserve((size_t)(G + 1) * 4));
+    GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
+    GCRF_CUDA(m->b_out.reserve((size_t)G * osz));
+    char *d = static_cast<char *>(m->b_wire.ptr);
+    const size_t o_ids = gcrf::wire_off_len_ids(w), o_bytes = gcrf::wire_off_len_bytes(w), o_stream = gcrf::wire_off_stream(w);
+    // The block was cut into contig-aligned slices when it was encoded: while slice k is decoded, run through the
+    // kernels and copied back (copy_stream), slice k+1 is already on its way in — PCIe is full duplex and the two
+    // directions have their own copy engines.  Every array lands where the whole batch would have put it.
+    const int slices = m->timing ? 1 : gcrf::wire_slices(w);  // one bracketed region when the kernels are being timed
+    GCRF_CUDA(cudaMemcpyAsync(d, h, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+    int used = 0;
+    for (int k = 0; k < slices; ++k) {
+        int64_t c0, c1, g0, g1, p0, p1, b0, b1;
+        if (slices == 1) {
+            c0 = 0; c1 = C; g0 = 0; g1 = G; p0 = 0; p1 = nnz; b0 = 0; b1 = gcrf::wire_stream_bytes(w);
+        } else {
+            gcrf::wire_slice(w, k, &c0, &g0, &p0, &b0);
+            gcrf::wire_slice(w, k + 1, &c1, &g1, &p1, &b1);
+        }
+        if (g1 <= g0) continue;
+        {
+            NvtxRange range("gcrf:stage wire");
+            GCRF_CUDA(cudaMemcpyAsync(d + o_ids + (size_t)g0 * lw, h + o_ids + (size_t)g0 * lw, (size_t)(g1 - g0) * lw, cudaMemcpyHostToDevice, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(d + o_bytes + (size_t)g0 * lw, h + o_bytes + (size_t)g0 * lw, (size_t)(g1 - g0) * lw, cudaMemcpyHostToDevice, m->stream));
+            if (b1 > b0)
+                GCRF_CUDA(cudaMemcpyAsync(d + o_stream + (size_t)b0, h + o_stream + (size_t)b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, m->stream));
+            GCRF_CUDA(timing_begin(m));
+            cudaError_t derr = gcrf::launch_wire_decode(d + o_ids + (size_t)g0 * lw, d + o_bytes + (size_t)g0 * lw, lw,
+                                                        reinterpret_cast<const uint8_t *>(d + o_stream) + b0, g1 - g0, p0,
+                                                        static_cast<int64_t *>(m->b_wire_sums.ptr), static_cast<int32_t *>(m->b_gene.ptr) + g0,
+                                                        static_cast<int32_t *>(m->b_attr.ptr), m->stream, &m->launches);
+            if (derr != cudaSuccess) return fail_cuda(derr, "launch_wire_decode");
+        }
+        // the decoded slice is a device-pointer batch of the regular entry point; its result lands in the library's buffer
+        m->slice_gene_base = g0;
+        const int rc = gcrf_marginals_windowed(m, reinterpret_cast<const int32_t *>(d) + c0, static_cast<int32_t *>(m->b_gene.ptr) + g0,
+                                               m->b_attr.ptr, c1 - c0, g1 - g0, nnz, window, step, pad,
+                                               static_cast<char *>(m->b_out.ptr) + (size_t)g0 * osz,
+                                               flags | GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_SLICE);
+        if (rc != GCRF_OK) return rc;
+        NvtxRange range("gcrf:finish");
+        cudaStream_t back = m->stream;
+        if (slices > 1) {
+            GCRF_CUDA(cudaEventRecord(m->ev_slice[used], m->stream));
+            GCRF_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_slice[used], 0));
+            back = m->copy_stream;
+            ++used;
+        }
+        GCRF_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + (size_t)g0 * osz, static_cast<char *>(m->b_out.ptr) + (size_t)g0 * osz,
+                                  (size_t)(g1 - g0) * osz, cudaMemcpyDeviceToHost, back));
     }
-    // the decoded batch is a device-pointer batch of the regular entry point; its result lands in the library's buffer
-    const int rc = gcrf_marginals_windowed(m, static_cast<const int32_t *>(m->b_wire.ptr), m->b_gene.ptr, m->b_attr.ptr, C, G, nnz, window,
-                                           step, pad, m->b_out.ptr, flags | GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_KEEP_TIMING);
-    if (rc != GCRF_OK) return rc;
-    NvtxRange range("gcrf:finish");
-    GCRF_CUDA(cudaMemcpyAsync(out, m->b_out.ptr, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+    if (slices > 1) GCRF_CUDA(cudaStreamSynchronize(m->copy_stream));
     GCRF_CUDA(cudaStreamSynchronize(m->stream));
     return GCRF_OK;
 }

@@ -122,8 +122,14 @@ cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int nu
 // Compact wire format (gcrf_wire.cu): rebuild gene_ptr[G+1] / attr_idx[nnz] from the length arrays and the delta-coded
 // id stream; `sums` is scratch of 2 * wire_chunks(G) int64.
 int64_t wire_chunks(int64_t G);
+// (slice form: the arrays point at the slice's first gene / first stream byte, id_base = attribute ids in front of it;
+// gene_ptr receives absolute offsets into attr_idx)
 cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
-                               int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t stream_, int64_t *launches);
+                               int64_t id_base, int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t stream_,
+                               int64_t *launches);
+int wire_slices(const gcrf_wire *w);
+void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte);  // k in [0, slices]
+int64_t wire_stream_bytes(const gcrf_wire *w);
 const char *wire_block(const gcrf_wire *w);
 size_t wire_total(const gcrf_wire *w);
 size_t wire_off_len_ids(const gcrf_wire *w);

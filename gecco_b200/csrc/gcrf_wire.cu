@@ -32,6 +32,10 @@ struct gcrf_wire {
     int32_t len_width = 1;  // bytes per entry of len_ids / len_bytes: 1 or 2
     char *block = nullptr;  // page-locked: [contig_ptr | len_ids | len_bytes | stream], every part 16-byte aligned
     size_t off_len_ids = 0, off_len_bytes = 0, off_stream = 0, total = 0;
+    // contig-aligned slices of about equal bytes (the call overlaps slice k's way back with slice k+1's way in)
+    static constexpr int kMaxSlices = 8;
+    int n_slices = 1;
+    int64_t s_contig[kMaxSlices + 1] = {}, s_gene[kMaxSlices + 1] = {}, s_id[kMaxSlices + 1] = {}, s_byte[kMaxSlices + 1] = {};
 };
 
 namespace gcrf {
@@ -133,7 +137,8 @@ wire_scan_sums_kernel(int64_t *__restrict__ sums, int64_t n) {
 template <typename LenT>
 __global__ void __launch_bounds__(kWireThreads)
 wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ len_bytes, const uint8_t *__restrict__ stream,
-                   int64_t G, const int64_t *__restrict__ sums, int32_t *__restrict__ gene_ptr, int32_t *__restrict__ attr_idx) {
+                   int64_t G, int64_t id_base, const int64_t *__restrict__ sums, int32_t *__restrict__ gene_ptr,
+                   int32_t *__restrict__ attr_idx) {
     __shared__ int sIds[kWireChunk], sBytes[kWireChunk];  // lengths, then exclusive offsets within the block
     __shared__ int sWarpA[kWireThreads / 32], sWarpB[kWireThreads / 32];
     const int64_t base = (int64_t)blockIdx.x * kWireChunk;
@@ -179,7 +184,7 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
         sBytes[tid * kWirePerThread + k] = wb + ib - tb + b[k];
     }
     __syncthreads();
-    const int64_t id0 = sums[2 * (int64_t)blockIdx.x], byte0 = sums[2 * (int64_t)blockIdx.x + 1];
+    const int64_t id0 = id_base + sums[2 * (int64_t)blockIdx.x], byte0 = sums[2 * (int64_t)blockIdx.x + 1];
     for (int k = 0; k < kWirePerThread; ++k) {
         const int j = tid + k * kWireThreads;  // neighbouring threads take neighbouring genes: their bytes share lines
         const int64_t g = base + j;
@@ -209,7 +214,8 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
 int64_t wire_chunks(int64_t G) { return (G + kWireChunk - 1) / kWireChunk; }
 
 cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
-                               int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t cuda_stream, int64_t *launches) {
+                               int64_t id_base, int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t cuda_stream,
+                               int64_t *launches) {
     if (G <= 0) return cudaSuccess;
     const int64_t nb = wire_chunks(G);
     if (len_width == 1) {
@@ -222,12 +228,12 @@ cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32
     wire_scan_sums_kernel<<<1, 1024, 0, cuda_stream>>>(sums, nb);
     if (len_width == 1) {
         wire_decode_kernel<uint8_t><<<(unsigned)nb, kWireThreads, 0, cuda_stream>>>(static_cast<const uint8_t *>(len_ids),
-                                                                                 static_cast<const uint8_t *>(len_bytes), stream, G, sums,
-                                                                                 gene_ptr, attr_idx);
+                                                                                 static_cast<const uint8_t *>(len_bytes), stream, G, id_base,
+                                                                                 sums, gene_ptr, attr_idx);
     } else {
         wire_decode_kernel<uint16_t><<<(unsigned)nb, kWireThreads, 0, cuda_stream>>>(static_cast<const uint16_t *>(len_ids),
-                                                                                  static_cast<const uint16_t *>(len_bytes), stream, G, sums,
-                                                                                  gene_ptr, attr_idx);
+                                                                                  static_cast<const uint16_t *>(len_bytes), stream, G, id_base,
+                                                                                  sums, gene_ptr, attr_idx);
     }
     if (launches) *launches += 3;
     return cudaGetLastError();
@@ -360,6 +366,47 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
         if (!c.stream.empty()) memcpy(w->block + w->off_stream + spos, c.stream.data(), c.stream.size());
         spos += c.stream.size();
     }
+    // slice table: cut at contig starts into parts of about equal bytes moved (stream + lengths in, 8 per gene out).
+    // ONE slice unless GCRF_WIRE_SLICES asks for more: on the PCIe Gen5 hosts measured the copy back of slice k did not
+    // overlap the copy in of slice k+1 to any effect (config 2: 965 / 967 / 950 / 856 M genes/s with 1 / 2 / 4 / 8
+    // slices, profiles/r2_e2e_wire_slices.txt) and every slice costs ~25 us of extra launches and copies
+    {
+        std::vector<int64_t> gene_id((size_t)G + 1), gene_byte((size_t)G + 1);
+        int64_t ids = 0, bytes = 0, gg = 0;
+        for (const auto &c : chunks)
+            for (size_t k = 0; k < c.n_ids.size(); ++k, ++gg) {
+                gene_id[gg] = ids;
+                gene_byte[gg] = bytes;
+                ids += c.n_ids[k];
+                bytes += c.n_bytes[k];
+            }
+        gene_id[G] = ids;
+        gene_byte[G] = bytes;
+        auto cost_at = [&](int64_t c) -> double { const int64_t g = contig_ptr[c]; return (double)gene_byte[g] + (2.0 * lw + 8.0) * (double)g; };
+        const double total_cost = G > 0 ? cost_at(C) : 0.0;
+        int n = 1;
+        if (const char *env = getenv("GCRF_WIRE_SLICES")) n = atoi(env);
+        if (n > gcrf_wire::kMaxSlices) n = gcrf_wire::kMaxSlices;
+        if (n > C) n = (int)C;
+        if (n < 1) n = 1;
+        w->n_slices = n;
+        for (int k = 0; k <= n; ++k) {
+            int64_t c = k == n ? C : 0;
+            if (k > 0 && k < n) {
+                int64_t lo = w->s_contig[k - 1], hi = C;
+                const double want = total_cost * k / n;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) / 2;
+                    if (cost_at(mid) < want) lo = mid + 1; else hi = mid;
+                }
+                c = lo;
+            }
+            w->s_contig[k] = c;
+            w->s_gene[k] = G > 0 ? contig_ptr[c] : 0;
+            w->s_id[k] = gene_id[w->s_gene[k]];
+            w->s_byte[k] = gene_byte[w->s_gene[k]];
+        }
+    }
     *out = w;
     return GCRF_OK;
 }
@@ -418,4 +465,12 @@ size_t wire_off_len_ids(const gcrf_wire *w) { return w->off_len_ids; }
 size_t wire_off_len_bytes(const gcrf_wire *w) { return w->off_len_bytes; }
 size_t wire_off_stream(const gcrf_wire *w) { return w->off_stream; }
 int32_t wire_len_width(const gcrf_wire *w) { return w->len_width < 0 ? -w->len_width : w->len_width; }
+int wire_slices(const gcrf_wire *w) { return w->n_slices; }
+void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte) {
+    *contig = w->s_contig[k];
+    *gene = w->s_gene[k];
+    *id = w->s_id[k];
+    *byte = w->s_byte[k];
+}
+int64_t wire_stream_bytes(const gcrf_wire *w) { return w->stream_bytes; }
 }  // namespace gcrf

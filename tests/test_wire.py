@@ -52,8 +52,9 @@ def test_encoder_rejects_malformed_row_pointers(weights):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("slices", ["1", "3", "8"])
 @pytest.mark.parametrize("make", ["ragged", "dense", "sparse", "long_rows"])
-def test_wire_call_equals_the_plain_call(engine, weights, make):
+def test_wire_call_equals_the_plain_call(engine, weights, make, slices, monkeypatch):
     """Bit for bit in FP32 arithmetic (exact integer row sums: the order inside a row does not matter); the f64 path
     sums in the sorted order, i.e. within a few ulps of the first-occurrence order."""
     A = len(weights.attrs)
@@ -66,6 +67,8 @@ def test_wire_call_equals_the_plain_call(engine, weights, make):
     for g in range(0, batch.G, 3):
         a, b = int(batch.gene_ptr[g]), int(batch.gene_ptr[g + 1])
         shuffled[a:b] = shuffled[a:b][::-1]
+    # the block is cut into contig-aligned slices when it is encoded (the call overlaps their copies): any cut, same result
+    monkeypatch.setenv("GCRF_WIRE_SLICES", slices)
     wire = WireBatch(batch.contig_ptr, batch.gene_ptr, shuffled, A)
     for window, step, pad in ((20, 1, True), (5, 2, False)):
         plain = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, shuffled, window=window, step=step, pad=pad)
