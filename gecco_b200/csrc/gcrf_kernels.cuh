@@ -59,6 +59,7 @@ struct WindowedArgs {
 struct WindowedPlan {
     int threads;          // CTA size
     int tile_out;         // genes written per tile
+    int slots;            // streaming kernel: window slots per tile (256; 128 / 64 for dense batches)
     int chunk;            // attribute ids staged per gather round (elements)
     size_t smem_bytes;    // dynamic shared memory per CTA
     int64_t num_tiles;

@@ -50,9 +50,13 @@ constexpr int kNT = GCRF_STREAM_NT, kMinB = GCRF_STREAM_MINB;
 constexpr int kStreamSmemCap = 100 * 1024;  // largest dynamic shared memory a streaming CTA may ask for
 constexpr int kFewPerLane = 16;  // ids per lane of the one-warp walk used for tiles with <= 512 staged ids
 
-template <int W, int NT>
+// SLOTS: window slots per tile.  2 * NT (two windows per DP thread) is the production geometry; the same kernel with
+// NT or NT / 2 slots (the upper DP threads idle) halves / quarters the genes per tile while the id buffer stays — for
+// batches so dense (> ~26 ids per gene on average) that a full tile's ids would not fit one staging round and every tile
+// would fall to the row-by-row path (2.7x slower: tools/density_probe.py).
+template <int W, int NT, int SLOTS = 2 * NT>
 struct StreamTiling {
-    static constexpr int kSlots = 2 * NT;          // window slots per tile
+    static constexpr int kSlots = SLOTS;           // window slots per tile
     static constexpr int kCap = NT * kWalk;        // ids staged per tile
     static constexpr int kPitch = NT + 16;         // pool pitch: odd and even genes land 16 banks apart
     static constexpr int lo = W;                   // local index of the first output gene
@@ -70,7 +74,7 @@ struct StreamTiling {
         off_u0 = o; o += round_up4s(ng + 2);
         off_q = o; o += round_up4s(ng + 2);
         off_sp = o; o += round_up4s(tile_out + 3);
-        off_cp = o; o += round_up4s(ng + 4);
+        off_cp = o; o += round_up4s((ng > NT ? ng : NT) + 4);  // one slice entry per thread at least
         off_stat = o; o += round_up4s((ng + 8) / 4);
         words = o;
     }
@@ -92,10 +96,10 @@ struct StreamTiling {
 #define GCRF_SKIP(bit) false
 #endif
 
-template <int W, int NT, int MINB, typename PtrT>
+template <int W, int NT, int MINB, typename PtrT, int SLOTS = 2 * NT>
 __global__ void __launch_bounds__(NT, MINB)
 stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const int num_tiles, const int tiles_per_cta) {
-    using T = StreamTiling<W, NT>;
+    using T = StreamTiling<W, NT, SLOTS>;
     constexpr int kCap = T::kCap, kPitch = T::kPitch;
     const CsrDev &csr = args.csr;
     const T tl(args.model.A);
@@ -431,7 +435,7 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
             const int b0 = 2 * tid;
             // contig of slot b0 (or of the first existing gene, for the slots in front of gene 0)
             float va = 0.f, vb = 0.f;
-            if (b0 + 1 >= jlo && b0 < jhi) {
+            if (b0 + 1 >= jlo && b0 < jhi && b0 < T::kSlots) {
                 const int js = max(b0, jlo);
                 int k = 0;
                 if (kt <= 4) {
@@ -570,11 +574,11 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
 #endif
 }
 
-template <int W, int NT, int MINB, typename PtrT>
+template <int W, int NT, int MINB, typename PtrT, int SLOTS>
 cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
-    const StreamTiling<W, NT> tl(A);
+    const StreamTiling<W, NT, SLOTS> tl(A);
     *bytes = tl.bytes();
-    auto kernel = stream_kernel<W, NT, MINB, PtrT>;
+    auto kernel = stream_kernel<W, NT, MINB, PtrT, SLOTS>;
     // The attribute is per kernel and device, not per launch: always raise it to the cap stream_supported() enforces, so
     // that host threads with models of different sizes cannot lower it under each other's cached plans.
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemCap);
@@ -588,18 +592,57 @@ cudaError_t configure_stream(int A, int *ctas_per_sm, size_t *bytes) {
 // gecco/crf/__init__.py:134-137); every other size runs the generic kernel (or, past 128, the f64 path).
 #define GCRF_STREAM_WINDOWS(X) X(5) X(10) X(15) X(20) X(25) X(30) X(40) X(50) X(64)
 
-template <int W>
-cudaError_t configure_window(const WindowedArgs &args, int *per_sm, size_t *bytes, int *tile_out) {
-    *tile_out = StreamTiling<W, kNT>::tile_out;
-    return args.csr.gene_ptr64 ? configure_stream<W, kNT, kMinB, int64_t>(args.model.A, per_sm, bytes)
-                               : configure_stream<W, kNT, kMinB, int32_t>(args.model.A, per_sm, bytes);
+// Windows that also get the half- and quarter-tile variants for dense batches: the shipped model's and `gecco train`'s.
+#define GCRF_STREAM_DENSE_WINDOWS(X) X(5) X(20)
+template <int W> constexpr bool has_dense_variants() {
+    bool yes = false;
+#define X(V) yes = yes || W == V;
+    GCRF_STREAM_DENSE_WINDOWS(X)
+#undef X
+    return yes;
 }
 
+template <int W, int SLOTS>
+cudaError_t configure_slots(const WindowedArgs &args, int *per_sm, size_t *bytes, int *tile_out) {
+    *tile_out = StreamTiling<W, kNT, SLOTS>::tile_out;
+    return args.csr.gene_ptr64 ? configure_stream<W, kNT, kMinB, int64_t, SLOTS>(args.model.A, per_sm, bytes)
+                               : configure_stream<W, kNT, kMinB, int32_t, SLOTS>(args.model.A, per_sm, bytes);
+}
 template <int W>
-cudaError_t launch_window(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int num_tiles, int tiles_per_cta) {
+cudaError_t configure_window(const WindowedArgs &args, int slots, int *per_sm, size_t *bytes, int *tile_out) {
+    if constexpr (has_dense_variants<W>()) {
+        if (slots == kNT) return configure_slots<W, kNT>(args, per_sm, bytes, tile_out);
+        if (slots == kNT / 2) return configure_slots<W, kNT / 2>(args, per_sm, bytes, tile_out);
+    }
+    return configure_slots<W, 2 * kNT>(args, per_sm, bytes, tile_out);
+}
+
+template <int W, int SLOTS>
+cudaError_t launch_slots(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int num_tiles, int tiles_per_cta) {
     return args.csr.gene_ptr64
-               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int64_t>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
-               : cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int32_t>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
+               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int64_t, SLOTS>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
+               : cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int32_t, SLOTS>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
+}
+template <int W>
+cudaError_t launch_window(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int slots, int num_tiles, int tiles_per_cta) {
+    if constexpr (has_dense_variants<W>()) {
+        if (slots == kNT) return launch_slots<W, kNT>(cfg, args, num_tiles, tiles_per_cta);
+        if (slots == kNT / 2) return launch_slots<W, kNT / 2>(cfg, args, num_tiles, tiles_per_cta);
+    }
+    return launch_slots<W, 2 * kNT>(cfg, args, num_tiles, tiles_per_cta);
+}
+
+// Window slots per tile for a batch of this density: the most that keep an average tile's ids (plus 4 % headroom for
+// the spread between tiles) inside one staging round.
+template <int W>
+int slots_for_density(double ids_per_gene) {
+    if constexpr (has_dense_variants<W>()) {
+        constexpr int kCap = StreamTiling<W, kNT>::kCap;
+        if (StreamTiling<W, kNT, 2 * kNT>::tile_out * ids_per_gene * 1.04 <= kCap) return 2 * kNT;
+        if (StreamTiling<W, kNT, kNT>::tile_out * ids_per_gene * 1.04 <= kCap) return kNT;
+        return kNT / 2;
+    }
+    return 2 * kNT;
 }
 
 }  // namespace
@@ -619,22 +662,33 @@ bool stream_supported(const WindowedArgs &args) {
 
 cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *plan) {
     // the kernel attribute / occupancy query depend on (device, A, pointer width, window) only: cache them per thread
-    struct Cached { int device = -1, A = -1, p64 = -1, window = -1, per_sm = 0, tile_out = 0; size_t bytes = 0; };
+    struct Cached { int device = -1, A = -1, p64 = -1, window = -1, slots = -1, per_sm = 0, tile_out = 0; size_t bytes = 0; };
     static thread_local Cached cache;
     int device = 0;
     cudaGetDevice(&device);
     const bool p64 = args.csr.gene_ptr64 != nullptr;
-    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64 || cache.window != args.window) {
+    const double density = args.csr.G > 0 ? (double)args.csr.nnz / (double)args.csr.G : 0.0;
+    int slots = 2 * kNT;
+    switch (args.window) {
+#define X(W) case W: slots = slots_for_density<W>(density); break;
+        GCRF_STREAM_WINDOWS(X)
+#undef X
+    }
+    if (const char *env = getenv("GCRF_STREAM_SLOTS")) {  // A/B: 256, 128 or 64 window slots per tile
+        const int want = atoi(env);
+        if (want == 2 * kNT || want == kNT || want == kNT / 2) slots = want;
+    }
+    if (cache.device != device || cache.A != args.model.A || cache.p64 != (int)p64 || cache.window != args.window || cache.slots != slots) {
         int q = 0, tile_out = 0;
         size_t b = 0;
         cudaError_t err = cudaErrorInvalidValue;
         switch (args.window) {
-#define X(W) case W: err = configure_window<W>(args, &q, &b, &tile_out); break;
+#define X(W) case W: err = configure_window<W>(args, slots, &q, &b, &tile_out); break;
             GCRF_STREAM_WINDOWS(X)
 #undef X
         }
         if (err != cudaSuccess) return err;
-        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.window = args.window;
+        cache.device = device; cache.A = args.model.A; cache.p64 = (int)p64; cache.window = args.window; cache.slots = slots;
         cache.per_sm = q; cache.bytes = b; cache.tile_out = tile_out;
     }
     int per_sm = cache.per_sm;
@@ -647,6 +701,7 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
 #endif
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     plan->threads = kNT;
+    plan->slots = slots;
     plan->tile_out = cache.tile_out;
     plan->chunk = kNT * kWalk;
     plan->smem_bytes = bytes;
@@ -676,7 +731,7 @@ cudaError_t launch_stream(const WindowedArgs &args, const WindowedPlan &plan, cu
     cfg.numAttrs = 1;
     cudaError_t err = cudaErrorInvalidValue;
     switch (args.window) {
-#define X(W) case W: err = launch_window<W>(cfg, args, nt_, tpc); break;
+#define X(W) case W: err = launch_window<W>(cfg, args, plan.slots, nt_, tpc); break;
         GCRF_STREAM_WINDOWS(X)
 #undef X
     }

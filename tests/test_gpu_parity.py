@@ -593,3 +593,34 @@ def test_peer_output_arrays_single_gpu(engine, weights, device_path):
         call(None, peers[:1])
         engine.synchronize()
         assert numpy.array_equal(peers[0].cpu().numpy()[off:off + batch.G], ref)
+
+
+@pytest.mark.parametrize("slots", ["128", "64"])
+def test_half_and_quarter_tiles(engine, weights, slots, monkeypatch, device_path):
+    """The streaming kernel's half- and quarter-tile variants (chosen by density; forced here): every control-flow shape
+    of the full-tile kernel again, plus batches dense enough to need them."""
+    from gecco_b200 import synth
+
+    if device_path == "generic":
+        pytest.skip("streaming kernel only")
+    monkeypatch.setenv("GCRF_STREAM_SLOTS", slots)
+    batch = synth.ragged_edge_cases(len(weights.attrs))
+    for window, step, pad in ((20, 1, True), (20, 3, False), (5, 1, True), (5, 2, False)):
+        got = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window, step=step, pad=pad)
+        assert_close(got, oracle(weights, batch, window, step, pad), what=f"slots={slots} W={window} step={step} pad={pad}")
+    for shape in (synth.config2(len(weights.attrs), contigs=150), synth.config4(len(weights.attrs), contigs=3000, mean_domains=6.0)):
+        assert_close(engine.marginals_windowed(shape.contig_ptr, shape.gene_ptr, shape.attr_idx), oracle(weights, shape), what=f"slots={slots}")
+    rng = numpy.random.default_rng(8)
+    tiny = synth.make_batch(rng, rng.integers(1, 4, size=2000), 3.0, len(weights.attrs), 0.05)
+    assert_close(engine.marginals_windowed(tiny.contig_ptr, tiny.gene_ptr, tiny.attr_idx), oracle(weights, tiny), what="tiny contigs")
+
+
+def test_dense_batches_pick_smaller_tiles(engine, weights, monkeypatch, device_path):
+    """40 and 90 ids per gene on average: a full tile's ids no longer fit one staging round; the plan switches to half /
+    quarter tiles by itself and the result is the oracle's."""
+    from gecco_b200 import synth
+
+    monkeypatch.delenv("GCRF_STREAM_SLOTS", raising=False)
+    for d in (40.0, 90.0):
+        batch = synth.config2(len(weights.attrs), contigs=60, mean_domains=d)
+        assert_close(engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx), oracle(weights, batch), what=f"d={d}")
