@@ -476,7 +476,7 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
     const bool want_generic = force && force[0] == '1';
     const bool fast = gcrf::stream_supported(args) && !want_generic;
     if (!fast && args.n_peer_out > 0)
-        return fail(GCRF_EUNSUPPORTED, "peer output arrays need the streaming kernel (window 5, 10 or 20, FP32 arithmetic)");
+        return fail(GCRF_EUNSUPPORTED, "peer output arrays need the streaming kernel's peer-store variant (window 5 or 20, FP32 arithmetic)");
     cudaError_t err = fast ? gcrf::plan_stream(args, m->num_sms, &plan) : gcrf::plan_windowed(args, m->num_sms, &plan);
     if (err == cudaErrorInvalidValue) {
         cudaGetLastError();
@@ -601,7 +601,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     if (rc != GCRF_OK || G == 0) return rc;
 
     if ((flags & GCRF_FLAG_F64) && has_peers)
-        return fail(GCRF_EUNSUPPORTED, "peer output arrays need the streaming kernel (window 5, 10 or 20, FP32 arithmetic)");
+        return fail(GCRF_EUNSUPPORTED, "peer output arrays need the streaming kernel's peer-store variant (window 5 or 20, FP32 arithmetic)");
     if (flags & GCRF_FLAG_F64) {
         // the reference's own arithmetic (gcrf_exact.cu)
         gcrf::ExactArgs ex{};

@@ -96,7 +96,9 @@ struct StreamTiling {
 #define GCRF_SKIP(bit) false
 #endif
 
-template <int W, int NT, int MINB, typename PtrT, int SLOTS = 2 * NT>
+// PEERS: results also go to the peer output arrays of a contig-sharded batch (gcrf_marginals_windowed_peers); a
+// separate instantiation, so that the single-GPU kernel carries none of it.
+template <int W, int NT, int MINB, typename PtrT, int SLOTS = 2 * NT, bool PEERS = false>
 __global__ void __launch_bounds__(NT, MINB)
 stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const int num_tiles, const int tiles_per_cta) {
     using T = StreamTiling<W, NT, SLOTS>;
@@ -555,7 +557,12 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
                 // the approximate reciprocal can land one ulp above q/(1+q): a probability must not exceed 1
                 float p = fminf(q * rcp_fast(1.0f + q), 1.0f);
                 if (stat == 2) p = __int_as_float(0x7fc00000);
-                store_result(args, Gs + g, p);
+                if constexpr (PEERS) {
+                    store_result(args, Gs + g, p);
+                } else {
+                    if (args.out_f32) static_cast<float *>(args.out)[Gs + g] = p;
+                    else static_cast<double *>(args.out)[Gs + g] = (double)p;
+                }
             }
         }
         GCRF_MARK(7);
@@ -623,9 +630,27 @@ cudaError_t launch_slots(const cudaLaunchConfig_t &cfg, const WindowedArgs &args
                ? cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int64_t, SLOTS>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
                : cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int32_t, SLOTS>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
 }
+// the peer-store instantiation (full tiles only; the windows that have dense variants have this one too)
+template <int W, typename PtrT>
+cudaError_t launch_peers(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, const PtrT *gene_ptr, int num_tiles, int tiles_per_cta) {
+    auto kernel = stream_kernel<W, kNT, kMinB, PtrT, 2 * kNT, true>;
+    static thread_local int configured_device = -1;
+    int device = 0;
+    cudaGetDevice(&device);
+    if (configured_device != device) {
+        const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemCap);
+        if (err != cudaSuccess) return err;
+        configured_device = device;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, args, gene_ptr, num_tiles, tiles_per_cta);
+}
+
 template <int W>
 cudaError_t launch_window(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int slots, int num_tiles, int tiles_per_cta) {
     if constexpr (has_dense_variants<W>()) {
+        if (args.n_peer_out > 0)
+            return args.csr.gene_ptr64 ? launch_peers<W>(cfg, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
+                                       : launch_peers<W>(cfg, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
         if (slots == kNT) return launch_slots<W, kNT>(cfg, args, num_tiles, tiles_per_cta);
         if (slots == kNT / 2) return launch_slots<W, kNT / 2>(cfg, args, num_tiles, tiles_per_cta);
     }
@@ -648,6 +673,13 @@ int slots_for_density(double ids_per_gene) {
 }  // namespace
 
 bool stream_supported(const WindowedArgs &args) {
+    if (args.n_peer_out > 0) {  // peer output arrays: the windows with a peer-store instantiation
+        bool ok = false;
+#define X(W) ok = ok || args.window == W;
+        GCRF_STREAM_DENSE_WINDOWS(X)
+#undef X
+        if (!ok) return false;
+    }
     size_t bytes = 0;
     switch (args.window) {
 #define X(W) case W: bytes = StreamTiling<W, kNT>(args.model.A).bytes(); break;
@@ -674,6 +706,7 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
         GCRF_STREAM_WINDOWS(X)
 #undef X
     }
+    if (args.n_peer_out > 0) slots = 2 * kNT;  // the peer-store kernel exists for full tiles only
     if (const char *env = getenv("GCRF_STREAM_SLOTS")) {  // A/B: 256, 128 or 64 window slots per tile
         const int want = atoi(env);
         if (want == 2 * kNT || want == kNT || want == kNT / 2) slots = want;

@@ -191,7 +191,7 @@ class FusedGather:
     stores, or ONE ``multimem.st`` to the NVLS multicast address when the fabric offers it — so the transfer overlaps the
     computation tile by tile and no collective follows, only a device-side barrier before anybody reads.
 
-    Needs the streaming kernel (window 5 / 10 / 20, FP32 arithmetic); callers fall back to ``predict_sharded`` otherwise.
+    Needs the streaming kernel's peer-store variant (window 5 or 20, FP32 arithmetic); callers fall back to ``predict_sharded`` otherwise.
     """
 
     def __init__(self, genes_per_rank: Sequence[int], device, *, f32: bool = False, multicast: Optional[bool] = None, group=None):

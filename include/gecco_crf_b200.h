@@ -158,8 +158,8 @@ int gcrf_marginals_windowed(gcrf_model *model, const int32_t *contig_ptr, const 
  * gecco_b200/sharding.py).  With GCRF_FLAG_MULTICAST peer_out[0] is an NVLS multicast address: one store, replicated to
  * every GPU by the switch.  The transfer overlaps the computation tile by tile; no collective follows, only a barrier
  * among the GPUs (theirs to provide) before anybody reads.  out_offset = index of this shard's first gene in the
- * gathered array.  Device pointers only (GCRF_FLAG_DEVICE_PTRS is required); the streaming kernel only (window 5, 10
- * or 20, FP32 arithmetic), GCRF_EUNSUPPORTED otherwise — fall back to gcrf_marginals_windowed + a collective.
+ * gathered array.  Device pointers only (GCRF_FLAG_DEVICE_PTRS is required); the streaming kernel only (window 5 or 20,
+ * FP32 arithmetic), GCRF_EUNSUPPORTED otherwise — fall back to gcrf_marginals_windowed + a collective.
  * Replaces: nothing in the reference, which is single-process (gecco/crf/__init__.py:244-258).
  */
 int gcrf_marginals_windowed_peers(gcrf_model *model, const int32_t *contig_ptr, const void *gene_ptr,
