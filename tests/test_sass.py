@@ -69,3 +69,36 @@ def test_feature_kernel_is_branch_light_and_works_in_shared_memory(sass):
         assert not any("LDL" in ins or "STL" in ins for ins in body)
     for body in find(functions, "features_kernel", "Li32ELi2ELi256ELb0E"):  # sparse tables: hashed bitmaps
         assert count(body, "BRA.DIV") == 0 and count(body, "ATOMS.OR") >= 2
+
+
+def test_streaming_kernel_variants_exist(sass):
+    """Nine window sizes, the half / quarter-tile variants of W = 5 and 20, and the peer-store instantiation."""
+    functions, _ = sass
+    for w in (5, 10, 15, 20, 25, 30, 40, 50, 64):
+        assert find(functions, "stream_kernel", f"ILi{w}ELi128ELi4EiLi256ELb0E")
+    for w in (5, 20):
+        for slots in (128, 64):
+            assert find(functions, "stream_kernel", f"ILi{w}ELi128ELi4EiLi{slots}ELb0E")
+        assert find(functions, "stream_kernel", f"ILi{w}ELi128ELi4EiLi256ELb1E")
+
+
+def test_reference_order_f64_kernel(sass):
+    """separate double multiplies and adds (the recursion is not contracted into FMAs: the only DFMAs are
+    those of the IEEE division sequence and of the double-double exponential), 64-bit atomic max for the pool."""
+    functions, _ = sass
+    for body in find(functions, "exact_window_kernel", "ILi20E"):
+        assert count(body, "DMUL") >= 200 and count(body, "DADD") >= 60
+        assert count(body, "MUFU.RCP64H") >= 20, "IEEE divisions (reciprocal seed + Newton steps)"
+        assert any("ATOMG" in ins and "MAX" in ins and "64" in ins for ins in body) or any("RED" in ins and "MAX" in ins for ins in body)
+        assert not any("LDL" in ins or "STL" in ins for ins in body)
+    for body in find(functions, "exact_unary_kernel"):
+        assert count(body, "DFMA") >= 20 and count(body, "DADD") >= 10  # the double-double exponential
+
+
+def test_segment_kernels_are_ballot_and_popcount_code(sass):
+    """gene masks by warp votes, bit-parallel replay, release / acquire flags instead of grid barriers."""
+    functions, _ = sass
+    for body in find(functions, "scan_kernel", "SegmentsArgs"):
+        assert count(body, "VOTE") >= 5 and count(body, "POPC") >= 10 and count(body, "FLO") >= 1
+        assert any("LDG" in ins and "STRONG.GPU" in ins for ins in body), "acquire loads of the published summaries"
+        assert not any("LDL" in ins or "STL" in ins for ins in body)
