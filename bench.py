@@ -50,7 +50,7 @@ import numpy  # noqa: E402
 METRIC = "genes/sec CRF marginal inference"
 UNIT = "genes/s"
 WINDOW, STEP, PAD = 20, 1, True
-KERNEL_NAME = "gcrf::stream_kernel<20,128,4,int>"
+KERNEL_NAME = "gcrf::stream_kernel<20,128,4,int,256,false>"
 
 
 def load_weights():

@@ -103,6 +103,10 @@ struct gcrf_model {
     static constexpr int kMaxSlices = 8;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_slice[kMaxSlices] = {};
+    // gcrf_marginals_windowed_wire with several slices: the copies in run on their own stream as well, so that the
+    // kernels of slice k (stream) overlap the copy in of slice k+1 (in_stream) and the copy back of slice k-1
+    cudaStream_t in_stream = nullptr;
+    cudaEvent_t ev_in[kMaxSlices] = {};
     bool timed = false;
     bool timing = false;  // record events around the kernels (gcrf_model_set_timing)
     bool ev_open = false; // ev_start already recorded by this call (in front of a widening / feature-extraction kernel)
@@ -113,7 +117,7 @@ struct gcrf_model {
     void *peer_out[gcrf::WindowedArgs::kMaxPeers] = {};  // gcrf_marginals_windowed_peers: valid during that call only
     int32_t n_peer_out = 0, peer_multicast = 0;
     int64_t slice_gene_base = 0;  // GCRF_FLAG_SLICE
-    DeviceBuffer b_wire, b_wire_sums;      // gcrf_marginals_windowed_wire: the block as it came over PCIe, scan scratch
+    DeviceBuffer b_wire;        // gcrf_marginals_windowed_wire: the block as it came over PCIe
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
     DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
 };
@@ -397,9 +401,14 @@ int gcrf_model_create(const double *state_w, int32_t A, int32_t L, const double 
     m->stream = m->own_stream;
     if ((err = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return cleanup(fail_cuda(err, "cudaStreamCreate"));
-    for (int k = 0; k < gcrf_model::kMaxSlices; ++k)
+    if ((err = cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cleanup(fail_cuda(err, "cudaStreamCreate"));
+    for (int k = 0; k < gcrf_model::kMaxSlices; ++k) {
         if ((err = cudaEventCreateWithFlags(&m->ev_slice[k], cudaEventDisableTiming)) != cudaSuccess)
             return cleanup(fail_cuda(err, "cudaEventCreate"));
+        if ((err = cudaEventCreateWithFlags(&m->ev_in[k], cudaEventDisableTiming)) != cudaSuccess)
+            return cleanup(fail_cuda(err, "cudaEventCreate"));
+    }
     if ((err = cudaEventCreate(&m->ev_start)) != cudaSuccess) return cleanup(fail_cuda(err, "cudaEventCreate"));
     if ((err = cudaEventCreate(&m->ev_stop)) != cudaSuccess) return cleanup(fail_cuda(err, "cudaEventCreate"));
     m->dev.table = m->d_table;
@@ -429,7 +438,6 @@ void gcrf_model_destroy(gcrf_model *m) {
     m->b_idx16.release();
     m->b_acc.release();
     m->b_wire.release();
-    m->b_wire_sums.release();
     m->b_unary.release();
     m->b_pool.release();
     m->b_work.release();
@@ -440,8 +448,14 @@ void gcrf_model_destroy(gcrf_model *m) {
     if (m->d_lut) cudaFree(m->d_lut);
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
-    for (int k = 0; k < gcrf_model::kMaxSlices; ++k)
+    for (int k = 0; k < gcrf_model::kMaxSlices; ++k) {
         if (m->ev_slice[k]) cudaEventDestroy(m->ev_slice[k]);
+        if (m->ev_in[k]) cudaEventDestroy(m->ev_in[k]);
+    }
+    if (m->in_stream) {
+        cudaStreamSynchronize(m->in_stream);
+        cudaStreamDestroy(m->in_stream);
+    }
     if (m->copy_stream) {
         cudaStreamSynchronize(m->copy_stream);
         cudaStreamDestroy(m->copy_stream);
@@ -696,6 +710,43 @@ int gcrf_marginals_windowed_peers(gcrf_model *m, const int32_t *contig_ptr, cons
 
 extern "C" {
 
+namespace {
+// GCRF_WIRE_TRACE=1: a timeline of one sliced call on stderr (events on the three streams), for tools/wire_slices_probe.py
+struct WireTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    struct Mark { cudaEvent_t ev; const char *what; int slice; };
+    std::vector<Mark> marks;
+    WireTrace() {
+        static const bool enabled = getenv("GCRF_WIRE_TRACE") != nullptr;
+        on = enabled;
+    }
+    void start(cudaStream_t s) {
+        if (!on) return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s);
+    }
+
+    void mark(cudaStream_t s, const char *what, int slice) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.push_back({e, what, slice});
+    }
+    ~WireTrace() {
+        if (!on || !t0) return;
+        for (auto &k : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, k.ev);
+            fprintf(stderr, "[gcrf wire] slice %d %-10s done at %.3f ms\n", k.slice, k.what, ms);
+            cudaEventDestroy(k.ev);
+        }
+        cudaEventDestroy(t0);
+    }
+};
+}  // namespace
+
 int gcrf_marginals_windowed_wire(gcrf_model *m, const gcrf_wire *w, int32_t window, int32_t step, int32_t pad, void *out,
                                  uint32_t flags) {
     if (!m) return fail(GCRF_EINVAL, "model handle is NULL");
@@ -710,59 +761,103 @@ int gcrf_marginals_windowed_wire(gcrf_model *m, const gcrf_wire *w, int32_t wind
     const int lw = gcrf::wire_len_width(w);
     const char *h = gcrf::wire_block(w);
     GCRF_CUDA(m->b_wire.reserve(gcrf::wire_total(w)));
-    GCRF_CUDA(m->b_wire_sums.reserve((size_t)gcrf::wire_chunks(G) * 2 * sizeof(int64_t) + 64));
     GCRF_CUDA(m->b_gene.reserve((size_t)(G + 1) * 4));
     GCRF_CUDA(m->b_attr.reserve((size_t)(nnz > 0 ? nnz : 1) * 4 + 64));
     GCRF_CUDA(m->b_out.reserve((size_t)G * osz));
-    char *d = static_cast<char *>(m->b_wire.ptr);
-    const size_t o_ids = gcrf::wire_off_len_ids(w), o_bytes = gcrf::wire_off_len_bytes(w), o_stream = gcrf::wire_off_stream(w);
-    // The block was cut into contig-aligned slices when it was encoded: while slice k is decoded, run through the
-    // kernels and copied back (copy_stream), slice k+1 is already on its way in — PCIe is full duplex and the two
-    // directions have their own copy engines.  Every array lands where the whole batch would have put it.
-    const int slices = m->timing ? 1 : gcrf::wire_slices(w);  // one bracketed region when the kernels are being timed
-    GCRF_CUDA(cudaMemcpyAsync(d, h, (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, m->stream));
-    int used = 0;
-    for (int k = 0; k < slices; ++k) {
+    char *d = static_cast<char *>(m->b_wire.ptr);  // the device copy has the layout of the host block
+    // The block was cut into contig-aligned slices when it was encoded, each one section of the block.  Three streams:
+    // slice k+1 comes in (in_stream) while slice k is decoded and run through the kernels (stream) and slice k-1
+    // travels back (copy_stream); every array lands where the whole batch would have put it.  The copy in is the long
+    // pole (PCIe); the rest hides behind it except for the last — smallest — slice's kernels and copy back.
+    // With the kernels being timed (gcrf_model_set_timing) the three stages run one after the other on `stream`, so
+    // that the bracketed region holds kernels only.
+    const int slices = gcrf::wire_slices(w);
+    const bool pipelined = slices > 1 && !m->timing;
+    cudaStream_t in = pipelined ? m->in_stream : m->stream, back = pipelined ? m->copy_stream : m->stream;
+    WireTrace trace;
+    trace.start(m->stream);
+    if (pipelined) {  // work queued on the caller's stream before this call stays ahead of it
+        GCRF_CUDA(cudaEventRecord(m->ev_slice[0], m->stream));
+        GCRF_CUDA(cudaStreamWaitEvent(in, m->ev_slice[0], 0));
+    }
+    GCRF_CUDA(cudaMemcpyAsync(d, h, gcrf::wire_head_bytes(w), cudaMemcpyHostToDevice, in));  // contig_ptr + chunk sums
+
+    auto copy_in = [&](int k) -> int {
+        NvtxRange range("gcrf:stage wire");
+        size_t off, size, rel_bytes, rel_stream;
+        int64_t chunk0;
+        gcrf::wire_section(w, k, &off, &size, &rel_bytes, &rel_stream, &chunk0);
+        GCRF_CUDA(cudaMemcpyAsync(d + off, h + off, size, cudaMemcpyHostToDevice, in));
+        trace.mark(in, "copy in", k);
+        if (pipelined) GCRF_CUDA(cudaEventRecord(m->ev_in[k], in));
+        return GCRF_OK;
+    };
+    bool timed_before = false;
+    auto kernels = [&](int k) -> int {
         int64_t c0, c1, g0, g1, p0, p1, b0, b1;
-        if (slices == 1) {
-            c0 = 0; c1 = C; g0 = 0; g1 = G; p0 = 0; p1 = nnz; b0 = 0; b1 = gcrf::wire_stream_bytes(w);
-        } else {
-            gcrf::wire_slice(w, k, &c0, &g0, &p0, &b0);
-            gcrf::wire_slice(w, k + 1, &c1, &g1, &p1, &b1);
-        }
-        if (g1 <= g0) continue;
-        {
-            NvtxRange range("gcrf:stage wire");
-            GCRF_CUDA(cudaMemcpyAsync(d + o_ids + (size_t)g0 * lw, h + o_ids + (size_t)g0 * lw, (size_t)(g1 - g0) * lw, cudaMemcpyHostToDevice, m->stream));
-            GCRF_CUDA(cudaMemcpyAsync(d + o_bytes + (size_t)g0 * lw, h + o_bytes + (size_t)g0 * lw, (size_t)(g1 - g0) * lw, cudaMemcpyHostToDevice, m->stream));
-            if (b1 > b0)
-                GCRF_CUDA(cudaMemcpyAsync(d + o_stream + (size_t)b0, h + o_stream + (size_t)b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, m->stream));
-            GCRF_CUDA(timing_begin(m));
-            cudaError_t derr = gcrf::launch_wire_decode(d + o_ids + (size_t)g0 * lw, d + o_bytes + (size_t)g0 * lw, lw,
-                                                        reinterpret_cast<const uint8_t *>(d + o_stream) + b0, g1 - g0, p0,
-                                                        static_cast<int64_t *>(m->b_wire_sums.ptr), static_cast<int32_t *>(m->b_gene.ptr) + g0,
-                                                        static_cast<int32_t *>(m->b_attr.ptr), m->stream, &m->launches);
-            if (derr != cudaSuccess) return fail_cuda(derr, "launch_wire_decode");
-        }
+        gcrf::wire_slice(w, k, &c0, &g0, &p0, &b0);
+        gcrf::wire_slice(w, k + 1, &c1, &g1, &p1, &b1);
+        size_t off, size, rel_bytes, rel_stream;
+        int64_t chunk0;
+        gcrf::wire_section(w, k, &off, &size, &rel_bytes, &rel_stream, &chunk0);
+        if (pipelined) GCRF_CUDA(cudaStreamWaitEvent(m->stream, m->ev_in[k], 0));
+        if (timed_before) m->ev_open = true;  // one bracket around the kernels of all slices: the first start, the last stop
+        GCRF_CUDA(timing_begin(m));
+        timed_before = m->timing;
+        trace.mark(m->stream, "ready", k);
+        cudaError_t derr = gcrf::launch_wire_decode(d + off, d + off + rel_bytes, lw, reinterpret_cast<const uint8_t *>(d + off + rel_stream),
+                                                    g1 - g0, p0, gcrf::wire_short_deltas(w),
+                                                    reinterpret_cast<const int64_t *>(d + gcrf::wire_off_sums(w)) + 2 * chunk0,
+                                                    static_cast<int32_t *>(m->b_gene.ptr) + g0, static_cast<int32_t *>(m->b_attr.ptr),
+                                                    m->stream, &m->launches);
+        if (derr != cudaSuccess) return fail_cuda(derr, "launch_wire_decode");
+        trace.mark(m->stream, "decoded", k);
         // the decoded slice is a device-pointer batch of the regular entry point; its result lands in the library's buffer
         m->slice_gene_base = g0;
         const int rc = gcrf_marginals_windowed(m, reinterpret_cast<const int32_t *>(d) + c0, static_cast<int32_t *>(m->b_gene.ptr) + g0,
-                                               m->b_attr.ptr, c1 - c0, g1 - g0, nnz, window, step, pad,
-                                               static_cast<char *>(m->b_out.ptr) + (size_t)g0 * osz,
+                                               m->b_attr.ptr, c1 - c0, g1 - g0, p1 - p0 /* the slice's own density picks the tile size */,
+                                               window, step, pad, static_cast<char *>(m->b_out.ptr) + (size_t)g0 * osz,
                                                flags | GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_SLICE);
         if (rc != GCRF_OK) return rc;
+        trace.mark(m->stream, "kernels", k);
+        if (pipelined) GCRF_CUDA(cudaEventRecord(m->ev_slice[k], m->stream));
+        return GCRF_OK;
+    };
+    auto copy_back = [&](int k) -> int {
         NvtxRange range("gcrf:finish");
-        cudaStream_t back = m->stream;
-        if (slices > 1) {
-            GCRF_CUDA(cudaEventRecord(m->ev_slice[used], m->stream));
-            GCRF_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_slice[used], 0));
-            back = m->copy_stream;
-            ++used;
-        }
+        int64_t c0, c1, g0, g1, p0, p1, b0, b1;
+        gcrf::wire_slice(w, k, &c0, &g0, &p0, &b0);
+        gcrf::wire_slice(w, k + 1, &c1, &g1, &p1, &b1);
+        if (pipelined) GCRF_CUDA(cudaStreamWaitEvent(back, m->ev_slice[k], 0));
         GCRF_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + (size_t)g0 * osz, static_cast<char *>(m->b_out.ptr) + (size_t)g0 * osz,
                                   (size_t)(g1 - g0) * osz, cudaMemcpyDeviceToHost, back));
+        trace.mark(back, "copy back", k);
+        return GCRF_OK;
+    };
+    auto empty = [&](int k) {
+        int64_t c0, c1, g0, g1, p0, p1, b0, b1;
+        gcrf::wire_slice(w, k, &c0, &g0, &p0, &b0);
+        gcrf::wire_slice(w, k + 1, &c1, &g1, &p1, &b1);
+        return g1 <= g0;
+    };
+    int rc = GCRF_OK;
+    if (pipelined) {
+        for (int k = 0; k < slices; ++k) {
+            if (empty(k)) continue;
+            if ((rc = copy_in(k)) != GCRF_OK || (rc = kernels(k)) != GCRF_OK || (rc = copy_back(k)) != GCRF_OK) return rc;
+        }
+    } else {
+        for (int k = 0; k < slices; ++k)
+            if (!empty(k) && (rc = copy_in(k)) != GCRF_OK) return rc;
+        for (int k = 0; k < slices; ++k)
+            if (!empty(k) && (rc = kernels(k)) != GCRF_OK) return rc;
+        for (int k = 0; k < slices; ++k)
+            if (!empty(k) && (rc = copy_back(k)) != GCRF_OK) return rc;
     }
-    if (slices > 1) GCRF_CUDA(cudaStreamSynchronize(m->copy_stream));
+    if (pipelined) {
+        GCRF_CUDA(cudaStreamSynchronize(m->in_stream));
+        GCRF_CUDA(cudaStreamSynchronize(m->copy_stream));
+    }
     GCRF_CUDA(cudaStreamSynchronize(m->stream));
     return GCRF_OK;
 }

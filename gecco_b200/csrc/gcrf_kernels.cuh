@@ -120,22 +120,23 @@ cudaError_t launch_features(const int32_t *accession, const int32_t *gene_ptr32,
 // uint16 attribute ids -> int32 (0xFFFF -> -1); out holds at least round_up(n, 8) entries
 cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int num_sms, cudaStream_t stream, int64_t *launches);
 
-// Compact wire format (gcrf_wire.cu): rebuild gene_ptr[G+1] / attr_idx[nnz] from the length arrays and the delta-coded
-// id stream; `sums` is scratch of 2 * wire_chunks(G) int64.
+// Compact wire format (gcrf_wire.cu): rebuild gene_ptr[G+1] / attr_idx[nnz] of one slice from its length arrays and its
+// stretch of the delta-coded id stream.  `sums` = the encoder's chunk sums of the slice (device copy), id_base = attribute
+// ids in front of the slice; gene_ptr (the slice's first entry) receives absolute offsets into attr_idx; short_deltas:
+// every delta is below 2^21, i.e. at most three bytes.  One launch.
 int64_t wire_chunks(int64_t G);
-// (slice form: the arrays point at the slice's first gene / first stream byte, id_base = attribute ids in front of it;
-// gene_ptr receives absolute offsets into attr_idx)
 cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
-                               int64_t id_base, int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t stream_,
-                               int64_t *launches);
+                               int64_t id_base, bool short_deltas, const int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx,
+                               cudaStream_t stream_, int64_t *launches);
+bool wire_short_deltas(const gcrf_wire *w);
 int wire_slices(const gcrf_wire *w);
 void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte);  // k in [0, slices]
 int64_t wire_stream_bytes(const gcrf_wire *w);
 const char *wire_block(const gcrf_wire *w);
 size_t wire_total(const gcrf_wire *w);
-size_t wire_off_len_ids(const gcrf_wire *w);
-size_t wire_off_len_bytes(const gcrf_wire *w);
-size_t wire_off_stream(const gcrf_wire *w);
+size_t wire_head_bytes(const gcrf_wire *w);
+size_t wire_off_sums(const gcrf_wire *w);
+void wire_section(const gcrf_wire *w, int k, size_t *off, size_t *size, size_t *rel_len_bytes, size_t *rel_stream, int64_t *first_chunk);
 int32_t wire_len_width(const gcrf_wire *w);
 
 // Threshold + segment extraction (gcrf_segments.cu; gecco/refine.py:51-200, criterion "gecco").

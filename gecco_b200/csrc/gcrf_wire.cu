@@ -29,20 +29,27 @@
 struct gcrf_wire {
     int64_t C = 0, G = 0, nnz = 0, stream_bytes = 0;
     int32_t A = 0;
-    int32_t len_width = 1;  // bytes per entry of len_ids / len_bytes: 1 or 2
-    char *block = nullptr;  // page-locked: [contig_ptr | len_ids | len_bytes | stream], every part 16-byte aligned
-    size_t off_len_ids = 0, off_len_bytes = 0, off_stream = 0, total = 0;
-    // contig-aligned slices of about equal bytes (the call overlaps slice k's way back with slice k+1's way in)
+    int32_t len_width = 1;  // bytes per entry of len_ids / len_bytes: 1 or 2 (negative: the block came from malloc)
+    // One page-locked block, every part 16-byte aligned:
+    //   [contig_ptr int32[C+1] | chunk sums int64[2 * chunks] | section of slice 0 | section of slice 1 | ...]
+    //   section of a slice = [len_ids | len_bytes | its stretch of the delta stream]
+    // The head (contig_ptr + sums) and every section travel as ONE copy each.  The chunk sums are what the decoder's
+    // blocks start from: ids and stream bytes in front of every kChunk-th gene of the slice, relative to the slice.
+    char *block = nullptr;
+    size_t off_sums = 0, total = 0;
+    // contig-aligned slices (the bulk call pipelines them: copy in / decode + kernels / copy back)
     static constexpr int kMaxSlices = 8;
     int n_slices = 1;
     int64_t s_contig[kMaxSlices + 1] = {}, s_gene[kMaxSlices + 1] = {}, s_id[kMaxSlices + 1] = {}, s_byte[kMaxSlices + 1] = {};
+    size_t s_off[kMaxSlices] = {}, s_size[kMaxSlices] = {};
+    int64_t s_chunk[kMaxSlices + 1] = {};  // index of the slice's first pair of chunk sums
 };
 
 namespace gcrf {
 
 namespace {
 
-constexpr int kWireThreads = 256, kWirePerThread = 8, kWireChunk = kWireThreads * kWirePerThread;  // genes per block
+constexpr int kWireThreads = 256, kWirePerThread = 2, kWireChunk = kWireThreads * kWirePerThread;  // genes per block
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -55,91 +62,72 @@ inline void put_varint(std::vector<uint8_t> &out, uint32_t v) {
     out.push_back((uint8_t)v);
 }
 
-// ---- kernel 1: per block of kWireChunk genes, the sums of both length arrays
-template <typename LenT>
-__global__ void __launch_bounds__(kWireThreads)
-wire_block_sums_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ len_bytes, int64_t G, int64_t *__restrict__ sums) {
-    __shared__ long long sA[kWireThreads / 32], sB[kWireThreads / 32];
-    const int64_t base = (int64_t)blockIdx.x * kWireChunk;
-    long long a = 0, b = 0;
-    for (int k = 0; k < kWirePerThread; ++k) {
-        const int64_t g = base + threadIdx.x + (int64_t)k * kWireThreads;
-        if (g < G) {
-            a += len_ids[g];
-            b += len_bytes[g];
+// ---- the decoder: offsets of every gene inside its block (scan), gene_ptr, and the ids themselves.  `sums` holds, per
+// block, the ids and stream bytes in front of it (written by the encoder: no scan over the whole batch on the device).
+// The block's stretch of the byte stream is contiguous, and so are the ids it produces: both go through shared
+// memory in rounds (as many genes as fit the two staging areas), so that global memory sees 16-byte loads and
+// coalesced 4-byte stores only; the serial LEB128 walk of one gene per thread runs on shared memory.  (The first
+// version walked global memory directly: 0.41 ms for BASELINE config 2, five times this one.)
+constexpr int kWireCapIds = 8192;     // ids staged per round
+constexpr int kWireCapBytes = 12288;  // stream bytes staged per round (plus the 16-byte alignment slack)
+constexpr int kWireInSlack = 32;       // 16 for the alignment of the first word, 8 + for the look-ahead of decode_gene_short
+constexpr size_t kWireDecodeSmem = (size_t)(2 * (kWireChunk + 1)) * sizeof(int) + (size_t)kWireCapIds * 4 + kWireCapBytes + kWireInSlack + 16;
+
+__device__ __forceinline__ const uint8_t *decode_gene(const uint8_t *src, int n, int32_t *dst) {
+    int32_t prev = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t v = 0, byte;
+        int shift = 0;
+        do {
+            byte = *src++;
+            v |= (byte & 127u) << shift;
+            shift += 7;
+        } while (byte & 128u);
+        prev += (int32_t)v;
+        dst[i] = prev;
+    }
+    return src;
+}
+
+// The same walk for deltas below 2^21 (at most three bytes each; the encoder says so per batch), on shared memory:
+// a 64-bit window of the upcoming bytes refilled by aligned 4-byte loads, length and value of a varint from its
+// continuation bits without a loop — a third of the instructions of the byte-by-byte walk, one load per four bytes.
+// Reads up to 11 bytes past the gene's last byte (inside the staging area's slack).
+__device__ __forceinline__ void decode_gene_short(const uint8_t *src, int n, int32_t *dst) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *next = reinterpret_cast<const uint32_t *>(src - mis);
+    unsigned long long w = ((unsigned long long)next[1] << 32 | next[0]) >> (8 * mis);
+    int avail = 8 - (int)mis;
+    next += 2;
+    int32_t prev = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t x = (uint32_t)w;
+        const bool c0 = (x & 0x80u) != 0, c1 = c0 && (x & 0x8000u) != 0;
+        uint32_t v = x & 0x7fu;
+        if (c0) v |= (x >> 1) & 0x3f80u;
+        if (c1) v |= (x >> 2) & 0x1fc000u;
+        const int len = 1 + (c0 ? 1 : 0) + (c1 ? 1 : 0);
+        w >>= 8 * len;
+        avail -= len;
+        if (avail < 4) {
+            w |= (unsigned long long)*next++ << (8 * avail);
+            avail += 4;
         }
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-        a += __shfl_down_sync(0xffffffffu, a, d);
-        b += __shfl_down_sync(0xffffffffu, b, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        sA[threadIdx.x >> 5] = a;
-        sB[threadIdx.x >> 5] = b;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long ta = 0, tb = 0;
-        for (int w = 0; w < kWireThreads / 32; ++w) {
-            ta += sA[w];
-            tb += sB[w];
-        }
-        sums[2 * (int64_t)blockIdx.x] = ta;
-        sums[2 * (int64_t)blockIdx.x + 1] = tb;
+        prev += (int32_t)v;
+        dst[i] = prev;
     }
 }
 
-// ---- kernel 2: exclusive scan of the block sums, in place (one block; n = number of chunks)
-__global__ void __launch_bounds__(1024)
-wire_scan_sums_kernel(int64_t *__restrict__ sums, int64_t n) {
-    __shared__ long long sWarp[2][32];
-    __shared__ long long sCarry[2];
-    if (threadIdx.x < 2) sCarry[threadIdx.x] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        long long v[2] = {i < n ? sums[2 * i] : 0, i < n ? sums[2 * i + 1] : 0};
-        long long inc[2] = {v[0], v[1]};
-        for (int c = 0; c < 2; ++c) {
-            for (int d = 1; d < 32; d <<= 1) {
-                const long long y = __shfl_up_sync(0xffffffffu, inc[c], d);
-                if (lane >= d) inc[c] += y;
-            }
-            if (lane == 31) sWarp[c][warp] = inc[c];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            for (int c = 0; c < 2; ++c) {
-                long long w = sWarp[c][lane];
-                for (int d = 1; d < 32; d <<= 1) {
-                    const long long y = __shfl_up_sync(0xffffffffu, w, d);
-                    if (lane >= d) w += y;
-                }
-                sWarp[c][lane] = w;  // inclusive scan of the warp totals
-            }
-        }
-        __syncthreads();
-        for (int c = 0; c < 2; ++c) {
-            const long long before = sCarry[c] + (warp > 0 ? sWarp[c][warp - 1] : 0) + inc[c] - v[c];
-            if (i < n) sums[2 * i + c] = before;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            sCarry[0] += sWarp[0][31];
-            sCarry[1] += sWarp[1][31];
-        }
-        __syncthreads();
-    }
-}
-
-// ---- kernel 3: offsets of every gene inside its block (scan), gene_ptr, and the ids themselves
-template <typename LenT>
+template <typename LenT, bool SHORT>
 __global__ void __launch_bounds__(kWireThreads)
 wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ len_bytes, const uint8_t *__restrict__ stream,
                    int64_t G, int64_t id_base, const int64_t *__restrict__ sums, int32_t *__restrict__ gene_ptr,
                    int32_t *__restrict__ attr_idx) {
-    __shared__ int sIds[kWireChunk], sBytes[kWireChunk];  // lengths, then exclusive offsets within the block
+    extern __shared__ __align__(16) unsigned char sDyn[];
+    int32_t *sOut = reinterpret_cast<int32_t *>(sDyn);                    // [kWireCapIds]
+    uint8_t *sIn = sDyn + (size_t)kWireCapIds * 4;                        // [kWireCapBytes + kWireInSlack]
+    int *sIds = reinterpret_cast<int *>(sIn + kWireCapBytes + kWireInSlack);  // [kWireChunk + 1] lengths, then exclusive offsets
+    int *sBytes = sIds + kWireChunk + 1;                                  // [kWireChunk + 1]
     __shared__ int sWarpA[kWireThreads / 32], sWarpB[kWireThreads / 32];
     const int64_t base = (int64_t)blockIdx.x * kWireChunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -183,29 +171,48 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
         sIds[tid * kWirePerThread + k] = wa + ia - ta + a[k];
         sBytes[tid * kWirePerThread + k] = wb + ib - tb + b[k];
     }
+    if (tid == kWireThreads - 1) {  // the sentinel: totals of the block
+        sIds[kWireChunk] = wa + ia;
+        sBytes[kWireChunk] = wb + ib;
+    }
     __syncthreads();
     const int64_t id0 = id_base + sums[2 * (int64_t)blockIdx.x], byte0 = sums[2 * (int64_t)blockIdx.x + 1];
-    for (int k = 0; k < kWirePerThread; ++k) {
-        const int j = tid + k * kWireThreads;  // neighbouring threads take neighbouring genes: their bytes share lines
-        const int64_t g = base + j;
-        if (g >= G) break;
-        const int64_t p0 = id0 + sIds[j];
-        gene_ptr[g] = (int32_t)p0;
-        const int n = (int)len_ids[g];
-        const uint8_t *src = stream + byte0 + sBytes[j];
-        int32_t prev = 0;
-        for (int i = 0; i < n; ++i) {
-            uint32_t v = 0, byte;
-            int shift = 0;
-            do {
-                byte = *src++;
-                v |= (byte & 127u) << shift;
-                shift += 7;
-            } while (byte & 128u);
-            prev += (int32_t)v;
-            attr_idx[p0 + i] = prev;
+    const int nG = (int)(G - base < kWireChunk ? G - base : kWireChunk);
+    for (int j = tid; j < nG; j += kWireThreads) gene_ptr[base + j] = (int32_t)(id0 + sIds[j]);
+    if (base + nG == G && tid == 0) gene_ptr[G] = (int32_t)(id0 + sIds[nG]);
+
+    int s = 0;
+    while (s < nG) {  // every quantity that steers the loop is the same in all threads
+        const int i0 = sIds[s], b0 = sBytes[s];
+        // the largest e <= nG whose genes [s, e) fit both staging areas (the offsets are non-decreasing)
+        int lo = s, hi = nG;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sIds[mid] - i0 <= kWireCapIds && sBytes[mid] - b0 <= kWireCapBytes) lo = mid;
+            else hi = mid - 1;
         }
-        if (g == G - 1) gene_ptr[G] = (int32_t)(p0 + n);
+        const int e = lo;
+        if (e == s) {  // one gene larger than a staging area (thousands of domains): straight from and to global memory
+            if (tid == 0) decode_gene(stream + byte0 + b0, sIds[s + 1] - i0, attr_idx + id0 + i0);
+            s += 1;
+            continue;
+        }
+        const int nbytes = sBytes[e] - b0, nids = sIds[e] - i0;
+        const uint8_t *src = stream + byte0 + b0;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint4 *src16 = reinterpret_cast<const uint4 *>(src - mis);
+        const int n16 = (mis + nbytes + 15) >> 4;
+        for (int k = tid; k < n16; k += kWireThreads) reinterpret_cast<uint4 *>(sIn)[k] = __ldg(src16 + k);
+        __syncthreads();
+        for (int j = s + tid; j < e; j += kWireThreads) {
+            if constexpr (SHORT) decode_gene_short(sIn + mis + (sBytes[j] - b0), sIds[j + 1] - sIds[j], sOut + (sIds[j] - i0));
+            else decode_gene(sIn + mis + (sBytes[j] - b0), sIds[j + 1] - sIds[j], sOut + (sIds[j] - i0));
+        }
+        __syncthreads();
+        int32_t *dst = attr_idx + id0 + i0;
+        for (int k = tid; k < nids; k += kWireThreads) dst[k] = sOut[k];
+        __syncthreads();
+        s = e;
     }
 }
 
@@ -214,28 +221,26 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
 int64_t wire_chunks(int64_t G) { return (G + kWireChunk - 1) / kWireChunk; }
 
 cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
-                               int64_t id_base, int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx, cudaStream_t cuda_stream,
-                               int64_t *launches) {
+                               int64_t id_base, bool short_deltas, const int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx,
+                               cudaStream_t cuda_stream, int64_t *launches) {
     if (G <= 0) return cudaSuccess;
     const int64_t nb = wire_chunks(G);
+    auto decode = [&](auto kernel, auto *ids, auto *bytes) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWireDecodeSmem);
+        if (err != cudaSuccess) return err;
+        kernel<<<(unsigned)nb, kWireThreads, kWireDecodeSmem, cuda_stream>>>(ids, bytes, stream, G, id_base, sums, gene_ptr, attr_idx);
+        return cudaSuccess;
+    };
+    cudaError_t err;
     if (len_width == 1) {
-        wire_block_sums_kernel<uint8_t><<<(unsigned)nb, kWireThreads, 0, cuda_stream>>>(static_cast<const uint8_t *>(len_ids),
-                                                                                     static_cast<const uint8_t *>(len_bytes), G, sums);
+        auto *ids = static_cast<const uint8_t *>(len_ids), *bytes = static_cast<const uint8_t *>(len_bytes);
+        err = short_deltas ? decode(wire_decode_kernel<uint8_t, true>, ids, bytes) : decode(wire_decode_kernel<uint8_t, false>, ids, bytes);
     } else {
-        wire_block_sums_kernel<uint16_t><<<(unsigned)nb, kWireThreads, 0, cuda_stream>>>(static_cast<const uint16_t *>(len_ids),
-                                                                                      static_cast<const uint16_t *>(len_bytes), G, sums);
+        auto *ids = static_cast<const uint16_t *>(len_ids), *bytes = static_cast<const uint16_t *>(len_bytes);
+        err = short_deltas ? decode(wire_decode_kernel<uint16_t, true>, ids, bytes) : decode(wire_decode_kernel<uint16_t, false>, ids, bytes);
     }
-    wire_scan_sums_kernel<<<1, 1024, 0, cuda_stream>>>(sums, nb);
-    if (len_width == 1) {
-        wire_decode_kernel<uint8_t><<<(unsigned)nb, kWireThreads, 0, cuda_stream>>>(static_cast<const uint8_t *>(len_ids),
-                                                                                 static_cast<const uint8_t *>(len_bytes), stream, G, id_base,
-                                                                                 sums, gene_ptr, attr_idx);
-    } else {
-        wire_decode_kernel<uint16_t><<<(unsigned)nb, kWireThreads, 0, cuda_stream>>>(static_cast<const uint16_t *>(len_ids),
-                                                                                  static_cast<const uint16_t *>(len_bytes), stream, G, id_base,
-                                                                                  sums, gene_ptr, attr_idx);
-    }
-    if (launches) *launches += 3;
+    if (err != cudaSuccess) return err;
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
@@ -333,58 +338,35 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
     gcrf_wire *w = new (std::nothrow) gcrf_wire();
     if (!w) return wire_fail(GCRF_ENOMEM, "out of host memory");
     w->C = C; w->G = G; w->nnz = nnz; w->A = num_attrs; w->stream_bytes = stream_bytes;
-    w->len_width = longest > 0xFF ? 2 : 1;
-    w->off_len_ids = gcrf::align16((size_t)(C + 1) * 4);
-    w->off_len_bytes = gcrf::align16(w->off_len_ids + (size_t)G * w->len_width);
-    w->off_stream = gcrf::align16(w->off_len_bytes + (size_t)G * w->len_width);
-    w->total = gcrf::align16(w->off_stream + (size_t)stream_bytes + 16);
-    if (cudaHostAlloc(reinterpret_cast<void **>(&w->block), w->total, cudaHostAllocDefault) != cudaSuccess) {
-        cudaGetLastError();
-        // no CUDA runtime / device on this host: plain memory keeps the encoder usable (the copy is then pageable)
-        w->block = static_cast<char *>(malloc(w->total));
-        if (!w->block) {
-            delete w;
-            return wire_fail(GCRF_ENOMEM, "out of host memory");
-        }
-        w->len_width = -w->len_width;  // negative: block came from malloc
-    }
-    memset(w->block, 0, w->total);
-    if (G > 0) memcpy(w->block, contig_ptr, (size_t)(C + 1) * 4);
-    const int lw = w->len_width < 0 ? -w->len_width : w->len_width;
-    int64_t g = 0;
-    size_t spos = 0;
-    for (const auto &c : chunks) {
-        for (size_t k = 0; k < c.n_ids.size(); ++k, ++g) {
-            if (lw == 1) {
-                reinterpret_cast<uint8_t *>(w->block + w->off_len_ids)[g] = (uint8_t)c.n_ids[k];
-                reinterpret_cast<uint8_t *>(w->block + w->off_len_bytes)[g] = (uint8_t)c.n_bytes[k];
-            } else {
-                reinterpret_cast<uint16_t *>(w->block + w->off_len_ids)[g] = (uint16_t)c.n_ids[k];
-                reinterpret_cast<uint16_t *>(w->block + w->off_len_bytes)[g] = (uint16_t)c.n_bytes[k];
-            }
-        }
-        if (!c.stream.empty()) memcpy(w->block + w->off_stream + spos, c.stream.data(), c.stream.size());
-        spos += c.stream.size();
-    }
-    // slice table: cut at contig starts into parts of about equal bytes moved (stream + lengths in, 8 per gene out).
-    // ONE slice unless GCRF_WIRE_SLICES asks for more: on the PCIe Gen5 hosts measured the copy back of slice k did not
-    // overlap the copy in of slice k+1 to any effect (config 2: 965 / 967 / 950 / 856 M genes/s with 1 / 2 / 4 / 8
-    // slices, profiles/r2_e2e_wire_slices.txt) and every slice costs ~25 us of extra launches and copies
+    const int lw = longest > 0xFF ? 2 : 1;
+    w->len_width = lw;
+
+    // ids and stream bytes in front of every gene; where every encoded range starts in the stream
+    std::vector<int64_t> gene_id((size_t)G + 1), gene_byte((size_t)G + 1), range_byte(chunks.size() + 1);
     {
-        std::vector<int64_t> gene_id((size_t)G + 1), gene_byte((size_t)G + 1);
         int64_t ids = 0, bytes = 0, gg = 0;
-        for (const auto &c : chunks)
-            for (size_t k = 0; k < c.n_ids.size(); ++k, ++gg) {
+        for (size_t t = 0; t < chunks.size(); ++t) {
+            range_byte[t] = bytes;
+            for (size_t k = 0; k < chunks[t].n_ids.size(); ++k, ++gg) {
                 gene_id[gg] = ids;
                 gene_byte[gg] = bytes;
-                ids += c.n_ids[k];
-                bytes += c.n_bytes[k];
+                ids += chunks[t].n_ids[k];
+                bytes += chunks[t].n_bytes[k];
             }
+        }
         gene_id[G] = ids;
         gene_byte[G] = bytes;
+        range_byte[chunks.size()] = bytes;
+    }
+    // Slice table: cut at contig starts.  A bulk call runs the slices as a three-stage pipeline (copy in / decode +
+    // kernels / copy back, gcrf_marginals_windowed_wire); the copy in is the long pole, so what the pipeline adds to it
+    // is the LAST slice's kernels and copy back: the slices shrink geometrically (8 : 4 : 2 : 1 of the bytes moved —
+    // stream + lengths in, 8 per gene out), each still long enough to cover its predecessor's kernels (~0.2 of its copy).
+    // Numbers: profiles/r2_e2e_wire_slices.txt.
+    {
         auto cost_at = [&](int64_t c) -> double { const int64_t g = contig_ptr[c]; return (double)gene_byte[g] + (2.0 * lw + 8.0) * (double)g; };
         const double total_cost = G > 0 ? cost_at(C) : 0.0;
-        int n = 1;
+        int n = total_cost >= 24e6 ? 4 : total_cost >= 8e6 ? 2 : 1;
         if (const char *env = getenv("GCRF_WIRE_SLICES")) n = atoi(env);
         if (n > gcrf_wire::kMaxSlices) n = gcrf_wire::kMaxSlices;
         if (n > C) n = (int)C;
@@ -394,7 +376,7 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
             int64_t c = k == n ? C : 0;
             if (k > 0 && k < n) {
                 int64_t lo = w->s_contig[k - 1], hi = C;
-                const double want = total_cost * k / n;
+                const double want = total_cost * (1.0 - (double)((1 << (n - k)) - 1) / (double)((1 << n) - 1));
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) / 2;
                     if (cost_at(mid) < want) lo = mid + 1; else hi = mid;
@@ -405,6 +387,60 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
             w->s_gene[k] = G > 0 ? contig_ptr[c] : 0;
             w->s_id[k] = gene_id[w->s_gene[k]];
             w->s_byte[k] = gene_byte[w->s_gene[k]];
+        }
+    }
+    // layout
+    int64_t n_chunks = 0;
+    for (int k = 0; k < w->n_slices; ++k) {
+        w->s_chunk[k] = n_chunks;
+        n_chunks += gcrf::wire_chunks(w->s_gene[k + 1] - w->s_gene[k]);
+    }
+    w->s_chunk[w->n_slices] = n_chunks;
+    w->off_sums = gcrf::align16((size_t)(C + 1) * 4);
+    size_t pos = gcrf::align16(w->off_sums + (size_t)n_chunks * 2 * sizeof(int64_t));
+    for (int k = 0; k < w->n_slices; ++k) {
+        const size_t genes = (size_t)(w->s_gene[k + 1] - w->s_gene[k]), bytes = (size_t)(w->s_byte[k + 1] - w->s_byte[k]);
+        w->s_off[k] = pos;
+        w->s_size[k] = 2 * gcrf::align16(genes * lw) + gcrf::align16(bytes + 16);  // the decoder reads whole 16-byte words
+        pos += w->s_size[k];
+    }
+    w->total = pos;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&w->block), w->total, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        // no CUDA runtime / device on this host: plain memory keeps the encoder usable (the copy is then pageable)
+        w->block = static_cast<char *>(malloc(w->total));
+        if (!w->block) {
+            delete w;
+            return wire_fail(GCRF_ENOMEM, "out of host memory");
+        }
+        w->len_width = -lw;  // negative: block came from malloc
+    }
+    memset(w->block, 0, w->total);
+    if (G > 0) memcpy(w->block, contig_ptr, (size_t)(C + 1) * 4);
+    int64_t *sums = reinterpret_cast<int64_t *>(w->block + w->off_sums);
+    for (int k = 0; k < w->n_slices; ++k) {
+        const int64_t g0 = w->s_gene[k], g1 = w->s_gene[k + 1];
+        for (int64_t j = 0, g = g0; g < g1; ++j, g += gcrf::kWireChunk) {
+            sums[2 * (w->s_chunk[k] + j)] = gene_id[g] - gene_id[g0];
+            sums[2 * (w->s_chunk[k] + j) + 1] = gene_byte[g] - gene_byte[g0];
+        }
+        char *sec = w->block + w->s_off[k];
+        char *sec_bytes = sec + gcrf::align16((size_t)(g1 - g0) * lw);
+        char *sec_stream = sec_bytes + gcrf::align16((size_t)(g1 - g0) * lw);
+        for (int64_t g = g0; g < g1; ++g) {
+            const int64_t ni = gene_id[g + 1] - gene_id[g], nb = gene_byte[g + 1] - gene_byte[g];
+            if (lw == 1) {
+                reinterpret_cast<uint8_t *>(sec)[g - g0] = (uint8_t)ni;
+                reinterpret_cast<uint8_t *>(sec_bytes)[g - g0] = (uint8_t)nb;
+            } else {
+                reinterpret_cast<uint16_t *>(sec)[g - g0] = (uint16_t)ni;
+                reinterpret_cast<uint16_t *>(sec_bytes)[g - g0] = (uint16_t)nb;
+            }
+        }
+        const int64_t b0 = w->s_byte[k], b1 = w->s_byte[k + 1];
+        for (size_t t = 0; t < chunks.size(); ++t) {  // the encoded ranges that overlap this slice's stretch of the stream
+            const int64_t lo = std::max(b0, range_byte[t]), hi = std::min(b1, range_byte[t + 1]);
+            if (hi > lo) memcpy(sec_stream + (lo - b0), chunks[t].stream.data() + (lo - range_byte[t]), (size_t)(hi - lo));
         }
     }
     *out = w;
@@ -428,28 +464,32 @@ int64_t gcrf_wire_ids(const gcrf_wire *w) { return w ? w->nnz : 0; }
 int gcrf_wire_decode_host(const gcrf_wire *w, int32_t *gene_ptr, int32_t *attr_idx) {
     if (!w || (w->G > 0 && !gene_ptr) || (w->nnz > 0 && !attr_idx)) return wire_fail(GCRF_EINVAL, "NULL argument");
     const int lw = w->len_width < 0 ? -w->len_width : w->len_width;
-    const uint8_t *src = reinterpret_cast<const uint8_t *>(w->block + w->off_stream);
     int64_t p = 0;
-    for (int64_t g = 0; g < w->G; ++g) {
-        const uint32_t n = lw == 1 ? reinterpret_cast<const uint8_t *>(w->block + w->off_len_ids)[g]
-                                   : reinterpret_cast<const uint16_t *>(w->block + w->off_len_ids)[g];
-        const uint32_t nb = lw == 1 ? reinterpret_cast<const uint8_t *>(w->block + w->off_len_bytes)[g]
-                                    : reinterpret_cast<const uint16_t *>(w->block + w->off_len_bytes)[g];
-        gene_ptr[g] = (int32_t)p;
-        const uint8_t *end = src + nb;
-        int32_t prev = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            uint32_t v = 0, byte;
-            int shift = 0;
-            do {
-                byte = *src++;
-                v |= (byte & 127u) << shift;
-                shift += 7;
-            } while (byte & 128u);
-            prev += (int32_t)v;
-            attr_idx[p++] = prev;
+    for (int k = 0; k < w->n_slices; ++k) {
+        const int64_t g0 = w->s_gene[k], g1 = w->s_gene[k + 1];
+        const char *sec = w->block + w->s_off[k];
+        const char *sec_bytes = sec + gcrf::align16((size_t)(g1 - g0) * lw);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(sec_bytes + gcrf::align16((size_t)(g1 - g0) * lw));
+        if (p != w->s_id[k]) return wire_fail(GCRF_EINVAL, "corrupt wire block");
+        for (int64_t g = g0; g < g1; ++g) {
+            const uint32_t n = lw == 1 ? reinterpret_cast<const uint8_t *>(sec)[g - g0] : reinterpret_cast<const uint16_t *>(sec)[g - g0];
+            const uint32_t nb = lw == 1 ? reinterpret_cast<const uint8_t *>(sec_bytes)[g - g0] : reinterpret_cast<const uint16_t *>(sec_bytes)[g - g0];
+            gene_ptr[g] = (int32_t)p;
+            const uint8_t *end = src + nb;
+            int32_t prev = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                uint32_t v = 0, byte;
+                int shift = 0;
+                do {
+                    byte = *src++;
+                    v |= (byte & 127u) << shift;
+                    shift += 7;
+                } while (byte & 128u);
+                prev += (int32_t)v;
+                attr_idx[p++] = prev;
+            }
+            if (src != end) return wire_fail(GCRF_EINVAL, "corrupt wire block");
         }
-        if (src != end) return wire_fail(GCRF_EINVAL, "corrupt wire block");
     }
     if (w->G > 0) gene_ptr[w->G] = (int32_t)p;
     return p == w->nnz ? GCRF_OK : wire_fail(GCRF_EINVAL, "corrupt wire block");
@@ -461,11 +501,20 @@ int gcrf_wire_decode_host(const gcrf_wire *w, int32_t *gene_ptr, int32_t *attr_i
 namespace gcrf {
 const char *wire_block(const gcrf_wire *w) { return w->block; }
 size_t wire_total(const gcrf_wire *w) { return w->total; }
-size_t wire_off_len_ids(const gcrf_wire *w) { return w->off_len_ids; }
-size_t wire_off_len_bytes(const gcrf_wire *w) { return w->off_len_bytes; }
-size_t wire_off_stream(const gcrf_wire *w) { return w->off_stream; }
+size_t wire_head_bytes(const gcrf_wire *w) { return w->n_slices > 0 ? w->s_off[0] : w->total; }  // contig_ptr + chunk sums
+size_t wire_off_sums(const gcrf_wire *w) { return w->off_sums; }
+void wire_section(const gcrf_wire *w, int k, size_t *off, size_t *size, size_t *rel_len_bytes, size_t *rel_stream, int64_t *first_chunk) {
+    const int lw = w->len_width < 0 ? -w->len_width : w->len_width;
+    const size_t part = align16((size_t)(w->s_gene[k + 1] - w->s_gene[k]) * lw);
+    *off = w->s_off[k];
+    *size = w->s_size[k];
+    *rel_len_bytes = part;
+    *rel_stream = 2 * part;
+    *first_chunk = w->s_chunk[k];
+}
 int32_t wire_len_width(const gcrf_wire *w) { return w->len_width < 0 ? -w->len_width : w->len_width; }
 int wire_slices(const gcrf_wire *w) { return w->n_slices; }
+bool wire_short_deltas(const gcrf_wire *w) { return w->A < (1 << 21); }  // deltas are at most A
 void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte) {
     *contig = w->s_contig[k];
     *gene = w->s_gene[k];

@@ -81,3 +81,90 @@ def test_wire_call_equals_the_plain_call(engine, weights, make, slices, monkeypa
         assert got32.dtype == numpy.float32 and numpy.array_equal(got32, got.astype(numpy.float32), equal_nan=True)
     exact = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, shuffled, f64_arith=True)
     assert numpy.allclose(engine.marginals_windowed_wire(wire, f64_arith=True), exact, rtol=0, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("slices", ["1", "3", "8"])
+@pytest.mark.parametrize("make", ["ragged", "dense", "long_rows"])
+def test_round_trip_of_a_sliced_block(weights, make, slices, monkeypatch):
+    """The block holds one section per slice (cut at contig starts when it is encoded): the host decoder walks them."""
+    A = len(weights.attrs)
+    rng = numpy.random.default_rng(11)
+    batch = {"ragged": lambda: synth.ragged_edge_cases(A), "dense": lambda: synth.config2(A, contigs=90),
+             "long_rows": lambda: synth.make_batch(rng, numpy.array([3, 40, 7, 1]), 400.0, A, 0.05)}[make]()
+    monkeypatch.setenv("GCRF_WIRE_SLICES", "1")
+    whole = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, A)
+    monkeypatch.setenv("GCRF_WIRE_SLICES", slices)
+    wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, A)
+    gene_ptr, attr_idx = wire.decode()
+    assert numpy.array_equal(gene_ptr, batch.gene_ptr)
+    assert numpy.array_equal(attr_idx, sorted_reference(batch, A))
+    assert wire.nbytes <= whole.nbytes + 64 * int(slices) + 16 * (batch.G // 512 + int(slices) + 1)
+
+
+@pytest.mark.gpu
+def test_a_gene_larger_than_the_decoder_staging_area(engine, weights):
+    """Rows of 9,000 - 20,000 ids (the decoder stages 8,192 ids / 12 KB of stream per round in shared memory) next to
+    ordinary ones."""
+    A = len(weights.attrs)
+    rng = numpy.random.default_rng(13)
+    sizes = numpy.array([3, 9000, 0, 25, 20000, 8192, 8193, 1, 30] + [20] * 40)
+    gene_ptr = numpy.concatenate([[0], numpy.cumsum(sizes)]).astype(numpy.int32)
+    attr_idx = rng.integers(0, A, size=int(gene_ptr[-1])).astype(numpy.int32)
+    contig_ptr = numpy.array([0, 5, 9, len(sizes)], dtype=numpy.int32)
+    wire = WireBatch(contig_ptr, gene_ptr, attr_idx, A)
+    plain = engine.marginals_windowed(contig_ptr, gene_ptr, attr_idx, window=5, step=1, pad=True)
+    got = engine.marginals_windowed_wire(wire, window=5, step=1, pad=True)
+    assert numpy.allclose(got, plain, rtol=0, atol=1e-6)
+    exact = engine.marginals_windowed(contig_ptr, gene_ptr, attr_idx, window=5, f64_arith=True)
+    # (scores of thousands of summed weights overflow exp() in the reference's arithmetic: NaN on both sides)
+    assert numpy.allclose(engine.marginals_windowed_wire(wire, window=5, f64_arith=True), exact, rtol=0, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_sliced_wire_call_with_the_kernels_being_timed(engine, weights, monkeypatch):
+    """gcrf_model_set_timing: the slices run their three stages one after the other on one stream — same numbers."""
+    A = len(weights.attrs)
+    batch = synth.config2(A, contigs=200)
+    monkeypatch.setenv("GCRF_WIRE_SLICES", "4")
+    wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, A)
+    plain = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx)
+    engine.set_timing(True)
+    try:
+        got = engine.marginals_windowed_wire(wire)
+        assert engine.last_kernel_ms() > 0
+    finally:
+        engine.set_timing(False)
+    assert numpy.array_equal(got, plain)
+    assert numpy.array_equal(engine.marginals_windowed_wire(wire), plain)
+
+
+@pytest.mark.gpu
+def test_wire_call_with_a_vocabulary_past_three_byte_deltas(weights):
+    """A model with more than 2^21 attributes: deltas can take four LEB128 bytes, the decoder's general walk."""
+    import dataclasses
+
+    from gecco_b200._lib import CRFEngine
+
+    A = (1 << 21) + 1000
+    rng = numpy.random.default_rng(17)
+    state_w = (rng.standard_normal((A, 2)) * 0.3).astype(numpy.float64)
+    big = dataclasses.replace(weights, attrs=[f"A{i}" for i in range(A)], state_w=state_w, state_mask=numpy.ones((A, 2), dtype=bool))
+    eng = CRFEngine(big, device=0)
+    sizes = rng.poisson(6.0, size=84)
+    gene_ptr = numpy.concatenate([[0], numpy.cumsum(sizes)]).astype(numpy.int32)
+    batch = synth.CsrBatch(numpy.array([0, 30, 34, 84], dtype=numpy.int32), gene_ptr,
+                           rng.integers(0, A, size=int(gene_ptr[-1])).astype(numpy.int32))
+    for g in range(0, batch.G, 7):  # deltas of four bytes: a first id (delta from 0) and a jump at or above 2^21
+        a, b = int(batch.gene_ptr[g]), int(batch.gene_ptr[g + 1])
+        if b - a >= 2:
+            batch.attr_idx[a], batch.attr_idx[a + 1] = (1 << 21) + 7 + g, 3
+        elif b - a == 1:
+            batch.attr_idx[a] = (1 << 21) + g
+    wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, A)
+    # (a vocabulary of this size is past the FP32 kernels' shared-memory table: the f64 path takes it)
+    plain = eng.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=5, step=1, pad=True, f64_arith=True)
+    got = eng.marginals_windowed_wire(wire, window=5, step=1, pad=True, f64_arith=True)
+    assert numpy.allclose(got, plain, rtol=0, atol=1e-12)
+    gene_ptr, attr_idx = wire.decode()
+    assert numpy.array_equal(attr_idx, sorted_reference(batch, A))
+    eng.close()
