@@ -116,7 +116,7 @@ struct gcrf_model {
     DeviceBuffer b_unary, b_pool, b_work;  // GCRF_FLAG_F64: exp of the state scores, max-pool (float output), work area
     void *peer_out[gcrf::WindowedArgs::kMaxPeers] = {};  // gcrf_marginals_windowed_peers: valid during that call only
     int32_t n_peer_out = 0, peer_multicast = 0;
-    int64_t slice_gene_base = 0;  // GCRF_FLAG_SLICE
+    int64_t slice_gene_base = 0, slice_ids = 0;  // GCRF_FLAG_SLICE
     DeviceBuffer b_wire;        // gcrf_marginals_windowed_wire: the block as it came over PCIe
     DeviceBuffer b_idx16;       // GCRF_FLAG_IDX_U16, host buffers: the compact ids as they came over PCIe
     DeviceBuffer b_acc;         // GCRF_FLAG_ACCESSIONS, host buffers: the accessions as they came over PCIe
@@ -517,9 +517,11 @@ int launch_windowed_path(gcrf_model *m, gcrf::WindowedArgs &args, bool prof) {
     return GCRF_OK;
 }
 
-// Host-buffer batches large enough to be PCIe-bound are cut into contig-aligned slices: while slice k's marginals
-// travel back to the host (copy_stream), slice k+1's CSR arrays are already on their way in (stream).  Contigs are
-// independent, so every slice is a plain kernel launch over its own contigs (CsrDev::gene_base).
+// Host-buffer batches large enough to be PCIe-bound are cut into contig-aligned slices and pipelined over three
+// streams: while slice k runs through the kernel (stream), slice k+1's CSR arrays are on their way in (in_stream) and
+// slice k-1's marginals travel back to the host (copy_stream).  Contigs are independent, so every slice is a plain
+// kernel launch over its own contigs (CsrDev::gene_base).  The slices shrink 8:4:2:1 — what the pipeline adds to the
+// copy in, the long pole, is the last slice's kernel and copy back.
 int windowed_sliced(gcrf_model *m, gcrf::WindowedArgs args, const int32_t *contig_ptr, const void *gene_ptr,
                     const int32_t *attr_idx, void *out, int slices) {
     const gcrf::CsrDev whole = args.csr;
@@ -534,7 +536,7 @@ int windowed_sliced(gcrf_model *m, gcrf::WindowedArgs args, const int32_t *conti
     int64_t cut[gcrf_model::kMaxSlices + 1];
     cut[0] = 0;
     for (int k = 1; k < slices; ++k) {
-        const double want = total * k / slices;
+        const double want = total * (1.0 - (double)((1 << (slices - k)) - 1) / (double)((1 << slices) - 1));
         int64_t lo = cut[k - 1], hi = whole.C;
         while (lo < hi) {
             const int64_t mid = (lo + hi) / 2;
@@ -546,23 +548,30 @@ int windowed_sliced(gcrf_model *m, gcrf::WindowedArgs args, const int32_t *conti
     char *d_contig = static_cast<char *>(m->b_contig.ptr), *d_gene = static_cast<char *>(m->b_gene.ptr);
     char *d_attr = static_cast<char *>(m->b_attr.ptr), *d_out = static_cast<char *>(m->b_out.ptr);
     int used = 0;
+    cudaStream_t in = m->in_stream;
+    GCRF_CUDA(cudaEventRecord(m->ev_slice[0], m->stream));  // work queued on the caller's stream stays ahead of the copies
+    GCRF_CUDA(cudaStreamWaitEvent(in, m->ev_slice[0], 0));
+    // the small arrays go first, whole: one copy each instead of one per slice
+    GCRF_CUDA(cudaMemcpyAsync(d_contig, contig_ptr, (size_t)(whole.C + 1) * 4, cudaMemcpyHostToDevice, in));
     for (int k = 0; k < slices; ++k) {
         const int64_t c0 = cut[k], c1 = cut[k + 1];
         if (c1 <= c0) continue;
         const int64_t g0 = contig_ptr[c0], g1 = contig_ptr[c1];
         const int64_t p0 = row(g0), p1 = row(g1);
         // every array lands where the whole batch would have put it, so all indices stay valid as they are
-        GCRF_CUDA(cudaMemcpyAsync(d_contig + (size_t)c0 * 4, contig_ptr + c0, (size_t)(c1 - c0 + 1) * 4, cudaMemcpyHostToDevice, m->stream));
         GCRF_CUDA(cudaMemcpyAsync(d_gene + (size_t)g0 * psz, static_cast<const char *>(gene_ptr) + (size_t)g0 * psz,
-                                  (size_t)(g1 - g0 + 1) * psz, cudaMemcpyHostToDevice, m->stream));
+                                  (size_t)(g1 - g0 + 1) * psz, cudaMemcpyHostToDevice, in));
         if (p1 > p0)
-            GCRF_CUDA(cudaMemcpyAsync(d_attr + (size_t)p0 * 4, attr_idx + p0, (size_t)(p1 - p0) * 4, cudaMemcpyHostToDevice, m->stream));
+            GCRF_CUDA(cudaMemcpyAsync(d_attr + (size_t)p0 * 4, attr_idx + p0, (size_t)(p1 - p0) * 4, cudaMemcpyHostToDevice, in));
+        GCRF_CUDA(cudaEventRecord(m->ev_in[used], in));
+        GCRF_CUDA(cudaStreamWaitEvent(m->stream, m->ev_in[used], 0));
         args.csr = whole;
         args.csr.contig_ptr = reinterpret_cast<const int32_t *>(d_contig) + c0;
         args.csr.gene_ptr32 = ptr64 ? nullptr : reinterpret_cast<const int32_t *>(d_gene) + g0;
         args.csr.gene_ptr64 = ptr64 ? reinterpret_cast<const int64_t *>(d_gene) + g0 : nullptr;
         args.csr.C = c1 - c0;
         args.csr.G = g1 - g0;
+        args.csr.slice_ids = p1 - p0;  // the slice's own density picks the tile size
         args.csr.gene_base = g0;
         args.out = d_out + (size_t)g0 * osz;
         const int rc = launch_windowed_path(m, args, false);
@@ -573,6 +582,7 @@ int windowed_sliced(gcrf_model *m, gcrf::WindowedArgs args, const int32_t *conti
                                   cudaMemcpyDeviceToHost, m->copy_stream));
         ++used;
     }
+    GCRF_CUDA(cudaStreamSynchronize(m->in_stream));
     GCRF_CUDA(cudaStreamSynchronize(m->copy_stream));
     GCRF_CUDA(cudaStreamSynchronize(m->stream));
     return GCRF_OK;
@@ -589,6 +599,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     if (!(flags & GCRF_FLAG_KEEP_TIMING)) m->ev_open = false;
     const bool has_peers = (flags & GCRF_FLAG_HAS_PEERS) != 0, no_local_out = (flags & GCRF_FLAG_NO_LOCAL_OUT) != 0;
     const int64_t gene_base = (flags & GCRF_FLAG_SLICE) ? m->slice_gene_base : 0;
+    const int64_t slice_ids = (flags & GCRF_FLAG_SLICE) ? m->slice_ids : 0;
     flags &= ~(uint32_t)(GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_HAS_PEERS | GCRF_FLAG_NO_LOCAL_OUT | GCRF_FLAG_SLICE);
     // gecco/_meta.py:127-130
     if (window <= 0) return fail(GCRF_EINVAL, "Window size must be strictly positive");
@@ -602,10 +613,9 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     if (!(flags & (GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_IDX_U16 | GCRF_FLAG_ACCESSIONS | GCRF_FLAG_F64)) && !m->timing && !prof && C >= 2) {
         const double bytes = 4.0 * (double)nnz + 12.0 * (double)G;
         const char *env = getenv("GCRF_HOST_SLICES");  // tuning / A-B: 1 turns the overlap off
-        // Off unless asked for: on the PCIe Gen5 hosts measured (config 2, 207 MB in / 16 MB out) the D2H overlap
-        // bought < 1 % and every slice costs ~25 us of launch/copy latency (profiles/r1_e2e_slices.txt).
-        (void)bytes;
-        slices = env ? atoi(env) : 1;
+        // (round 1 measured "no gain" from slicing — with the copies in queued behind the kernels on one stream;
+        // numbers of the three-stream pipeline: profiles/r2_e2e_wire_slices.txt)
+        slices = env ? atoi(env) : bytes >= 24e6 ? 4 : bytes >= 8e6 ? 2 : 1;
         if (slices > gcrf_model::kMaxSlices) slices = gcrf_model::kMaxSlices;
         if (slices > C) slices = (int)C;
         if (slices < 1) slices = 1;
@@ -650,6 +660,7 @@ int gcrf_marginals_windowed(gcrf_model *m, const int32_t *contig_ptr, const void
     args.model = m->dev;
     args.csr = b.csr;
     args.csr.gene_base = gene_base;
+    args.csr.slice_ids = slice_ids;
     args.out = no_local_out ? nullptr : b.d_out;
     args.out_f32 = (flags & GCRF_FLAG_OUT_F32) ? 1 : 0;
     args.window = window;
@@ -814,8 +825,9 @@ int gcrf_marginals_windowed_wire(gcrf_model *m, const gcrf_wire *w, int32_t wind
         trace.mark(m->stream, "decoded", k);
         // the decoded slice is a device-pointer batch of the regular entry point; its result lands in the library's buffer
         m->slice_gene_base = g0;
+        m->slice_ids = p1 - p0;  // the slice's own density picks the tile size
         const int rc = gcrf_marginals_windowed(m, reinterpret_cast<const int32_t *>(d) + c0, static_cast<int32_t *>(m->b_gene.ptr) + g0,
-                                               m->b_attr.ptr, c1 - c0, g1 - g0, p1 - p0 /* the slice's own density picks the tile size */,
+                                               m->b_attr.ptr, c1 - c0, g1 - g0, nnz,
                                                window, step, pad, static_cast<char *>(m->b_out.ptr) + (size_t)g0 * osz,
                                                flags | GCRF_FLAG_DEVICE_PTRS | GCRF_FLAG_KEEP_TIMING | GCRF_FLAG_SLICE);
         if (rc != GCRF_OK) return rc;

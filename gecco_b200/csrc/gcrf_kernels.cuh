@@ -36,6 +36,9 @@ struct CsrDev {
     // contig / gene, but the VALUES of contig_ptr still count genes from the start of the whole batch:
     // gene_base is subtracted from them.  gene_ptr values keep indexing the whole attr_idx array.
     int64_t gene_base;
+    // ... and slice_ids, when positive, the attribute ids of the slice itself (nnz stays the length of the whole
+    // attr_idx array, the bound of what may be read): the density the streaming kernel sizes its tiles by
+    int64_t slice_ids;
 };
 
 struct WindowedArgs {

@@ -699,7 +699,7 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
     int device = 0;
     cudaGetDevice(&device);
     const bool p64 = args.csr.gene_ptr64 != nullptr;
-    const double density = args.csr.G > 0 ? (double)args.csr.nnz / (double)args.csr.G : 0.0;
+    const double density = args.csr.G > 0 ? (double)(args.csr.slice_ids > 0 ? args.csr.slice_ids : args.csr.nnz) / (double)args.csr.G : 0.0;
     int slots = 2 * kNT;
     switch (args.window) {
 #define X(W) case W: slots = slots_for_density<W>(density); break;

@@ -70,11 +70,13 @@ def test_wire_call_equals_the_plain_call(engine, weights, make, slices, monkeypa
     # the block is cut into contig-aligned slices when it is encoded (the call overlaps their copies): any cut, same result
     monkeypatch.setenv("GCRF_WIRE_SLICES", slices)
     wire = WireBatch(batch.contig_ptr, batch.gene_ptr, shuffled, A)
-    for window, step, pad in ((20, 1, True), (5, 2, False)):
+    for window, step, pad in ((20, 1, True), (5, 2, False), (7, 1, True)):
         plain = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, shuffled, window=window, step=step, pad=pad)
         got = engine.marginals_windowed_wire(wire, window=window, step=step, pad=pad)
-        if make == "long_rows":  # rows past the fixed-point guard take the float path: same value up to summation order
-            assert numpy.allclose(got, plain, rtol=0, atol=1e-6, equal_nan=True)
+        # rows past the fixed-point guard take the float path, and so does every row of the first-generation kernel
+        # (window 7 has no streaming instantiation): same value up to summation order
+        if make == "long_rows" or window == 7:
+            assert numpy.allclose(got, plain, rtol=0, atol=5e-6 if window == 7 else 1e-6, equal_nan=True)
         else:
             assert numpy.array_equal(got, plain, equal_nan=True)
         got32 = engine.marginals_windowed_wire(wire, window=window, step=step, pad=pad, f32=True)
