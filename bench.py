@@ -438,13 +438,13 @@ def run_ours(args) -> None:
         def csr_bytes(ids_pin):
             return pins[0].array.nbytes + pins[1].array.nbytes + ids_pin.array.nbytes
 
-        # headline: the compact wire format (gcrf_wire_encode: sorted ids as LEB128 deltas, one-byte row lengths, one
+        # headline: the compact wire format (gcrf_wire_encode: sorted ids as Rice-coded deltas, one-byte row lengths, one
         # page-locked block — what the packers hand to a bulk call), float64 marginals back
         from gecco_b200._lib import WireBatch
 
         wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, len(weights.attrs))
         e2e = e2e_leg(lambda: engine.marginals_windowed_wire(wire, window=WINDOW, step=STEP, pad=PAD, out=pout.array), wire.nbytes, pout)
-        e2e["layout"] = "gcrf_wire block (int32 contig_ptr, uint8 ids/bytes per gene, LEB128 delta stream of the sorted ids), float64 marginals"
+        e2e["layout"] = "gcrf_wire block (int32 contig_ptr, uint8 ids/bytes per gene, Rice-coded deltas of the sorted ids; copy in / kernels / copy back pipelined over 4 slices), float64 marginals"
         e2e["bit_identical_to_device_path"] = bool(numpy.array_equal(pout.array, out_f32_arith))
         e2e_u16 = e2e_leg(csr_call(pins[3], pout, False), csr_bytes(pins[3]), pout)
         e2e_u16["layout"] = "int32 row pointers, uint16 attribute ids, float64 marginals"

@@ -239,8 +239,8 @@ class PinnedArray:
 
 class WireBatch:
     """A CSR batch in the compact wire format (``gcrf_wire_encode``): one page-locked block holding ``contig_ptr``, per-gene
-    id / byte counts and the genes' sorted attribute ids as LEB128 deltas — what a host-buffer call has to move over
-    PCIe, at ~1.3 bytes per id instead of 4.  Encoding is host code (no GPU needed)."""
+    id / byte counts and the genes' sorted attribute ids as Rice-coded deltas — what a host-buffer call has to move over
+    PCIe, at ~1.06 bytes per id instead of 4.  Encoding is host code (no GPU needed)."""
 
     def __init__(self, contig_ptr, gene_ptr, attr_idx, num_attrs: int):
         self._lib = load_library()

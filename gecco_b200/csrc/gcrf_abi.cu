@@ -817,7 +817,7 @@ int gcrf_marginals_windowed_wire(gcrf_model *m, const gcrf_wire *w, int32_t wind
         timed_before = m->timing;
         trace.mark(m->stream, "ready", k);
         cudaError_t derr = gcrf::launch_wire_decode(d + off, d + off + rel_bytes, lw, reinterpret_cast<const uint8_t *>(d + off + rel_stream),
-                                                    g1 - g0, p0, gcrf::wire_short_deltas(w),
+                                                    g1 - g0, p0, gcrf::wire_rice_k(w),
                                                     reinterpret_cast<const int64_t *>(d + gcrf::wire_off_sums(w)) + 2 * chunk0,
                                                     static_cast<int32_t *>(m->b_gene.ptr) + g0, static_cast<int32_t *>(m->b_attr.ptr),
                                                     m->stream, &m->launches);

@@ -125,13 +125,13 @@ cudaError_t launch_widen_u16(const uint16_t *in, int32_t *out, int64_t n, int nu
 
 // Compact wire format (gcrf_wire.cu): rebuild gene_ptr[G+1] / attr_idx[nnz] of one slice from its length arrays and its
 // stretch of the delta-coded id stream.  `sums` = the encoder's chunk sums of the slice (device copy), id_base = attribute
-// ids in front of the slice; gene_ptr (the slice's first entry) receives absolute offsets into attr_idx; short_deltas:
-// every delta is below 2^21, i.e. at most three bytes.  One launch.
+// ids in front of the slice; gene_ptr (the slice's first entry) receives absolute offsets into attr_idx; rice_k = the
+// batch's code parameter.  One launch.
 int64_t wire_chunks(int64_t G);
 cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
-                               int64_t id_base, bool short_deltas, const int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx,
+                               int64_t id_base, int32_t rice_k, const int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx,
                                cudaStream_t stream_, int64_t *launches);
-bool wire_short_deltas(const gcrf_wire *w);
+int32_t wire_rice_k(const gcrf_wire *w);
 int wire_slices(const gcrf_wire *w);
 void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte);  // k in [0, slices]
 int64_t wire_stream_bytes(const gcrf_wire *w);

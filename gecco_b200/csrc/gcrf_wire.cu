@@ -7,14 +7,23 @@
 //     len_ids[G]        ids of gene g            uint8, or uint16 when a gene has more than 255 of them
 //     len_bytes[G]      bytes of gene g's stream (same width)
 //     stream[]          per gene: its attribute ids SORTED ascending, unknown ids (outside [0, A)) mapped to A, as
-//                       deltas (first id absolute) in LEB128 — 7 value bits per byte, high bit = "more follows"
-// in ONE page-locked block, i.e. one host-to-device copy.  Sorting is free for the result: a gene's features are a set
-// (gecco/crf/features.py:32) and the device forms row sums in exact integer arithmetic, so the order of a row does not
-// matter (rows of >= ModelDev::fx_nsafe ids, which take the float path, may differ in the last bit).  For config 2
-// (Poisson(25) ids per gene out of 2,659): 1.3 bytes per id + 2 per gene instead of 4 + 4.
+//                       deltas (first id absolute) in a Rice code, padded to a whole byte per gene
+// in ONE page-locked block (one section per slice, see struct gcrf_wire).  Sorting is free for the result: a gene's
+// features are a set (gecco/crf/features.py:32) and the device forms row sums in exact integer arithmetic, so the
+// order of a row does not matter (rows of >= ModelDev::fx_nsafe ids, which take the float path, may differ in the last
+// bit).
 //
-// On the device three small kernels rebuild gene_ptr and attr_idx (block sums of the two length arrays, a one-block
-// scan of those, scan-within-block + decode), then the marginal kernels run unchanged.
+// The code of one delta v, bits written LSB first, k chosen per batch from the mean delta (k ~ log2(mean ln 2)):
+//     q = v >> k < 8:   q ones, a zero, the k low bits of v             (q + 1 + k bits)
+//     otherwise:        eight ones, v in 24 bits                        (32 bits; hence A < 2^24)
+// Gaps between sorted uniform ids are geometric, for which this is within a few percent of the entropy: config 2
+// (Poisson(25) ids per gene out of 2,659, k = 6) costs 1.03 bytes per id + 2.5 per gene instead of 4 + 4 (LEB128
+// deltas, this format's first version: 1.30 per id).  A code never exceeds 32 bits, so a decoder keeps a 64-bit window
+// and refills it with aligned 32-bit words.
+//
+// On the device ONE kernel rebuilds gene_ptr and attr_idx (the encoder wrote the sums in front of every block of
+// genes; scan within the block, then one thread per gene decoding in shared memory), then the marginal kernels run
+// unchanged.
 #include "../../include/gecco_crf_b200.h"
 #include "gcrf_kernels.cuh"
 
@@ -29,6 +38,7 @@
 struct gcrf_wire {
     int64_t C = 0, G = 0, nnz = 0, stream_bytes = 0;
     int32_t A = 0;
+    int32_t rice_k = 0;     // parameter of the delta code (header comment)
     int32_t len_width = 1;  // bytes per entry of len_ids / len_bytes: 1 or 2 (negative: the block came from malloc)
     // One page-locked block, every part 16-byte aligned:
     //   [contig_ptr int32[C+1] | chunk sums int64[2 * chunks] | section of slice 0 | section of slice 1 | ...]
@@ -53,75 +63,92 @@ constexpr int kWireThreads = 256, kWirePerThread = 2, kWireChunk = kWireThreads 
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// LEB128 of one non-negative value
-inline void put_varint(std::vector<uint8_t> &out, uint32_t v) {
-    while (v >= 128) {
-        out.push_back((uint8_t)(v | 128));
-        v >>= 7;
+// the code of the header comment, bits LSB first; a gene ends on a byte boundary (flush)
+struct BitWriter {
+    std::vector<uint8_t> &out;
+    unsigned long long acc = 0;
+    int n = 0;
+    void put(uint32_t v, int bits) {  // bits <= 32
+        acc |= (unsigned long long)v << n;
+        n += bits;
+        while (n >= 8) {
+            out.push_back((uint8_t)(acc & 0xff));
+            acc >>= 8;
+            n -= 8;
+        }
     }
-    out.push_back((uint8_t)v);
-}
+    void put_delta(uint32_t v, int k) {
+        const uint32_t q = v >> k;
+        if (q < 8) {
+            put((1u << q) - 1u, (int)q + 1);
+            if (k > 0) put(v & ((1u << k) - 1u), k);
+        } else {
+            put(0xffu, 8);
+            put(v, 24);
+        }
+    }
+    void flush() {
+        if (n > 0) out.push_back((uint8_t)(acc & 0xff));
+        acc = 0;
+        n = 0;
+    }
+};
 
 // ---- the decoder: offsets of every gene inside its block (scan), gene_ptr, and the ids themselves.  `sums` holds, per
 // block, the ids and stream bytes in front of it (written by the encoder: no scan over the whole batch on the device).
 // The block's stretch of the byte stream is contiguous, and so are the ids it produces: both go through shared
 // memory in rounds (as many genes as fit the two staging areas), so that global memory sees 16-byte loads and
-// coalesced 4-byte stores only; the serial LEB128 walk of one gene per thread runs on shared memory.  (The first
+// coalesced 4-byte stores only; the serial walk of one gene per thread runs on shared memory.  (The first
 // version walked global memory directly: 0.41 ms for BASELINE config 2, five times this one.)
 constexpr int kWireCapIds = 8192;     // ids staged per round
 constexpr int kWireCapBytes = 12288;  // stream bytes staged per round (plus the 16-byte alignment slack)
-constexpr int kWireInSlack = 32;       // 16 for the alignment of the first word, 8 + for the look-ahead of decode_gene_short
+constexpr int kWireInSlack = 32;       // 16 for the alignment of the first word, 11 + for the look-ahead of decode_gene
 constexpr size_t kWireDecodeSmem = (size_t)(2 * (kWireChunk + 1)) * sizeof(int) + (size_t)kWireCapIds * 4 + kWireCapBytes + kWireInSlack + 16;
 
-__device__ __forceinline__ const uint8_t *decode_gene(const uint8_t *src, int n, int32_t *dst) {
-    int32_t prev = 0;
-    for (int i = 0; i < n; ++i) {
-        uint32_t v = 0, byte;
-        int shift = 0;
-        do {
-            byte = *src++;
-            v |= (byte & 127u) << shift;
-            shift += 7;
-        } while (byte & 128u);
-        prev += (int32_t)v;
-        dst[i] = prev;
-    }
-    return src;
-}
-
-// The same walk for deltas below 2^21 (at most three bytes each; the encoder says so per batch), on shared memory:
-// a 64-bit window of the upcoming bytes refilled by aligned 4-byte loads, length and value of a varint from its
-// continuation bits without a loop — a third of the instructions of the byte-by-byte walk, one load per four bytes.
-// Reads up to 11 bytes past the gene's last byte (inside the staging area's slack).
-__device__ __forceinline__ void decode_gene_short(const uint8_t *src, int n, int32_t *dst) {
+// n ids of one gene from its stretch of the stream (any address space; reads aligned 32-bit words, up to 11 bytes past
+// the gene's last byte — the sections and the staging area carry that slack).  Returns the bits consumed.
+__host__ __device__ inline int64_t decode_gene(const uint8_t *src, int n, int k, int32_t *dst) {
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
     const uint32_t *next = reinterpret_cast<const uint32_t *>(src - mis);
     unsigned long long w = ((unsigned long long)next[1] << 32 | next[0]) >> (8 * mis);
-    int avail = 8 - (int)mis;
+    int avail = 64 - 8 * (int)mis;
     next += 2;
+    const uint32_t kmask = (1u << k) - 1u;
     int32_t prev = 0;
+    int64_t bits = 0;
     for (int i = 0; i < n; ++i) {
         const uint32_t x = (uint32_t)w;
-        const bool c0 = (x & 0x80u) != 0, c1 = c0 && (x & 0x8000u) != 0;
-        uint32_t v = x & 0x7fu;
-        if (c0) v |= (x >> 1) & 0x3f80u;
-        if (c1) v |= (x >> 2) & 0x1fc000u;
-        const int len = 1 + (c0 ? 1 : 0) + (c1 ? 1 : 0);
-        w >>= 8 * len;
+        uint32_t v;
+        int len;
+        if ((x & 0xffu) != 0xffu) {
+#ifdef __CUDA_ARCH__
+            const int q = __ffs((int)~x) - 1;  // ones in front of the first zero
+#else
+            const int q = __builtin_ctz(~x);
+#endif
+            len = q + 1 + k;
+            v = ((uint32_t)q << k) | ((uint32_t)(w >> (q + 1)) & kmask);
+        } else {
+            len = 32;
+            v = x >> 8;
+        }
+        w >>= len;
         avail -= len;
-        if (avail < 4) {
-            w |= (unsigned long long)*next++ << (8 * avail);
-            avail += 4;
+        bits += len;
+        if (avail <= 32) {
+            w |= (unsigned long long)*next++ << avail;
+            avail += 32;
         }
         prev += (int32_t)v;
         dst[i] = prev;
     }
+    return bits;
 }
 
-template <typename LenT, bool SHORT>
+template <typename LenT>
 __global__ void __launch_bounds__(kWireThreads)
 wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ len_bytes, const uint8_t *__restrict__ stream,
-                   int64_t G, int64_t id_base, const int64_t *__restrict__ sums, int32_t *__restrict__ gene_ptr,
+                   int64_t G, int64_t id_base, int rice_k, const int64_t *__restrict__ sums, int32_t *__restrict__ gene_ptr,
                    int32_t *__restrict__ attr_idx) {
     extern __shared__ __align__(16) unsigned char sDyn[];
     int32_t *sOut = reinterpret_cast<int32_t *>(sDyn);                    // [kWireCapIds]
@@ -193,7 +220,7 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
         }
         const int e = lo;
         if (e == s) {  // one gene larger than a staging area (thousands of domains): straight from and to global memory
-            if (tid == 0) decode_gene(stream + byte0 + b0, sIds[s + 1] - i0, attr_idx + id0 + i0);
+            if (tid == 0) decode_gene(stream + byte0 + b0, sIds[s + 1] - i0, rice_k, attr_idx + id0 + i0);
             s += 1;
             continue;
         }
@@ -204,10 +231,8 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
         const int n16 = (mis + nbytes + 15) >> 4;
         for (int k = tid; k < n16; k += kWireThreads) reinterpret_cast<uint4 *>(sIn)[k] = __ldg(src16 + k);
         __syncthreads();
-        for (int j = s + tid; j < e; j += kWireThreads) {
-            if constexpr (SHORT) decode_gene_short(sIn + mis + (sBytes[j] - b0), sIds[j + 1] - sIds[j], sOut + (sIds[j] - i0));
-            else decode_gene(sIn + mis + (sBytes[j] - b0), sIds[j + 1] - sIds[j], sOut + (sIds[j] - i0));
-        }
+        for (int j = s + tid; j < e; j += kWireThreads)
+            decode_gene(sIn + mis + (sBytes[j] - b0), sIds[j + 1] - sIds[j], rice_k, sOut + (sIds[j] - i0));
         __syncthreads();
         int32_t *dst = attr_idx + id0 + i0;
         for (int k = tid; k < nids; k += kWireThreads) dst[k] = sOut[k];
@@ -221,24 +246,19 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
 int64_t wire_chunks(int64_t G) { return (G + kWireChunk - 1) / kWireChunk; }
 
 cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32_t len_width, const uint8_t *stream, int64_t G,
-                               int64_t id_base, bool short_deltas, const int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx,
+                               int64_t id_base, int32_t rice_k, const int64_t *sums, int32_t *gene_ptr, int32_t *attr_idx,
                                cudaStream_t cuda_stream, int64_t *launches) {
     if (G <= 0) return cudaSuccess;
     const int64_t nb = wire_chunks(G);
     auto decode = [&](auto kernel, auto *ids, auto *bytes) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWireDecodeSmem);
         if (err != cudaSuccess) return err;
-        kernel<<<(unsigned)nb, kWireThreads, kWireDecodeSmem, cuda_stream>>>(ids, bytes, stream, G, id_base, sums, gene_ptr, attr_idx);
+        kernel<<<(unsigned)nb, kWireThreads, kWireDecodeSmem, cuda_stream>>>(ids, bytes, stream, G, id_base, (int)rice_k, sums, gene_ptr, attr_idx);
         return cudaSuccess;
     };
     cudaError_t err;
-    if (len_width == 1) {
-        auto *ids = static_cast<const uint8_t *>(len_ids), *bytes = static_cast<const uint8_t *>(len_bytes);
-        err = short_deltas ? decode(wire_decode_kernel<uint8_t, true>, ids, bytes) : decode(wire_decode_kernel<uint8_t, false>, ids, bytes);
-    } else {
-        auto *ids = static_cast<const uint16_t *>(len_ids), *bytes = static_cast<const uint16_t *>(len_bytes);
-        err = short_deltas ? decode(wire_decode_kernel<uint16_t, true>, ids, bytes) : decode(wire_decode_kernel<uint16_t, false>, ids, bytes);
-    }
+    if (len_width == 1) err = decode(wire_decode_kernel<uint8_t>, static_cast<const uint8_t *>(len_ids), static_cast<const uint8_t *>(len_bytes));
+    else err = decode(wire_decode_kernel<uint16_t>, static_cast<const uint16_t *>(len_ids), static_cast<const uint16_t *>(len_bytes));
     if (err != cudaSuccess) return err;
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -258,11 +278,11 @@ struct EncodedChunk {
 };
 
 template <typename PtrT>
-void encode_range(const PtrT *gene_ptr, const int32_t *attr_idx, int64_t g0, int64_t g1, int32_t A, EncodedChunk *out) {
+void encode_range(const PtrT *gene_ptr, const int32_t *attr_idx, int64_t g0, int64_t g1, int32_t A, int k, EncodedChunk *out) {
     std::vector<uint32_t> row;
     out->n_ids.reserve((size_t)(g1 - g0));
     out->n_bytes.reserve((size_t)(g1 - g0));
-    out->stream.reserve((size_t)((gene_ptr[g1] - gene_ptr[g0]) * 3 / 2 + 16));
+    out->stream.reserve((size_t)((gene_ptr[g1] - gene_ptr[g0]) * 5 / 4 + (g1 - g0) + 16));
     for (int64_t g = g0; g < g1; ++g) {
         row.clear();
         for (int64_t p = (int64_t)gene_ptr[g]; p < (int64_t)gene_ptr[g + 1]; ++p) {
@@ -271,11 +291,13 @@ void encode_range(const PtrT *gene_ptr, const int32_t *attr_idx, int64_t g0, int
         }
         std::sort(row.begin(), row.end());
         const size_t before = out->stream.size();
+        gcrf::BitWriter bw{out->stream};
         uint32_t prev = 0;
         for (uint32_t a : row) {
-            gcrf::put_varint(out->stream, a - prev);
+            bw.put_delta(a - prev, k);
             prev = a;
         }
+        bw.flush();
         out->n_ids.push_back((uint32_t)row.size());
         out->n_bytes.push_back((uint32_t)(out->stream.size() - before));
     }
@@ -302,6 +324,7 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
     if (G > 0 && (!contig_ptr || !gene_ptr)) return wire_fail(GCRF_EINVAL, "NULL array");
     if (nnz > 0 && !attr_idx) return wire_fail(GCRF_EINVAL, "attr_idx is NULL");
     if (nnz > 0x7fffffff) return wire_fail(GCRF_EUNSUPPORTED, "the wire format rebuilds 32-bit row pointers: nnz must stay below 2^31");
+    if (num_attrs >= (1 << 24)) return wire_fail(GCRF_EUNSUPPORTED, "the wire format codes ids in at most 24 bits: fewer than 2^24 attributes");
     const bool ptr64 = (flags & GCRF_FLAG_PTR64) != 0;
     auto row = [&](int64_t g) -> int64_t {
         return ptr64 ? static_cast<const int64_t *>(gene_ptr)[g] : (int64_t)static_cast<const int32_t *>(gene_ptr)[g];
@@ -314,18 +337,39 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
     if (nthreads == 0) nthreads = 1;
     if (nthreads > 16) nthreads = 16;
     if ((int64_t)nthreads > G / 4096 + 1) nthreads = (unsigned)(G / 4096 + 1);
+    // the Rice parameter from the mean delta = (sum over genes of their largest id) / ids
+    std::vector<double> top_sum(nthreads, 0.0);
+    auto each_range = [&](auto body) {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const int64_t g0 = G * t / nthreads, g1 = G * (t + 1) / nthreads;
+            if (t + 1 == nthreads) body(t, g0, g1);
+            else pool.emplace_back(body, t, g0, g1);
+        }
+        for (auto &th : pool) th.join();
+    };
+    each_range([&](unsigned t, int64_t g0, int64_t g1) {
+        double sum = 0;
+        for (int64_t g = g0; g < g1; ++g) {
+            uint32_t top = 0;
+            for (int64_t p = row(g); p < row(g + 1); ++p) {
+                const uint32_t a = (uint32_t)attr_idx[p];
+                top = std::max(top, a < (uint32_t)num_attrs ? a : (uint32_t)num_attrs);
+            }
+            sum += top;
+        }
+        top_sum[t] = sum;
+    });
+    double mean_delta = 0;
+    for (double v : top_sum) mean_delta += v;
+    mean_delta = nnz > 0 ? mean_delta / (double)nnz : 0.0;
+    int rice_k = 0;
+    while (rice_k < 20 && (double)(1u << (rice_k + 1)) <= mean_delta * 0.6931 * 1.4142) ++rice_k;  // round(log2(mean ln 2))
     std::vector<EncodedChunk> chunks(nthreads);
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < nthreads; ++t) {
-        const int64_t g0 = G * t / nthreads, g1 = G * (t + 1) / nthreads;
-        auto work = [=, &chunks]() {
-            if (ptr64) encode_range(static_cast<const int64_t *>(gene_ptr), attr_idx, g0, g1, num_attrs, &chunks[t]);
-            else encode_range(static_cast<const int32_t *>(gene_ptr), attr_idx, g0, g1, num_attrs, &chunks[t]);
-        };
-        if (t + 1 == nthreads) work();
-        else pool.emplace_back(work);
-    }
-    for (auto &th : pool) th.join();
+    each_range([&](unsigned t, int64_t g0, int64_t g1) {
+        if (ptr64) encode_range(static_cast<const int64_t *>(gene_ptr), attr_idx, g0, g1, num_attrs, rice_k, &chunks[t]);
+        else encode_range(static_cast<const int32_t *>(gene_ptr), attr_idx, g0, g1, num_attrs, rice_k, &chunks[t]);
+    });
 
     uint32_t longest = 0;
     int64_t stream_bytes = 0;
@@ -338,6 +382,7 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
     gcrf_wire *w = new (std::nothrow) gcrf_wire();
     if (!w) return wire_fail(GCRF_ENOMEM, "out of host memory");
     w->C = C; w->G = G; w->nnz = nnz; w->A = num_attrs; w->stream_bytes = stream_bytes;
+    w->rice_k = rice_k;
     const int lw = longest > 0xFF ? 2 : 1;
     w->len_width = lw;
 
@@ -475,20 +520,11 @@ int gcrf_wire_decode_host(const gcrf_wire *w, int32_t *gene_ptr, int32_t *attr_i
             const uint32_t n = lw == 1 ? reinterpret_cast<const uint8_t *>(sec)[g - g0] : reinterpret_cast<const uint16_t *>(sec)[g - g0];
             const uint32_t nb = lw == 1 ? reinterpret_cast<const uint8_t *>(sec_bytes)[g - g0] : reinterpret_cast<const uint16_t *>(sec_bytes)[g - g0];
             gene_ptr[g] = (int32_t)p;
-            const uint8_t *end = src + nb;
-            int32_t prev = 0;
-            for (uint32_t i = 0; i < n; ++i) {
-                uint32_t v = 0, byte;
-                int shift = 0;
-                do {
-                    byte = *src++;
-                    v |= (byte & 127u) << shift;
-                    shift += 7;
-                } while (byte & 128u);
-                prev += (int32_t)v;
-                attr_idx[p++] = prev;
-            }
-            if (src != end) return wire_fail(GCRF_EINVAL, "corrupt wire block");
+            if (p + (int64_t)n > w->nnz) return wire_fail(GCRF_EINVAL, "corrupt wire block");
+            const int64_t bits = gcrf::decode_gene(src, (int)n, w->rice_k, attr_idx + p);
+            p += n;
+            if ((bits + 7) / 8 != (int64_t)nb) return wire_fail(GCRF_EINVAL, "corrupt wire block");
+            src += nb;
         }
     }
     if (w->G > 0) gene_ptr[w->G] = (int32_t)p;
@@ -514,7 +550,7 @@ void wire_section(const gcrf_wire *w, int k, size_t *off, size_t *size, size_t *
 }
 int32_t wire_len_width(const gcrf_wire *w) { return w->len_width < 0 ? -w->len_width : w->len_width; }
 int wire_slices(const gcrf_wire *w) { return w->n_slices; }
-bool wire_short_deltas(const gcrf_wire *w) { return w->A < (1 << 21); }  // deltas are at most A
+int32_t wire_rice_k(const gcrf_wire *w) { return w->rice_k; }
 void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte) {
     *contig = w->s_contig[k];
     *gene = w->s_gene[k];

@@ -229,15 +229,17 @@ int gcrf_segments(gcrf_model *model, const int32_t *contig_ptr, const void *prob
  * the bytes that cross are its cost: 4 per attribute id, 4 per gene (row pointer), 8 per gene (float64 marginal) in the
  * CSR layout above.  gcrf_wire_encode packs the same batch into ONE page-locked block — contig_ptr unchanged, per gene the
  * number of ids and of stream bytes (uint8 each, uint16 when a gene has more than 255), and per gene its ids SORTED
- * ascending, unknown ids mapped to A, as LEB128 deltas: ~1.3 bytes per id for 25 ids out of 2,659 — and
- * gcrf_marginals_windowed_wire copies that block, rebuilds gene_ptr / attr_idx on the device (three small kernels) and
- * runs the regular kernels.  Results equal gcrf_marginals_windowed's on the unsorted batch bit for bit in the default
+ * ascending, unknown ids mapped to A, as Rice-coded deltas (parameter chosen per batch): ~1.06 bytes per id for 25 ids
+ * out of 2,659 — and gcrf_marginals_windowed_wire moves that block in contig-aligned slices (copy in, decode + kernels
+ * and copy back of successive slices overlap on three streams), rebuilds gene_ptr / attr_idx on the device (one kernel
+ * per slice) and runs the regular kernels.  Results equal gcrf_marginals_windowed's on the unsorted batch bit for bit in the default
  * FP32 arithmetic (row sums are exact integer sums; only rows long enough to take the float path, >= ~100 ids for the
  * shipped model, can differ in the last bit).  With GCRF_FLAG_F64 the row sums run in the SORTED order, so the result is
  * within a few ulps of the first-occurrence order of the reference, not bit-identical to it.  Combine with
  * GCRF_FLAG_OUT_F32 to halve the bytes coming back (the FP32 results, un-widened).
  * Replaces nothing in the reference (which never leaves the host); it is the packers' output format for bulk calls.
- * The encoder is host code (no device needed); nnz must stay below 2^31, a gene below 65,536 ids.
+ * The encoder is host code (no device needed); nnz must stay below 2^31, a gene below 65,536 ids and stream bytes,
+ * the vocabulary below 2^24 attributes.
  */
 typedef struct gcrf_wire gcrf_wire;
 const char *gcrf_wire_last_error(void);
