@@ -3,10 +3,10 @@
 r=${1:-r2}
 cd "$(dirname "$0")/.."
 for f in bench_1gpu.json bench_2gpu.json bench_8gpu.json bench_reference_arm.json launches.csv gpu_tests.txt sanitizer.txt \
-         segments_time.txt window_sizes_time.txt density_probe.txt predict_tables_time.txt entry_levels_mibig.txt topo_8gpu.txt; do
+         e2e_probe.txt wire_slices.txt wire_trace.txt segments_time.txt window_sizes_time.txt density_probe.txt predict_tables_time.txt entry_levels_mibig.txt topo_8gpu.txt; do
     [ -s gpurun_out/${r}_$f ] && cp gpurun_out/${r}_$f profiles/${r}_$f
 done
-for k in stream_kernel stream_kernel_sparse exact_window_kernel; do
+for k in stream_kernel stream_kernel_sparse exact_window_kernel wire_decode_kernel; do
     [ -s gpurun_out/${r}_$k.ncu-rep ] && python tools/ncu_summary.py gpurun_out/${r}_$k.ncu-rep > profiles/${r}_ncu_summary_$k.txt
 done
 python - "$r" <<'PY'
