@@ -6,9 +6,10 @@ the genes are reduced to three arrays (contig pointers, probabilities, "has a do
 ``libgecco_crf_b200.so`` (``gcrf_segments``) returns the valid clusters in the reference's order, and only those are
 turned back into ``Cluster`` objects.  ``Gene`` / ``Cluster`` are duck-typed like in :mod:`gecco_b200.crf`.
 
-Only ``criterion="gecco"`` — the default of the class and of ``gecco run`` — runs on the device; the
-``"antismash"`` criterion needs the domain *names* of every cluster (``:157-163``) and is delegated to the reference
-class when GECCO is importable.
+Both criteria take their segments from the device.  ``criterion="gecco"`` — the default of the class and of
+``gecco run`` — is validated there too (annotated genes, distance to the contig edge).  ``criterion="antismash"``
+(``:157-163``) needs the domain *names* of a cluster: the device returns every (trimmed) segment, and the three tests
+— mean probability, distinct biosynthetic Pfams, number of genes — run here over the few segments that exist.
 """
 
 from __future__ import annotations
@@ -18,7 +19,19 @@ from typing import Any, Iterator, List, Optional
 
 import numpy
 
-__all__ = ["ClusterRefiner"]
+__all__ = ["ClusterRefiner", "BIO_PFAMS"]
+
+
+def _load_bio_pfams() -> frozenset:
+    """The Pfam accessions antiSMASH counts as biosynthetic, as GECCO ships them (``gecco/refine.py:20-58``; data,
+    extracted by ``tools/make_golden.py antismash``)."""
+    import pathlib
+
+    path = pathlib.Path(__file__).resolve().parent / "data" / "bio_pfams.txt"
+    return frozenset(line.strip() for line in path.read_text().splitlines() if line.strip())
+
+
+BIO_PFAMS = _load_bio_pfams()
 
 
 class _Cluster:
@@ -69,18 +82,9 @@ class ClusterRefiner:
 
     def iter_clusters(self, genes: List[Any]) -> Iterator[Any]:
         """Find all clusters in a table of CRF predictions (``gecco/refine.py:120-137``)."""
-        if self.criterion == "antismash":
-            try:
-                import gecco.refine  # type: ignore
-            except ImportError as err:
-                raise NotImplementedError("criterion 'antismash' is delegated to gecco.refine, which is not installed") from err
-            yield from gecco.refine.ClusterRefiner(
-                threshold=self.threshold, criterion=self.criterion, n_cds=self.n_cds, n_biopfams=self.n_biopfams,
-                average_threshold=self.average_threshold, edge_distance=self.edge_distance, trim=self.trim,
-            ).iter_clusters(genes)
-            return
-        if self.criterion != "gecco":
+        if self.criterion not in ("gecco", "antismash"):
             raise ValueError(f"Unknown cluster filtering criterion: {self.criterion}")  # :164-165
+        antismash = self.criterion == "antismash"
 
         # :193-195 — stable sort by contig id, then by coordinates inside each contig
         ordered = sorted(genes, key=operator.attrgetter("source.id"))
@@ -100,10 +104,22 @@ class ClusterRefiner:
         prob = numpy.array([numpy.nan if (p := g.average_probability) is None else p for g in table], dtype=numpy.float64)
         annotated = numpy.array([1 if g.protein.domains else 0 for g in table], dtype=numpy.uint8)
 
+        # "antismash": every segment comes back (no annotated-gene or edge test on the device), validated below
         seg = self._get_engine().segments(numpy.asarray(contig_ptr, dtype=numpy.int32), prob, annotated,
-                                          threshold=self.threshold, n_cds=self.n_cds, edge_distance=self.edge_distance,
-                                          trim=self.trim)
+                                          threshold=self.threshold, n_cds=0 if antismash else self.n_cds,
+                                          edge_distance=0 if antismash else self.edge_distance, trim=self.trim)
         Cluster = _cluster_type()
         for c, b, e, k in zip(seg.contig.tolist(), seg.begin.tolist(), seg.end.tolist(), seg.ordinal.tolist()):
+            members = table[b:e]
+            if antismash:
+                # :157-163 — a segment trimmed down to nothing has no mean probability and fails the first test
+                if not members:
+                    continue
+                domains = {d.name for gene in members for d in gene.protein.domains}
+                p_crit = numpy.mean([gene.average_probability for gene in members]) >= self.average_threshold
+                bio_crit = len(domains & BIO_PFAMS) >= self.n_biopfams
+                cds_crit = len(members) >= self.n_cds
+                if not (p_crit and bio_crit and cds_crit):
+                    continue
             seq_id = table[contig_ptr[c]].source.id
-            yield Cluster(f"{seq_id}_cluster_{k}", table[b:e])  # :199-200 names clusters before validation
+            yield Cluster(f"{seq_id}_cluster_{k}", members)  # :199-200 names clusters before validation

@@ -168,3 +168,46 @@ def test_dropin_refiner_host_side(refine_cases):
 @pytest.mark.gpu
 def test_dropin_refiner_on_device(refine_cases):
     check_dropin({}, refine_cases)
+
+
+# ------------------------------------------------------------------------------ criterion "antismash" (:157-163)
+@pytest.fixture(scope="module")
+def antismash_cases():
+    return json.loads((GOLDEN / "refine_antismash_cases.json").read_text())["cases"]
+
+
+def genes_of_antismash_case(case, seed=5):
+    import random
+
+    from fake_model import Domain, Gene, Protein, Source
+
+    genes = []
+    for contig in case["contigs"]:
+        src = Source(contig["id"])
+        for i, g in enumerate(contig["genes"]):
+            doms = [Domain(name, 1 + 10 * j, 9 + 10 * j) for j, name in enumerate(g["domains"])]
+            genes.append(Gene(src, 100 + 1000 * i, 900 + 1000 * i, 1, Protein(g["id"], None, doms), g["p"]))
+    random.Random(seed).shuffle(genes)
+    return genes
+
+
+def check_antismash(refiner_of, cases):
+    """Clusters of the reference's own class with ``criterion="antismash"`` (tools/make_golden.py antismash)."""
+    from gecco_b200.refine import BIO_PFAMS, ClusterRefiner
+
+    assert len(BIO_PFAMS) == 130 and "PF00109" in BIO_PFAMS
+    assert sum(len(c["clusters"]) for c in cases) >= 40
+    for case in cases:
+        refiner = ClusterRefiner(criterion="antismash", **case["settings"], **refiner_of)
+        clusters = list(refiner.iter_clusters(genes_of_antismash_case(case)))
+        assert [cl.id for cl in clusters] == [cl["id"] for cl in case["clusters"]], case["settings"]
+        assert [[g.id for g in cl.genes] for cl in clusters] == [cl["genes"] for cl in case["clusters"]]
+
+
+def test_antismash_criterion_host_side(antismash_cases):
+    check_antismash({"engine": OracleSegmentsEngine()}, antismash_cases)
+
+
+@pytest.mark.gpu
+def test_antismash_criterion_on_device(antismash_cases):
+    check_antismash({}, antismash_cases)

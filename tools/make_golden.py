@@ -329,9 +329,64 @@ def make_refine_golden(ref_dir: str = "/root/reference") -> None:
     print(f"refine_cases: {len(cases)} cases, {sum(len(c['clusters']) for c in cases)} clusters")
 
 
+def make_antismash_golden(ref_dir: str = "/root/reference") -> None:
+    """``criterion="antismash"`` of the reference's ``ClusterRefiner`` (``gecco/refine.py:157-163``): the list of Pfam
+    accessions antiSMASH counts as biosynthetic (data of the reference, ``:20-58``) -> ``gecco_b200/data/bio_pfams.txt``,
+    and the class itself on random tables with named domains -> ``tests/golden/refine_antismash_cases.json``."""
+    ref = pathlib.Path(ref_dir)
+    crfmod, modelmod, SeqRecord = import_reference_crf(ref)
+    import gecco.refine
+
+    bio = sorted(gecco.refine.BIO_PFAMS)
+    (ROOT / "gecco_b200" / "data" / "bio_pfams.txt").write_text("\n".join(bio) + "\n")
+    rng = numpy.random.default_rng(47)
+    other = [f"PF{n:05d}" for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12)]
+    assert not set(other) & set(bio)
+    settings = [dict(threshold=0.8, n_cds=5, n_biopfams=5, average_threshold=0.6, trim=True),   # the class defaults
+                dict(threshold=0.8, n_cds=3, n_biopfams=2, average_threshold=0.9, trim=True),
+                dict(threshold=0.5, n_cds=1, n_biopfams=1, average_threshold=0.6, trim=False),
+                dict(threshold=0.6, n_cds=4, n_biopfams=3, average_threshold=0.85, trim=True),
+                dict(threshold=0.3, n_cds=2, n_biopfams=0, average_threshold=0.0, trim=False)]
+    cases = []
+    for k in range(20):
+        kw = settings[k % len(settings)]
+        contigs, genes = [], []
+        for c in range(int(rng.integers(1, 5))):
+            cid = f"ctg{int(rng.integers(0, 1000)):03d}_{c}"
+            src = SeqRecord(id=cid)
+            n = int(rng.integers(1, 70))
+            state = rng.random() < 0.4
+            cg = []
+            for i in range(n):
+                if rng.random() < 0.1:
+                    state = not state
+                p = float(numpy.clip(rng.normal(0.9 if state else 0.2, 0.12), 0, 1))
+                names = []
+                for _ in range(int(rng.poisson(1.2))):
+                    pool = bio[:12] if rng.random() < 0.5 else other
+                    names.append(pool[int(rng.integers(0, len(pool)))])
+                doms = [modelmod.Domain(a, 1 + 10 * j, 9 + 10 * j, "Pfam", 1e-20, 1e-20) for j, a in enumerate(names)]
+                gene = modelmod.Gene(src, 100 + 1000 * i, 900 + 1000 * i, modelmod.Strand.Coding,
+                                     modelmod.Protein(f"{cid}_{i + 1}", None, doms), _probability=p)
+                genes.append(gene)
+                cg.append({"id": gene.id, "p": p, "domains": names})
+            contigs.append({"id": cid, "genes": cg})
+        shuffled = list(genes)
+        rng.shuffle(shuffled)
+        refiner = gecco.refine.ClusterRefiner(criterion="antismash", **kw)
+        clusters = [{"id": cl.id, "genes": [g.id for g in cl.genes]} for cl in refiner.iter_clusters(shuffled)]
+        cases.append({"settings": kw, "contigs": contigs, "clusters": clusters})
+    out = ROOT / "tests" / "golden" / "refine_antismash_cases.json"
+    out.write_text(json.dumps({"cases": cases}, indent=0) + "\n")
+    print(f"refine_antismash_cases: {len(cases)} cases, {sum(len(c['clusters']) for c in cases)} clusters, {len(bio)} biosynthetic Pfams")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "refine":
         make_refine_golden(*sys.argv[2:])
+    elif len(sys.argv) > 1 and sys.argv[1] == "antismash":
+        make_antismash_golden(*sys.argv[2:])
     else:
         main(*sys.argv[1:])
         make_refine_golden(*sys.argv[1:])
+        make_antismash_golden(*sys.argv[1:])
