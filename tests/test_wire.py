@@ -170,3 +170,31 @@ def test_wire_call_with_a_vocabulary_past_three_byte_deltas(weights):
     gene_ptr, attr_idx = wire.decode()
     assert numpy.array_equal(attr_idx, sorted_reference(batch, A))
     eng.close()
+
+
+@pytest.mark.gpu
+def test_wire_call_fuzz(engine, weights, monkeypatch):
+    """Random shapes: densities from almost empty to rows past 255 ids (the uint8 / uint16 switch sits inside the
+    range), one to hundreds of contigs, every slice count — the FP32 marginals of the wire call equal the plain call's."""
+    A = len(weights.attrs)
+    rng = numpy.random.default_rng(23)
+    for trial in range(36):
+        contigs = int(rng.integers(1, 400))
+        density = float(rng.choice([0.2, 1.4, 8.0, 25.0, 60.0, 180.0]))
+        lens = numpy.maximum(1, rng.poisson(float(rng.choice([1.0, 6.0, 40.0])), size=contigs))
+        if density >= 60:
+            lens = lens[:40]
+        batch = synth.make_batch(rng, lens, density, A, float(rng.choice([0.0, 0.05, 0.5])))
+        monkeypatch.setenv("GCRF_WIRE_SLICES", str(int(rng.integers(1, 9))))
+        wire = WireBatch(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, A)
+        gene_ptr, attr_idx = wire.decode()
+        assert numpy.array_equal(gene_ptr, batch.gene_ptr) and numpy.array_equal(attr_idx, sorted_reference(batch, A))
+        window = int(rng.choice([5, 20]))
+        pad = bool(rng.integers(0, 2))
+        plain = engine.marginals_windowed(batch.contig_ptr, batch.gene_ptr, batch.attr_idx, window=window, step=1, pad=pad)
+        got = engine.marginals_windowed_wire(wire, window=window, step=1, pad=pad)
+        if density >= 60:  # rows past the fixed-point guard: float row sums, order-dependent in the last bit
+            assert numpy.allclose(got, plain, rtol=0, atol=1e-6, equal_nan=True), (trial, contigs, density)
+        else:
+            assert numpy.array_equal(got, plain, equal_nan=True), (trial, contigs, density)
+        wire.close()
