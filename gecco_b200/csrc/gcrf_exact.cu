@@ -66,9 +66,13 @@ exact_unary_kernel(const ExactArgs args, double *__restrict__ pool) {
             }
         }
         reinterpret_cast<double2 *>(args.unary)[g] = make_double2(expdd::exp_cr(s0), expdd::exp_cr(s1));
-        const int64_t c = find_contig(csr.contig_ptr, csr.C, g + csr.gene_base);
-        const int n = __ldg(csr.contig_ptr + c + 1) - __ldg(csr.contig_ptr + c);
-        pool[g] = (n < args.window && !args.pad) ? quiet_nan() : 0.0;
+        double init = 0.0;
+        if (!args.pad) {  // genes of a contig shorter than the window keep "no probability" (:228-234)
+            const int64_t c = find_contig(csr.contig_ptr, csr.C, g + csr.gene_base);
+            const int n = __ldg(csr.contig_ptr + c + 1) - __ldg(csr.contig_ptr + c);
+            if (n < args.window) init = quiet_nan();
+        }
+        pool[g] = init;
     }
 }
 

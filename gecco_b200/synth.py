@@ -62,15 +62,22 @@ def algorithmic_bytes(C: int, G: int, nnz: int, out_itemsize: int = 8) -> int:
 
 
 def make_batch(rng: numpy.random.Generator, genes_per_contig: numpy.ndarray, mean_domains: float, num_attrs: int,
-               unknown_fraction: float = 0.0, name: str = "") -> CsrBatch:
-    """k_g ~ Poisson(mean_domains) ids uniform over the vocabulary, made unique and sorted per gene."""
+               unknown_fraction: float = 0.0, name: str = "", zipf: float = 0.0) -> CsrBatch:
+    """k_g ~ Poisson(mean_domains) ids uniform over the vocabulary (``zipf`` > 0: attribute of rank r with probability
+    ~ r^-zipf, ranks assigned by a random permutation — the frequency skew of real Pfam annotations),
+    made unique and sorted per gene."""
     genes_per_contig = numpy.asarray(genes_per_contig, dtype=numpy.int64)
     contig_ptr = numpy.zeros(len(genes_per_contig) + 1, dtype=numpy.int64)
     numpy.cumsum(genes_per_contig, out=contig_ptr[1:])
     G = int(contig_ptr[-1])
     k = rng.poisson(mean_domains, size=G).astype(numpy.int64)
     raw = int(k.sum())
-    ids = rng.integers(0, num_attrs, size=raw, dtype=numpy.int64)
+    if zipf > 0:
+        cdf = numpy.cumsum(numpy.arange(1, num_attrs + 1, dtype=numpy.float64) ** -zipf)
+        ranks = numpy.searchsorted(cdf, rng.random(raw) * cdf[-1], side="right").clip(0, num_attrs - 1)
+        ids = rng.permutation(num_attrs)[ranks].astype(numpy.int64)
+    else:
+        ids = rng.integers(0, num_attrs, size=raw, dtype=numpy.int64)
     gene_of = numpy.repeat(numpy.arange(G, dtype=numpy.int64), k)
     key = gene_of * (1 << 20) + ids  # vocabularies stay far below 2^20
     key.sort()
@@ -90,11 +97,11 @@ def make_batch(rng: numpy.random.Generator, genes_per_contig: numpy.ndarray, mea
 
 
 def config2(num_attrs: int = 2659, seed: int = 2, contigs: int = 10_000, mean_genes: float = 200.0,
-            mean_domains: float = 25.0, unknown_fraction: float = 0.05) -> CsrBatch:
+            mean_domains: float = 25.0, unknown_fraction: float = 0.05, zipf: float = 0.0) -> CsrBatch:
     """10k contigs x Poisson(200) genes x Poisson(25) domains — the headline 1xB200 workload."""
     rng = numpy.random.default_rng(seed)
     n = numpy.maximum(1, rng.poisson(mean_genes, size=contigs))
-    return make_batch(rng, n, mean_domains, num_attrs, unknown_fraction, name=f"config2(seed={seed})")
+    return make_batch(rng, n, mean_domains, num_attrs, unknown_fraction, name=f"config2(seed={seed})", zipf=zipf)
 
 
 def config3_ecoli_like(num_attrs: int = 2659, seed: int = 3, genes: int = 4300, mean_domains: float = 1.4) -> CsrBatch:
