@@ -90,7 +90,9 @@ def test_reference_order_f64_kernel(sass):
         assert count(body, "DMUL") >= 200 and count(body, "DADD") >= 60
         assert count(body, "MUFU.RCP64H") >= 20, "IEEE divisions (reciprocal seed + Newton steps)"
         assert any("ATOMG" in ins and "MAX" in ins and "64" in ins for ins in body) or any("RED" in ins and "MAX" in ins for ins in body)
-        assert not any("LDL" in ins or "STL" in ins for ins in body)
+        # four blocks per SM = 128 registers: a few doubles of the stored forward half spill (0.41 ms against 0.47 ms
+        # at three blocks of 152 registers), nothing like the whole half
+        assert sum("LDL" in ins or "STL" in ins for ins in body) <= 48
     for body in find(functions, "exact_unary_kernel"):
         assert count(body, "DFMA") >= 20 and count(body, "DADD") >= 10  # the double-double exponential
 
