@@ -415,7 +415,7 @@ def run_ours(args) -> None:
         pout32 = PinnedArray((batch.G,), numpy.float32)
         e2e_steps = max(3, min(args.steps, 10))
 
-        def e2e_leg(one, h2d: int, out_pin):
+        def e2e_leg(one, h2d: int, out_pin, genes=None):
             for _ in range(2):
                 one()
             barrier()
@@ -427,7 +427,7 @@ def run_ours(args) -> None:
             secs = max_over_ranks(mine)
             barrier()
             d2h = int(out_pin.array.nbytes)
-            return {"value": total_genes * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+            return {"value": (total_genes if genes is None else genes) * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * secs / e2e_steps,
                     "this_rank_pcie_gbs": (h2d + d2h) * e2e_steps / mine / 1e9}
 
@@ -457,6 +457,22 @@ def run_ours(args) -> None:
         compact["layout"] = "gcrf_wire block, float32 marginals (the FP32 results un-widened)"
         compact["identical_to_float32_of_device_path"] = bool(numpy.array_equal(pout32.array, out_f32_arith.astype(numpy.float32)))
         wire.close()
+        # the same call on the real annotation density (1.4 domains per gene): what a metagenome table looks like
+        real = None
+        if world == 1:
+            from gecco_b200 import synth as synth_mod
+
+            sparse = synth_mod.config2(len(weights.attrs), seed=2, contigs=args.contigs, mean_domains=1.4, unknown_fraction=0.0)
+            wire_s = WireBatch(sparse.contig_ptr, sparse.gene_ptr, sparse.attr_idx, len(weights.attrs))
+            pout_s = PinnedArray((sparse.G,), numpy.float64)
+            want_s = engine.marginals_windowed(sparse.contig_ptr, sparse.gene_ptr, sparse.attr_idx, window=WINDOW, step=STEP, pad=PAD)
+            real = e2e_leg(lambda: engine.marginals_windowed_wire(wire_s, window=WINDOW, step=STEP, pad=PAD, out=pout_s.array), wire_s.nbytes, pout_s,
+                           genes=float(sparse.G))
+            real["layout"] = "gcrf_wire block, float64 marginals; config 2 at 1.4 domains per gene"
+            real["genes"] = int(sparse.G)
+            real["bit_identical_to_device_path"] = bool(numpy.array_equal(pout_s.array, want_s))
+            wire_s.close()
+            del sparse, want_s, pout_s
         per_rank_gbs = [e2e["this_rank_pcie_gbs"]]
         if world > 1:
             t = torch.tensor([e2e["this_rank_pcie_gbs"]], dtype=torch.float64, device=dev)
@@ -707,6 +723,7 @@ def run_ours(args) -> None:
             "e2e_uint16_ids": e2e_u16,
             "e2e_int32_ids": e2e_i32,
             "e2e_compact": compact,
+            "e2e_real_density": real,
             "f64": f64_line,
             "configs": configs,
             "sharded": sharded,
