@@ -8,7 +8,10 @@
 namespace gcrf {
 namespace {
 
-constexpr int kWalk = 52;  // ids walked per thread and staging round (4 * odd: conflict-free LDS.128)
+#ifndef GCRF_KWALK
+#define GCRF_KWALK 52
+#endif
+constexpr int kWalk = GCRF_KWALK;  // ids walked per thread and staging round (4 * odd: conflict-free LDS.128); -DGCRF_KWALK: A/B builds
 
 __host__ __device__ constexpr int round_up4s(int x) { return (x + 3) & ~3; }
 
@@ -30,8 +33,8 @@ __device__ __forceinline__ float exp_fast(float x) {
 
 // x / kWalk for 0 <= x < 13376 (kWalk = 52): one multiply and one shift
 __device__ __forceinline__ int walk_thread(int x) {
-    static_assert(kWalk == 52, "magic constant is for 52");
-    return (int)(((unsigned)x * 10083u) >> 19);
+    if constexpr (kWalk == 52) return (int)(((unsigned)x * 10083u) >> 19);
+    else return x / kWalk;  // A/B builds
 }
 
 __device__ __forceinline__ int lookup(const int *sTab, int32_t id, uint32_t A) {
