@@ -47,6 +47,11 @@ namespace {
 #define GCRF_STREAM_MINB 4
 #endif
 constexpr int kNT = GCRF_STREAM_NT, kMinB = GCRF_STREAM_MINB;
+// Resident CTAs the register budget is sized for: from W = 25 on the pool ((W + 1) rows) pushes a CTA past a quarter of
+// the SM's shared memory and three fit whatever the registers (two from W = 51 on) — so those windows get three (two)
+// CTAs' worth of registers: 168 (255) instead of 128, no spills up to W = 64.  W = 40 on config 2: 121.5 -> 112.4 us.
+template <int W>
+constexpr int min_blocks() { return W <= 20 ? kMinB : W <= 50 ? (kMinB < 3 ? kMinB : 3) : (kMinB < 2 ? kMinB : 2); }
 constexpr int kStreamSmemCap = 100 * 1024;  // largest dynamic shared memory a streaming CTA may ask for
 constexpr int kFewPerLane = 16;  // ids per lane of the one-warp walk used for tiles with <= 512 staged ids
 
@@ -612,8 +617,8 @@ template <int W> constexpr bool has_dense_variants() {
 template <int W, int SLOTS>
 cudaError_t configure_slots(const WindowedArgs &args, int *per_sm, size_t *bytes, int *tile_out) {
     *tile_out = StreamTiling<W, kNT, SLOTS>::tile_out;
-    return args.csr.gene_ptr64 ? configure_stream<W, kNT, kMinB, int64_t, SLOTS>(args.model.A, per_sm, bytes)
-                               : configure_stream<W, kNT, kMinB, int32_t, SLOTS>(args.model.A, per_sm, bytes);
+    return args.csr.gene_ptr64 ? configure_stream<W, kNT, min_blocks<W>(), int64_t, SLOTS>(args.model.A, per_sm, bytes)
+                               : configure_stream<W, kNT, min_blocks<W>(), int32_t, SLOTS>(args.model.A, per_sm, bytes);
 }
 template <int W>
 cudaError_t configure_window(const WindowedArgs &args, int slots, int *per_sm, size_t *bytes, int *tile_out) {
@@ -627,13 +632,13 @@ cudaError_t configure_window(const WindowedArgs &args, int slots, int *per_sm, s
 template <int W, int SLOTS>
 cudaError_t launch_slots(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, int num_tiles, int tiles_per_cta) {
     return args.csr.gene_ptr64
-               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int64_t, SLOTS>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
-               : cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, kMinB, int32_t, SLOTS>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
+               ? cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, min_blocks<W>(), int64_t, SLOTS>, args, args.csr.gene_ptr64, num_tiles, tiles_per_cta)
+               : cudaLaunchKernelEx(&cfg, stream_kernel<W, kNT, min_blocks<W>(), int32_t, SLOTS>, args, args.csr.gene_ptr32, num_tiles, tiles_per_cta);
 }
 // the peer-store instantiation (full tiles only; the windows that have dense variants have this one too)
 template <int W, typename PtrT>
 cudaError_t launch_peers(const cudaLaunchConfig_t &cfg, const WindowedArgs &args, const PtrT *gene_ptr, int num_tiles, int tiles_per_cta) {
-    auto kernel = stream_kernel<W, kNT, kMinB, PtrT, 2 * kNT, true>;
+    auto kernel = stream_kernel<W, kNT, min_blocks<W>(), PtrT, 2 * kNT, true>;
     static thread_local int configured_device = -1;
     int device = 0;
     cudaGetDevice(&device);

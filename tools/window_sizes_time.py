@@ -9,7 +9,7 @@ eng = CRFEngine(w, 0)
 for name, b in (("config2", synth.config2(len(w.attrs))), ("sparse", synth.config2(len(w.attrs), mean_domains=1.4))):
     cp = torch.from_numpy(b.contig_ptr).to(dev); gp = torch.from_numpy(b.gene_ptr).to(dev); ai = torch.from_numpy(b.attr_idx).to(dev)
     out = torch.empty(b.G, dtype=torch.float64, device=dev)
-    for W in (5, 10, 20, 40):
+    for W in (5, 10, 20, 25, 30, 40, 50, 64):
         eng.set_timing(True)
         ts = []
         for it in range(13):
