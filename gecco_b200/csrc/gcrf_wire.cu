@@ -100,8 +100,11 @@ struct BitWriter {
 // memory in rounds (as many genes as fit the two staging areas), so that global memory sees 16-byte loads and
 // coalesced 4-byte stores only; the serial walk of one gene per thread runs on shared memory.  (The first
 // version walked global memory directly: 0.41 ms for BASELINE config 2, five times this one.)
-constexpr int kWireCapIds = 8192;     // ids staged per round
-constexpr int kWireCapBytes = 12288;  // stream bytes staged per round (plus the 16-byte alignment slack)
+#ifndef GCRF_WIRE_CAP_IDS
+#define GCRF_WIRE_CAP_IDS 8192
+#endif
+constexpr int kWireCapIds = GCRF_WIRE_CAP_IDS;            // ids staged per round
+constexpr int kWireCapBytes = GCRF_WIRE_CAP_IDS * 3 / 2;  // stream bytes staged per round (plus the 16-byte alignment slack)
 constexpr int kWireInSlack = 32;       // 16 for the alignment of the first word, 11 + for the look-ahead of decode_gene
 constexpr size_t kWireDecodeSmem = (size_t)(2 * (kWireChunk + 1)) * sizeof(int) + (size_t)kWireCapIds * 4 + kWireCapBytes + kWireInSlack + 16;
 
