@@ -134,7 +134,6 @@ cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32
 int32_t wire_rice_k(const gcrf_wire *w);
 int wire_slices(const gcrf_wire *w);
 void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64_t *id, int64_t *byte);  // k in [0, slices]
-int64_t wire_stream_bytes(const gcrf_wire *w);
 const char *wire_block(const gcrf_wire *w);
 size_t wire_total(const gcrf_wire *w);
 size_t wire_head_bytes(const gcrf_wire *w);

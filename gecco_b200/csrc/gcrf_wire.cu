@@ -168,7 +168,7 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
         sBytes[j] = g < G ? (int)len_bytes[g] : 0;
     }
     __syncthreads();
-    // thread t scans entries [8t, 8t + 8), then the thread totals are scanned across the block
+    // thread t scans its kWirePerThread consecutive entries, then the thread totals are scanned across the block
     int a[kWirePerThread], b[kWirePerThread], ta = 0, tb = 0;
 #pragma unroll
     for (int k = 0; k < kWirePerThread; ++k) {
@@ -195,7 +195,7 @@ wire_decode_kernel(const LenT *__restrict__ len_ids, const LenT *__restrict__ le
         wa += sWarpA[w];
         wb += sWarpB[w];
     }
-    __syncthreads();  // everybody has read the lengths of its eight entries
+    __syncthreads();  // everybody has read the lengths of its entries
 #pragma unroll
     for (int k = 0; k < kWirePerThread; ++k) {
         sIds[tid * kWirePerThread + k] = wa + ia - ta + a[k];
@@ -560,5 +560,4 @@ void wire_slice(const gcrf_wire *w, int k, int64_t *contig, int64_t *gene, int64
     *id = w->s_id[k];
     *byte = w->s_byte[k];
 }
-int64_t wire_stream_bytes(const gcrf_wire *w) { return w->stream_bytes; }
 }  // namespace gcrf
