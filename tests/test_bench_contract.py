@@ -24,3 +24,28 @@ def test_reference_arm_prints_one_contract_line():
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["unit"] == line["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_own_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "3", "--warmup", "3", "--contigs", "600",
+                          "--no-configs", "--no-sharded"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] == 3 and line["gpu_launches"] == 3
+    roof = line["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and e2e["bit_identical_to_device_path"] is True
+    assert 0 < e2e["value"] < line["value"]
+    assert line["parity_max_abs_err_vs_oracle"] <= 1e-5 and line["f64"]["parity_max_abs_err_vs_oracle"] <= 1e-12
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
