@@ -133,8 +133,13 @@ stream_kernel(const WindowedArgs args, const PtrT *__restrict__ gene_ptr, const 
     __shared__ int64_t sNextPb;  // end of the next tile's id range, published by the thread that holds that row pointer
     __shared__ int sShort;
 
-    const int tile_begin = blockIdx.x * tiles_per_cta;
-    const int tile_end = min(num_tiles, tile_begin + tiles_per_cta);
+    // Consecutive tiles per CTA, spread evenly: the first num_tiles % grid CTAs take one more than the others (with
+    // everybody at the rounded-up count the last CTAs of the grid had nothing to do — 26 of config 2's 592 — and the
+    // SMs they would have shared finished no sooner for it)
+    (void)tiles_per_cta;
+    const int tiles_base = num_tiles / (int)gridDim.x, tiles_rem = num_tiles % (int)gridDim.x;
+    const int tile_begin = (int)blockIdx.x * tiles_base + min((int)blockIdx.x, tiles_rem);
+    const int tile_end = tile_begin + tiles_base + ((int)blockIdx.x < tiles_rem ? 1 : 0);
     if (tile_begin >= tile_end) return;
 #ifdef GCRF_TUNING
     const bool prof_on = args.prof != nullptr;
@@ -748,9 +753,8 @@ cudaError_t plan_stream(const WindowedArgs &args, int num_sms, WindowedPlan *pla
     int64_t grid = (int64_t)num_sms * per_sm;
     if (grid > plan->num_tiles) grid = plan->num_tiles;
     if (grid < 1) grid = 1;
-    plan->tiles_per_cta = (int)((plan->num_tiles + grid - 1) / grid);
-    // drop CTAs that would get no tile (the last ones when tiles_per_cta rounds up)
-    plan->grid = (int)((plan->num_tiles + plan->tiles_per_cta - 1) / plan->tiles_per_cta);
+    plan->tiles_per_cta = (int)((plan->num_tiles + grid - 1) / grid);  // the most any CTA gets (see the kernel)
+    plan->grid = (int)grid;
     return cudaSuccess;
 }
 
