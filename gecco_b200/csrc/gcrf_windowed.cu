@@ -169,9 +169,11 @@ windowed_kernel(const WindowedArgs args, const int64_t num_tiles, const int tile
     // delta table: staged once per CTA, reused by every tile it walks
     for (int a = tid; a <= (int)A; a += kThreads) sTab[a] = __ldg(args.model.table + a);
 
-    const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
-    int64_t tile_end = tile_begin + tiles_per_cta;
-    if (tile_end > num_tiles) tile_end = num_tiles;
+    // consecutive tiles per CTA, spread evenly: the first num_tiles % grid CTAs take one more than the others
+    (void)tiles_per_cta;
+    const int64_t tiles_base = num_tiles / gridDim.x, tiles_rem = num_tiles % gridDim.x;
+    const int64_t tile_begin = (int64_t)blockIdx.x * tiles_base + ((int64_t)blockIdx.x < tiles_rem ? (int64_t)blockIdx.x : tiles_rem);
+    const int64_t tile_end = tile_begin + tiles_base + ((int64_t)blockIdx.x < tiles_rem ? 1 : 0);
 
     const int G = (int)csr.G;  // G < 2^31 (checked on the host): tile arithmetic stays 32-bit
     int64_t c_first = 0;
