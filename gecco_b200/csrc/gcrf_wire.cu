@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <thread>
 #include <vector>
@@ -62,37 +63,6 @@ namespace {
 constexpr int kWireThreads = 256, kWirePerThread = 2, kWireChunk = kWireThreads * kWirePerThread;  // genes per block
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-// the code of the header comment, bits LSB first; a gene ends on a byte boundary (flush)
-struct BitWriter {
-    std::vector<uint8_t> &out;
-    unsigned long long acc = 0;
-    int n = 0;
-    void put(uint32_t v, int bits) {  // bits <= 32
-        acc |= (unsigned long long)v << n;
-        n += bits;
-        while (n >= 8) {
-            out.push_back((uint8_t)(acc & 0xff));
-            acc >>= 8;
-            n -= 8;
-        }
-    }
-    void put_delta(uint32_t v, int k) {
-        const uint32_t q = v >> k;
-        if (q < 8) {
-            put((1u << q) - 1u, (int)q + 1);
-            if (k > 0) put(v & ((1u << k) - 1u), k);
-        } else {
-            put(0xffu, 8);
-            put(v, 24);
-        }
-    }
-    void flush() {
-        if (n > 0) out.push_back((uint8_t)(acc & 0xff));
-        acc = 0;
-        n = 0;
-    }
-};
 
 // ---- the decoder: offsets of every gene inside its block (scan), gene_ptr, and the ids themselves.  `sums` holds, per
 // block, the ids and stream bytes in front of it (written by the encoder: no scan over the whole batch on the device).
@@ -276,34 +246,70 @@ cudaError_t launch_wire_decode(const void *len_ids, const void *len_bytes, int32
 namespace {
 
 struct EncodedChunk {
-    std::vector<uint8_t> stream;
+    std::unique_ptr<uint8_t[]> stream;  // not value-initialised: only the bytes written are ever touched
+    size_t stream_size = 0;
     std::vector<uint32_t> n_ids, n_bytes;
+    uint32_t longest = 0;  // largest entry of n_ids / n_bytes
 };
 
+// One range of genes -> their stream bytes and the two length arrays.  Written for speed (the encoder runs once per batch
+// in front of a call that takes a millisecond): rows that arrive sorted — what the packers emit — skip the sort, the
+// code of a delta is assembled in a register and leaves with one 8-byte store.
 template <typename PtrT>
 void encode_range(const PtrT *gene_ptr, const int32_t *attr_idx, int64_t g0, int64_t g1, int32_t A, int k, EncodedChunk *out) {
+    const size_t genes = (size_t)(g1 - g0), ids = (size_t)(gene_ptr[g1] - gene_ptr[g0]);
+    out->n_ids.resize(genes);
+    out->n_bytes.resize(genes);
+    out->stream.reset(new uint8_t[ids * 4 + genes + 16]);  // a code is at most 32 bits, a gene ends with at most one padding byte
+    uint8_t *base = out->stream.get();
+    uint32_t longest = 0;
+    size_t pos = 0;
     std::vector<uint32_t> row;
-    out->n_ids.reserve((size_t)(g1 - g0));
-    out->n_bytes.reserve((size_t)(g1 - g0));
-    out->stream.reserve((size_t)((gene_ptr[g1] - gene_ptr[g0]) * 5 / 4 + (g1 - g0) + 16));
+    const uint32_t kmask = (1u << k) - 1u, top = (uint32_t)A;
     for (int64_t g = g0; g < g1; ++g) {
-        row.clear();
-        for (int64_t p = (int64_t)gene_ptr[g]; p < (int64_t)gene_ptr[g + 1]; ++p) {
-            const uint32_t a = (uint32_t)attr_idx[p];
-            row.push_back(a < (uint32_t)A ? a : (uint32_t)A);  // every unknown id becomes the zero slot A
+        const int64_t p0 = (int64_t)gene_ptr[g], n = (int64_t)gene_ptr[g + 1] - p0;
+        row.resize((size_t)n);
+        bool sorted = true;
+        uint32_t last = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            uint32_t a = (uint32_t)attr_idx[p0 + i];
+            a = a < top ? a : top;  // every unknown id becomes the zero slot A
+            sorted &= a >= last;
+            last = a;
+            row[(size_t)i] = a;
         }
-        std::sort(row.begin(), row.end());
-        const size_t before = out->stream.size();
-        gcrf::BitWriter bw{out->stream};
+        if (!sorted) std::sort(row.begin(), row.end());
+        const size_t start = pos;
+        unsigned long long acc = 0;
+        int nb = 0;  // bits waiting in acc, < 8 between codes
         uint32_t prev = 0;
         for (uint32_t a : row) {
-            bw.put_delta(a - prev, k);
+            const uint32_t v = a - prev, q = v >> k;
             prev = a;
+            uint32_t code;
+            int len;
+            if (q < 8) {  // q ones, a zero, the k low bits
+                code = ((1u << q) - 1u) | ((v & kmask) << (q + 1));
+                len = (int)q + 1 + k;
+            } else {      // eight ones, 24 raw bits
+                code = 0xffu | (v << 8);
+                len = 32;
+            }
+            acc |= (unsigned long long)code << nb;
+            nb += len;
+            memcpy(base + pos, &acc, 8);  // little-endian hosts; the bytes behind the valid ones are rewritten later
+            const int whole = nb >> 3;
+            pos += (size_t)whole;
+            acc >>= 8 * whole;
+            nb &= 7;
         }
-        bw.flush();
-        out->n_ids.push_back((uint32_t)row.size());
-        out->n_bytes.push_back((uint32_t)(out->stream.size() - before));
+        if (nb) base[pos++] = (uint8_t)(acc & 0xff);
+        out->n_ids[(size_t)(g - g0)] = (uint32_t)n;
+        out->n_bytes[(size_t)(g - g0)] = (uint32_t)(pos - start);
+        longest = std::max(longest, std::max((uint32_t)n, (uint32_t)(pos - start)));
     }
+    out->stream_size = pos;
+    out->longest = longest;
 }
 
 thread_local char g_wire_error[256] = "";
@@ -377,9 +383,8 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
     uint32_t longest = 0;
     int64_t stream_bytes = 0;
     for (const auto &c : chunks) {
-        for (uint32_t v : c.n_ids) longest = std::max(longest, v);
-        for (uint32_t v : c.n_bytes) longest = std::max(longest, v);
-        stream_bytes += (int64_t)c.stream.size();
+        longest = std::max(longest, c.longest);
+        stream_bytes += (int64_t)c.stream_size;
     }
     if (longest > 0xFFFF) return wire_fail(GCRF_EUNSUPPORTED, "a gene with more than 65535 ids / stream bytes does not fit the wire format");
     gcrf_wire *w = new (std::nothrow) gcrf_wire();
@@ -390,21 +395,28 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
     w->len_width = lw;
 
     // ids and stream bytes in front of every gene; where every encoded range starts in the stream
-    std::vector<int64_t> gene_id((size_t)G + 1), gene_byte((size_t)G + 1), range_byte(chunks.size() + 1);
+    std::vector<int64_t> gene_id((size_t)G + 1), gene_byte((size_t)G + 1), range_byte(chunks.size() + 1), range_id(chunks.size() + 1);
     {
-        int64_t ids = 0, bytes = 0, gg = 0;
+        int64_t ids = 0, bytes = 0;
         for (size_t t = 0; t < chunks.size(); ++t) {
+            range_id[t] = ids;
             range_byte[t] = bytes;
-            for (size_t k = 0; k < chunks[t].n_ids.size(); ++k, ++gg) {
-                gene_id[gg] = ids;
-                gene_byte[gg] = bytes;
-                ids += chunks[t].n_ids[k];
-                bytes += chunks[t].n_bytes[k];
-            }
+            ids += (int64_t)row(G * (int64_t)(t + 1) / nthreads) - (int64_t)row(G * (int64_t)t / nthreads);
+            bytes += (int64_t)chunks[t].stream_size;
         }
+        range_id[chunks.size()] = ids;
+        range_byte[chunks.size()] = bytes;
         gene_id[G] = ids;
         gene_byte[G] = bytes;
-        range_byte[chunks.size()] = bytes;
+        each_range([&](unsigned t, int64_t g0, int64_t g1) {
+            int64_t i = range_id[t], b = range_byte[t];
+            for (int64_t g = g0; g < g1; ++g) {
+                gene_id[g] = i;
+                gene_byte[g] = b;
+                i += chunks[t].n_ids[(size_t)(g - g0)];
+                b += chunks[t].n_bytes[(size_t)(g - g0)];
+            }
+        });
     }
     // Slice table: cut at contig starts.  A bulk call runs the slices as a three-stage pipeline (copy in / decode +
     // kernels / copy back, gcrf_marginals_windowed_wire); the copy in is the long pole, so what the pipeline adds to it
@@ -463,8 +475,10 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
         }
         w->len_width = -lw;  // negative: block came from malloc
     }
-    memset(w->block, 0, w->total);
+    // fill: head, then every encoded range writes its genes' lengths and its stretch of the stream into the sections of
+    // the slices it overlaps (all threads); the few padding bytes between the parts are zeroed explicitly
     if (G > 0) memcpy(w->block, contig_ptr, (size_t)(C + 1) * 4);
+    memset(w->block + (size_t)(C + 1) * 4, 0, w->off_sums - (size_t)(C + 1) * 4);
     int64_t *sums = reinterpret_cast<int64_t *>(w->block + w->off_sums);
     for (int k = 0; k < w->n_slices; ++k) {
         const int64_t g0 = w->s_gene[k], g1 = w->s_gene[k + 1];
@@ -472,25 +486,46 @@ int gcrf_wire_encode(const int32_t *contig_ptr, const void *gene_ptr, const int3
             sums[2 * (w->s_chunk[k] + j)] = gene_id[g] - gene_id[g0];
             sums[2 * (w->s_chunk[k] + j) + 1] = gene_byte[g] - gene_byte[g0];
         }
+        // padding of the section: behind each length array and behind the stream
+        const size_t part = gcrf::align16((size_t)(g1 - g0) * lw), used = (size_t)(g1 - g0) * lw;
         char *sec = w->block + w->s_off[k];
-        char *sec_bytes = sec + gcrf::align16((size_t)(g1 - g0) * lw);
-        char *sec_stream = sec_bytes + gcrf::align16((size_t)(g1 - g0) * lw);
-        for (int64_t g = g0; g < g1; ++g) {
-            const int64_t ni = gene_id[g + 1] - gene_id[g], nb = gene_byte[g + 1] - gene_byte[g];
-            if (lw == 1) {
-                reinterpret_cast<uint8_t *>(sec)[g - g0] = (uint8_t)ni;
-                reinterpret_cast<uint8_t *>(sec_bytes)[g - g0] = (uint8_t)nb;
-            } else {
-                reinterpret_cast<uint16_t *>(sec)[g - g0] = (uint16_t)ni;
-                reinterpret_cast<uint16_t *>(sec_bytes)[g - g0] = (uint16_t)nb;
-            }
-        }
-        const int64_t b0 = w->s_byte[k], b1 = w->s_byte[k + 1];
-        for (size_t t = 0; t < chunks.size(); ++t) {  // the encoded ranges that overlap this slice's stretch of the stream
-            const int64_t lo = std::max(b0, range_byte[t]), hi = std::min(b1, range_byte[t + 1]);
-            if (hi > lo) memcpy(sec_stream + (lo - b0), chunks[t].stream.data() + (lo - range_byte[t]), (size_t)(hi - lo));
-        }
+        memset(sec + used, 0, part - used);
+        memset(sec + part + used, 0, part - used);
+        const size_t sbytes = (size_t)(w->s_byte[k + 1] - w->s_byte[k]);
+        memset(sec + 2 * part + sbytes, 0, w->s_size[k] - 2 * part - sbytes);
     }
+    {
+        const size_t head_end = w->off_sums + (size_t)n_chunks * 2 * sizeof(int64_t);
+        const size_t first = w->n_slices > 0 ? w->s_off[0] : w->total;
+        if (first > head_end) memset(w->block + head_end, 0, first - head_end);
+    }
+    each_range([&](unsigned t, int64_t ga, int64_t gb) {
+        int k = 0;
+        for (int64_t g = ga; g < gb;) {
+            while (g >= w->s_gene[k + 1]) ++k;  // the slice of gene g
+            const int64_t g0 = w->s_gene[k], g1 = w->s_gene[k + 1], ge = gb < g1 ? gb : g1;
+            const size_t part = gcrf::align16((size_t)(g1 - g0) * lw);
+            char *sec = w->block + w->s_off[k];
+            if (lw == 1) {
+                uint8_t *li = reinterpret_cast<uint8_t *>(sec), *lb = reinterpret_cast<uint8_t *>(sec + part);
+                for (int64_t x = g; x < ge; ++x) {
+                    li[x - g0] = (uint8_t)chunks[t].n_ids[(size_t)(x - ga)];
+                    lb[x - g0] = (uint8_t)chunks[t].n_bytes[(size_t)(x - ga)];
+                }
+            } else {
+                uint16_t *li = reinterpret_cast<uint16_t *>(sec), *lb = reinterpret_cast<uint16_t *>(sec + part);
+                for (int64_t x = g; x < ge; ++x) {
+                    li[x - g0] = (uint16_t)chunks[t].n_ids[(size_t)(x - ga)];
+                    lb[x - g0] = (uint16_t)chunks[t].n_bytes[(size_t)(x - ga)];
+                }
+            }
+            // this range's bytes of genes [g, ge) are contiguous in its stream and in the section
+            const int64_t b_lo = gene_byte[g], b_hi = gene_byte[ge];
+            if (b_hi > b_lo)
+                memcpy(sec + 2 * part + (size_t)(b_lo - w->s_byte[k]), chunks[t].stream.get() + (size_t)(b_lo - range_byte[t]), (size_t)(b_hi - b_lo));
+            g = ge;
+        }
+    });
     *out = w;
     return GCRF_OK;
 }
